@@ -1,0 +1,137 @@
+/*
+ * kmergpu.h -- C ABI of libkmergpu, the B200 (sm_100a) k-mer position index that stands in
+ * for kmer_hasheR's khash/kvec engine.
+ *
+ * This is the drop-in boundary.  The reference's R glue (src/kmer_hash.c) calls plain C
+ * functions of src/kmer_pos.c to build, read and probe the index; a maintainer replaces those
+ * calls by the functions below (see INTEGRATION.md and kmer_hasher_b200/rglue/kmer_hash.c).
+ * Citations are file:line in the reference checkout.
+ *
+ * Conventions
+ *   - every function returns KMG_OK (0) or a negative kmg_status; it never throws, aborts,
+ *     exits or longjmps.  kmg_last_error() gives the message for the calling thread.
+ *   - `seq`, `q` and every output pointer may address pageable host memory, pinned host memory
+ *     (kmg_host_alloc) or device memory of the current device; the library looks the pointer up.
+ *   - sequences are byte strings with an explicit length (the reference scans for the NUL of an
+ *     R CHARSXP, which cannot contain one).
+ *   - all coordinates are 1-based 32-bit ints exactly as the reference returns them.
+ *   - k-mers are ordered by ascending 2-bit key (A<C<T<G, first base most significant); the
+ *     reference orders them by khash bucket, which is not semantic.
+ */
+#ifndef KMERGPU_H
+#define KMERGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMG_MAX_K 32 /* MAX_K, src/kmer_util.h:12 */
+
+typedef enum {
+  KMG_OK = 0,
+  KMG_ERR_ARG = -1,    /* NULL / negative / inconsistent argument                        */
+  KMG_ERR_K = -2,      /* k outside [1,32]            (guard of src/kmer_hash.c:515)      */
+  KMG_ERR_RANGE = -3,  /* a size does not fit the reference's `int` coordinates/extents  */
+  KMG_ERR_CUDA = -4,   /* CUDA runtime error; message carries the CUDA error string       */
+  KMG_ERR_NOMEM = -5,  /* host or device allocation failed                                */
+  KMG_ERR_NODEV = -6   /* no usable sm_100 device                                         */
+} kmg_status;
+
+typedef struct kmg_index kmg_index; /* replaces khash_ptr            (src/kmer_pos.h:43-48)  */
+typedef struct kmg_query kmg_query; /* replaces the kmer_ppos result (src/kmer_pos.h:41)     */
+
+/* ---- library / device -------------------------------------------------------------------- */
+const char *kmg_last_error(void);
+int kmg_version(void);
+int kmg_device_count(int *n);
+int kmg_set_device(int device);          /* device used by this thread's subsequent calls      */
+int kmg_set_stream(void *cuda_stream);   /* run this thread's work on a caller stream (0 = own)  */
+void *kmg_host_alloc(size_t bytes);      /* pinned host memory: full-speed PCIe for in/outputs   */
+void kmg_host_free(void *p);
+
+/* ---- make.kmer.hash ------------------------------------------------------------------------
+ * kmg_build replaces   seq_to_hash(seq, k, hash)              src/kmer_pos.c:66-98
+ *   (and through it    init_kmer / skip_n                     src/kmer_util.c:4-32,
+ *                      kmer_h_insert / kh_put / kv_push       src/kmer_pos.c:36-50)
+ * as called from       make_kmer_h_index                      src/kmer_hash.c:524-527.
+ * It indexes every window the reference would insert (see DESIGN.md "window rule"), position =
+ * 1-based start.  The length guard `length(seq) <= k` (src/kmer_hash.c:519) belongs to the
+ * glue, as in the reference: like the C core, kmg_build accepts any len >= 0.
+ * sort_kmer_pos (src/kmer_pos.c:21-33, do.sort) has no counterpart: lists are always ascending.
+ */
+int kmg_build(const char *seq, int64_t len, int k, kmg_index **out);
+
+/* replaces clear_kmer_h (src/kmer_pos.c:10-19) + the finaliser body (src/kmer_hash.c:56-66).
+ * NULL is accepted. */
+int kmg_free(kmg_index *idx);
+
+/* U = distinct k-mers (kh_size, src/kmer_hash.c:1090), N = indexed windows = rows of `pos`,
+ * P = sum n(n-1)/2 = rows of `pair.pos`.  Any pointer may be NULL. */
+int kmg_sizes(const kmg_index *idx, uint64_t *U, uint64_t *N, uint64_t *P);
+int kmg_index_k(const kmg_index *idx);   /* khash_ptr.k, src/kmer_pos.h:45 */
+
+/* ---- kmer.pos: the four fields of kmer_positions, src/kmer_hash.c:1054-1147 --------------------
+ * Each writes directly into the caller's (R-allocated) buffer; the glue sizes it from kmg_sizes
+ * first, so nothing is staged twice (the reference's kvec + memcpy, :1127-1140).           */
+int kmg_kmers_u64(const kmg_index *idx, uint64_t *keys /* U */);
+/* flag 1: U strings of k upper-case bases + NUL, stride k+1 (kmer_seq, src/kmer_hash.c:123-133) */
+int kmg_kmers_ascii(const kmg_index *idx, char *buf /* U*(k+1) */);
+/* flag 8: list lengths (src/kmer_hash.c:1103-1104) */
+int kmg_counts(const kmg_index *idx, int32_t *counts /* U */);
+/* flag 2: column-major 2 x N = interleaved (i,pos) (src/kmer_hash.c:1109-1112) */
+int kmg_positions(const kmg_index *idx, int32_t *out /* 2N */);
+/* flag 4: column-major 3 x P = interleaved (i,x,y), x<y, x slowest (src/kmer_hash.c:1113-1120).
+ * kmg_pairs_chunk writes rows [first, first+n) so > 2^31-row results can be streamed. */
+int kmg_pairs(const kmg_index *idx, int32_t *out /* 3P */);
+int kmg_pairs_chunk(const kmg_index *idx, uint64_t first, uint64_t n, int32_t *out /* 3n */);
+
+/* ---- seq.kmer.pos --------------------------------------------------------------------------
+ * kmg_query_begin + kmg_query_emit replace seq_kmer_positions  src/kmer_pos.c:110-136
+ *   (kmer_pos lookup :55-60, pair_positions_push :101-108) as called from
+ *   sequence_kmer_positions, src/kmer_hash.c:1166-1170.
+ * begin encodes the query with its own k (never compared with the index's k, as in the
+ * reference), matches it and reports M = number of (i,j) rows; emit writes them: i = 1-based END
+ * of the query k-mer, j = 1-based start in the index, ordered by i then j.  k <= 32 is accepted;
+ * the reference's R-level limit k <= 31 (src/kmer_hash.c:1163) is the glue's business. */
+int kmg_query_begin(const kmg_index *idx, const char *q, int64_t qlen, int k, kmg_query **st,
+                    uint64_t *M);
+int kmg_query_emit(kmg_query *st, int32_t *out /* 2M */);
+int kmg_query_emit_chunk(kmg_query *st, uint64_t first, uint64_t n, int32_t *out /* 2n */);
+int kmg_query_free(kmg_query *st);
+
+/* ---- sharded build (one process per GPU; the exchange itself is the host's NCCL all-to-all) ----
+ * A rank holds bytes [g0,g1) of a global sequence of length L in device memory at d_seq (d_seq[0]
+ * is byte g0) and owns the window starts [s0,s1), g0 <= max(s0-1,0), g1 >= min(L, s1+k-1).
+ * kmg_shard_sample    : n evenly spaced window keys of the shard (for splitter selection).
+ * kmg_shard_partition : encodes the shard's windows and groups the (key,pos) records by owner
+ *                       (owner r holds keys in [splitters[r-1], splitters[r])), keeping sequence
+ *                       order inside each group; pos is global and 1-based.  counts[nparts] is host.
+ * kmg_build_records   : builds an index from device records (e.g. the concatenation, in source
+ *                       rank order, of what the all-to-all delivered).  Input arrays are consumed
+ *                       as scratch but stay owned by the caller.
+ */
+int kmg_shard_sample(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t s0, int64_t s1,
+                     int k, int n, uint64_t *d_samples);
+int kmg_shard_partition(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t s0,
+                        int64_t s1, int k, const uint64_t *splitters /* host, nparts-1 */,
+                        int nparts, uint64_t *d_keys, uint32_t *d_pos, uint64_t *counts);
+int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, int k, kmg_index **out);
+/* match pre-encoded query records (key, i) against the index: rows (i,j) ordered as given */
+int kmg_query_records(const kmg_index *idx, const uint64_t *d_keys, const int32_t *d_i, int64_t n,
+                      kmg_query **st, uint64_t *M);
+
+/* ---- instrumentation (bench.py / profiles) ------------------------------------------------------ */
+int kmg_profile_enable(int on);          /* bracket every kernel with CUDA events               */
+int kmg_profile_reset(void);
+int kmg_profile_count(void);             /* number of distinct kernels seen                     */
+int kmg_profile_get(int i, const char **name, double *total_ms, uint64_t *launches,
+                    double *algo_bytes);
+uint64_t kmg_launch_count(void);         /* kernels launched by this library since load         */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERGPU_H */

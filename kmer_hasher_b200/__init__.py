@@ -1,0 +1,245 @@
+"""kmer_hasher_b200 -- host-side mirror of kmer_hasheR's R API over libkmergpu (B200, sm_100a).
+
+The three functions keep the names, argument meaning, error behaviour and return layouts of the
+reference's R closures (kmer_hash.R:5-28 in the reference checkout):
+
+    make.kmer.hash(seq, k, do.sort) -> make_kmer_hash(seq, k, do_sort)   external pointer -> KmerHash
+    kmer.pos(ex.ptr, opt.flag)      -> kmer_pos(ex_ptr, opt_flag)        list(kmer,pos,pair.pos,count)
+    seq.kmer.pos(ex.ptr, seq, k)    -> seq_kmer_pos(ex_ptr, seq, k)      matrix with columns i, j
+
+R is not installed in the build image, so this Python layer plays the part of kmer_hash.R and the
+SEXP glue (the C glue that a real R session loads is kmer_hasher_b200/rglue/kmer_hash.c).  All
+work happens in the CUDA library; if it cannot be loaded the import of this module fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KmgError, check
+
+__all__ = ["KmerHash", "make_kmer_hash", "kmer_pos", "seq_kmer_pos", "pinned_empty", "KmgError",
+           "OPT_KMER", "OPT_POS", "OPT_PAIRS", "OPT_COUNT"]
+
+# opt.flag bits, src/kmer_hash.c:17 (pos_opt_flags) in the reference
+OPT_KMER, OPT_POS, OPT_PAIRS, OPT_COUNT = 1, 2, 4, 8
+KMER_HASH_TAG = "kmer_hash_250930"      # src/kmer_hash.c:22
+MAX_K = 32                              # src/kmer_util.h:12
+INT_MAX = 2**31 - 1
+
+_L = _lib.load()                        # loud failure when libkmergpu.so is absent
+
+
+def _seq_buffer(seq):
+    """(pointer, length, keepalive) of a str / bytes / uint8 array / torch CUDA tensor."""
+    if isinstance(seq, str):
+        seq = seq.encode("latin-1")
+    if isinstance(seq, (bytes, bytearray)):
+        b = bytes(seq)
+        return C.cast(C.c_char_p(b), C.c_void_p), len(b), b
+    if isinstance(seq, np.ndarray):
+        a = np.ascontiguousarray(seq.view(np.uint8) if seq.dtype != np.uint8 else seq)
+        return C.c_void_p(a.ctypes.data), a.size, a
+    if hasattr(seq, "data_ptr"):        # torch tensor (host or device), uint8
+        t = seq.contiguous()
+        return C.c_void_p(t.data_ptr()), t.numel() * t.element_size(), t
+    raise TypeError("seq must be str, bytes, a uint8 numpy array or a uint8 torch tensor")
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.ptr = _L.kmg_host_alloc(max(int(nbytes), 1))
+        if not self.ptr:
+            raise MemoryError(_L.kmg_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            _L.kmg_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """A numpy array in page-locked host memory (full-speed PCIe target/source)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    owner = _Pinned(n)
+    raw = (C.c_char * max(n, 1)).from_address(owner.ptr)
+    raw._owner = owner
+    return np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def _out_ptr(arr):
+    if arr is None:
+        return None
+    if isinstance(arr, np.ndarray):
+        return C.c_void_p(arr.ctypes.data)
+    return C.c_void_p(arr.data_ptr())   # torch tensor
+
+
+class KmerHash:
+    """What make.kmer.hash returns: an external pointer tagged "kmer_hash_250930" whose finaliser
+    frees the index (make_kmer_h_index / finalise_khash_ptr, src/kmer_hash.c:531-537, 56-66)."""
+
+    tag = KMER_HASH_TAG
+
+    def __init__(self, handle: int, k: int):
+        self._h = handle
+        self.k = k
+
+    @property
+    def sizes(self):
+        U, N, P = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(_L.kmg_sizes(self._handle(), C.byref(U), C.byref(N), C.byref(P)))
+        return U.value, N.value, P.value
+
+    def _handle(self):
+        if not self._h:
+            raise ValueError("external pointer has been cleared")
+        return self._h
+
+    def free(self):
+        if self._h:
+            _L.kmg_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _extract(ex_ptr) -> KmerHash:
+    # extract_khash_ptr, src/kmer_hash.c:491-503
+    if not isinstance(ex_ptr, KmerHash):
+        raise TypeError("ptr_r should be an external pointer")
+    if ex_ptr.tag != KMER_HASH_TAG:
+        raise ValueError("External pointer has incorrect tag")
+    return ex_ptr
+
+
+def make_kmer_hash(seq, k, do_sort=False) -> KmerHash:
+    """make.kmer.hash (kmer_hash.R:5-8 -> make_kmer_h_index, src/kmer_hash.c:506-540).
+
+    `seq` may be a character vector: like the reference, only its first element is used.
+    `do_sort` is accepted and has no effect: position lists are always ascending.
+    """
+    if isinstance(seq, (list, tuple)):
+        if len(seq) < 1:
+            raise ValueError("seq_r should be a character vector of length at least one")
+        seq = seq[0]
+    k = int(k)
+    int(do_sort)
+    if k < 1 or k > MAX_K:
+        raise ValueError("k must be a positive integer less than 1+MAX_K")
+    ptr, n, keep = _seq_buffer(seq)
+    if n <= k:
+        raise ValueError("the length of the sequence must be at least k")
+    h = C.c_void_p()
+    check(_L.kmg_build(ptr, n, k, C.byref(h)))
+    del keep
+    return KmerHash(h.value, k)
+
+
+def kmer_pos(ex_ptr, opt_flag, out: dict | None = None) -> dict:
+    """kmer.pos (kmer_hash.R:10-21 -> kmer_positions, src/kmer_hash.c:1054-1147).
+
+    Returns {"kmer", "pos", "pair.pos", "count"}; fields whose opt.flag bit is off are None.
+    "pos" is an N x 2 int32 array with columns (i, pos) and "pair.pos" a P x 3 array with columns
+    (i, x, y) -- the matrices R holds after kmer.pos's t().  k-mers are ordered by ascending key.
+    `out` may supply preallocated (e.g. pinned) arrays under the same names.
+    """
+    ix = _extract(ex_ptr)
+    opt_flag = int(opt_flag)
+    out = out or {}
+    U, N, P = ix.sizes
+    h = ix._handle()
+    res = {"kmer": None, "pos": None, "pair.pos": None, "count": None}
+    if opt_flag & OPT_KMER:
+        buf = out.get("kmer_buf")
+        if buf is None:
+            buf = np.empty(U * (ix.k + 1), np.uint8)
+        check(_L.kmg_kmers_ascii(h, _out_ptr(buf)))
+        res["kmer"] = np.ascontiguousarray(buf[:U * (ix.k + 1)].reshape(U, ix.k + 1)[:, :ix.k]).view(f"S{ix.k}").ravel()
+    if opt_flag & OPT_POS:
+        if N > INT_MAX:
+            raise OverflowError("pos matrix extent exceeds int")
+        a = out.get("pos")
+        if a is None:
+            a = np.empty((N, 2), np.int32)
+        check(_L.kmg_positions(h, _out_ptr(a)))
+        res["pos"] = a[:N]
+    if opt_flag & OPT_PAIRS:
+        if P > INT_MAX:
+            raise OverflowError(f"pair.pos would need {P} rows; an R matrix extent is int "
+                                "(use kmg_pairs_chunk to stream)")
+        a = out.get("pair.pos")
+        if a is None:
+            a = np.empty((P, 3), np.int32)
+        check(_L.kmg_pairs(h, _out_ptr(a)))
+        res["pair.pos"] = a[:P]
+    if opt_flag & OPT_COUNT:
+        a = out.get("count")
+        if a is None:
+            a = np.empty(U, np.int32)
+        check(_L.kmg_counts(h, _out_ptr(a)))
+        res["count"] = a[:U]
+    return res
+
+
+def kmer_keys(ex_ptr) -> np.ndarray:
+    """The distinct k-mers as uint64 keys, ascending (not part of the R API; used by tests)."""
+    ix = _extract(ex_ptr)
+    U, _, _ = ix.sizes
+    a = np.empty(U, np.uint64)
+    check(_L.kmg_kmers_u64(ix._handle(), _out_ptr(a)))
+    return a
+
+
+def seq_kmer_pos(ex_ptr, seq, k, *, allow_k32: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+    """seq.kmer.pos (kmer_hash.R:23-28 -> sequence_kmer_positions, src/kmer_hash.c:1151-1172).
+
+    M x 2 int32 array, columns (i, j): i = 1-based END of the query k-mer, j = 1-based start in the
+    index; rows ordered by i then j.  The reference's R entry rejects k > 31
+    (src/kmer_hash.c:1163) although its C core handles k = 32; `allow_k32=True` lifts that guard.
+    """
+    ix = _extract(ex_ptr)
+    if isinstance(seq, (list, tuple)):
+        if len(seq) != 1:
+            raise ValueError("seq_r should be a single sequence")
+        seq = seq[0]
+    k = int(k)
+    ptr, n, keep = _seq_buffer(seq)
+    if n <= k or k > (32 if allow_k32 else 31):
+        raise ValueError("the sequence should be longer than k and k should not be longer than 31")
+    st, M = C.c_void_p(), C.c_uint64()
+    check(_L.kmg_query_begin(ix._handle(), ptr, n, k, C.byref(st), C.byref(M)))
+    try:
+        if M.value > INT_MAX:
+            raise OverflowError(f"{M.value} result rows exceed an R matrix extent")
+        a = out if out is not None else np.empty((M.value, 2), np.int32)
+        check(_L.kmg_query_emit(st, _out_ptr(a)))
+    finally:
+        _L.kmg_query_free(st)
+    del keep
+    return a[:M.value]
+
+
+def profile(enable: bool | None = None, reset: bool = False) -> dict:
+    """Per-kernel CUDA-event totals recorded by the library: {name: (ms, launches, algo_bytes)}."""
+    if enable is not None:
+        check(_L.kmg_profile_enable(int(enable)))
+    res = {}
+    for i in range(_L.kmg_profile_count()):
+        name, ms, n, b = C.c_char_p(), C.c_double(), C.c_uint64(), C.c_double()
+        check(_L.kmg_profile_get(i, C.byref(name), C.byref(ms), C.byref(n), C.byref(b)))
+        res[name.value.decode()] = (ms.value, n.value, b.value)
+    if reset:
+        check(_L.kmg_profile_reset())
+    return res
+
+
+def launch_count() -> int:
+    return int(_L.kmg_launch_count())

@@ -1,0 +1,905 @@
+// api.cu -- host side of libkmergpu: the C ABI of include/kmergpu.h over the kernels in
+// sort.cuh / csr.cuh / probe.cuh.  No CPU implementation of any step lives here: without a
+// CUDA device every entry point fails with KMG_ERR_NODEV / KMG_ERR_CUDA.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/kmergpu.h"
+#include "common.cuh"
+#include "csr.cuh"
+#include "lookback.cuh"
+#include "probe.cuh"
+#include "sort.cuh"
+#include "windows.cuh"
+
+using namespace kmg;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      int code_ = (e_ == cudaErrorMemoryAllocation) ? KMG_ERR_NOMEM                                \
+                  : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? KMG_ERR_NODEV \
+                                                                                   : KMG_ERR_CUDA; \
+      return fail(code_, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+    }                                                                                              \
+  } while (0)
+#define TRY(call)            \
+  do {                       \
+    int rc_ = (call);        \
+    if (rc_ != KMG_OK) return rc_; \
+  } while (0)
+
+extern "C" const char *kmg_last_error(void) { return g_err; }
+extern "C" int kmg_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------
+// per-thread execution context
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  bool ready = false;
+  cudaStream_t own = nullptr, copy = nullptr;   // compute stream, second stream for overlapped copies
+  cudaStream_t user = nullptr;
+  bool use_user = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int sms = 148;
+  cudaStream_t stream() const { return use_user ? user : own; }
+};
+static thread_local Ctx g_ctx;
+
+static int ctx_init() {
+  Ctx &c = g_ctx;
+  if (c.ready) {
+    CU(cudaSetDevice(c.device));
+    return KMG_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(KMG_ERR_NODEV, "no CUDA device: %s (libkmergpu has no CPU path)", cudaGetErrorString(e));
+  if (c.device >= n) return fail(KMG_ERR_ARG, "device %d out of range (have %d)", c.device, n);
+  CU(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major < 10)
+    return fail(KMG_ERR_NODEV, "device %d is sm_%d%d; libkmergpu is built for sm_100a only", c.device, prop.major, prop.minor);
+  c.sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+  for (auto &ev : c.ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaMemPool_t pool;
+  CU(cudaDeviceGetDefaultMemPool(&pool, c.device));
+  uint64_t keep = ~uint64_t(0);                  // keep freed blocks: builds reuse them
+  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  c.ready = true;
+  return KMG_OK;
+}
+
+extern "C" int kmg_device_count(int *n) {
+  if (!n) return fail(KMG_ERR_ARG, "n is NULL");
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) { *n = 0; return fail(KMG_ERR_NODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  return KMG_OK;
+}
+extern "C" int kmg_set_device(int device) {
+  if (device < 0) return fail(KMG_ERR_ARG, "negative device");
+  if (g_ctx.ready && g_ctx.device != device) {   // new device: new streams
+    g_ctx = Ctx();
+  }
+  g_ctx.device = device;
+  return ctx_init();
+}
+extern "C" int kmg_set_stream(void *s) {
+  g_ctx.user = (cudaStream_t)s;
+  g_ctx.use_user = true;                          // NULL = the legacy default stream
+  return KMG_OK;
+}
+extern "C" int kmg_unset_stream(void) { g_ctx.use_user = false; return KMG_OK; }
+extern "C" void *kmg_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (ctx_init() != KMG_OK) return nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { fail(KMG_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+extern "C" void kmg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------
+// profiling: optional CUDA-event bracket around every kernel launch
+// ------------------------------------------------------------------------------------------------
+struct ProfEntry { double ms = 0; uint64_t launches = 0; double bytes = 0; };
+struct ProfPending { std::string name; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::map<std::string, ProfEntry> g_prof;
+static std::vector<ProfPending> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_free;
+static uint64_t g_launches = 0;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_free.empty()) { cudaEvent_t e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+static void prof_resolve() {   // caller holds the mutex; pending events must have completed
+  for (auto &p : g_prof_pending) {
+    float ms = 0;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      g_prof[p.name].ms += ms;
+    }
+    g_prof_free.push_back(p.a);
+    g_prof_free.push_back(p.b);
+  }
+  g_prof_pending.clear();
+}
+struct LaunchScope {
+  const char *name;
+  cudaStream_t s;
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool on;
+  LaunchScope(const char *n, cudaStream_t st) : name(n), s(st) {
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    on = g_prof_on;
+    ++g_launches;
+    if (on) { a = prof_event(); b = prof_event(); cudaEventRecord(a, s); }
+  }
+  ~LaunchScope() {
+    if (!on) return;
+    cudaEventRecord(b, s);
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    g_prof[name].launches++;
+    g_prof_pending.push_back({name, a, b});
+  }
+};
+static void prof_bytes(const char *name, double bytes) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (g_prof_on) g_prof[name].bytes += bytes;
+}
+#define LAUNCH(name, stream, ...)                                                              \
+  do {                                                                                         \
+    { LaunchScope ls_(name, stream); __VA_ARGS__; }                                            \
+    cudaError_t le_ = cudaGetLastError();                                                      \
+    if (le_ != cudaSuccess) return fail(KMG_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(le_)); \
+  } while (0)
+
+extern "C" int kmg_profile_enable(int on) { std::lock_guard<std::mutex> g(g_prof_mu); g_prof_on = on != 0; return KMG_OK; }
+extern "C" int kmg_profile_reset(void) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  prof_resolve();
+  g_prof.clear();
+  return KMG_OK;
+}
+extern "C" int kmg_profile_count(void) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  prof_resolve();
+  return (int)g_prof.size();
+}
+extern "C" int kmg_profile_get(int i, const char **name, double *total_ms, uint64_t *launches, double *algo_bytes) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  prof_resolve();
+  if (i < 0 || i >= (int)g_prof.size()) return fail(KMG_ERR_ARG, "profile index out of range");
+  auto it = g_prof.begin();
+  std::advance(it, i);
+  if (name) *name = it->first.c_str();
+  if (total_ms) *total_ms = it->second.ms;
+  if (launches) *launches = it->second.launches;
+  if (algo_bytes) *algo_bytes = it->second.bytes;
+  return KMG_OK;
+}
+extern "C" uint64_t kmg_launch_count(void) { std::lock_guard<std::mutex> g(g_prof_mu); return g_launches; }
+
+// ------------------------------------------------------------------------------------------------
+// memory helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int dalloc(T **p, size_t count, cudaStream_t s) {
+  *p = nullptr;
+  size_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMallocAsync((void **)p, bytes, s);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(KMG_ERR_NOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); }
+  return KMG_OK;
+}
+template <typename T>
+static void dfree(T *&p, cudaStream_t s) {
+  if (p) cudaFreeAsync((void *)p, s);
+  p = nullptr;
+}
+
+enum PtrKind { PK_HOST_PAGEABLE, PK_HOST_PINNED, PK_DEVICE };
+static PtrKind ptr_kind(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return PK_HOST_PAGEABLE; }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return PK_DEVICE;
+  if (a.type == cudaMemoryTypeHost) return PK_HOST_PINNED;
+  return PK_HOST_PAGEABLE;
+}
+
+// The sequence on the device: 16 bytes of front padding (so base[-1] exists), data, zero padding to
+// a multiple of 16 plus one spare group.
+struct DevSeq {
+  uint8_t *buf = nullptr;
+  uint8_t *base = nullptr;   // buf + 16 + lead
+  int64_t len = 0;
+};
+static int upload_seq(const void *src, int64_t len, cudaStream_t s, DevSeq *out) {
+  size_t cap = 16 + (size_t)((len + 15) / 16) * 16 + 16;
+  TRY(dalloc(&out->buf, cap, s));
+  out->base = out->buf + 16;
+  out->len = len;
+  CU(cudaMemsetAsync(out->buf, 0, 16, s));
+  CU(cudaMemsetAsync(out->buf + cap - 32, 0, 32, s));
+  if (len > 0) CU(cudaMemcpyAsync(out->base, src, (size_t)len, cudaMemcpyDefault, s));
+  return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the index
+// ------------------------------------------------------------------------------------------------
+struct kmg_index {
+  int device = 0;
+  int k = 0;
+  uint64_t U = 0, N = 0, P = 0, multi = 0;
+  uint32_t maxc = 0;
+  uint64_t *ukeys = nullptr;    // [U]
+  uint32_t *ustart = nullptr;   // [U+1]
+  uint32_t *pos = nullptr;      // [N]
+  // made on first use
+  std::mutex mu;
+  uint32_t *lut = nullptr;
+  int lut_bits = 0, lut_shift = 0;
+  uint32_t *multi_u = nullptr;
+  uint64_t *pair_off = nullptr;
+};
+struct kmg_query {
+  const kmg_index *idx = nullptr;
+  uint64_t H = 0, M = 0;
+  int32_t *hit_i = nullptr;
+  uint32_t *hit_u = nullptr;
+  uint64_t *row_off = nullptr;
+};
+
+constexpr int SORT_THREADS = 512, SORT_ITEMS = 16, SORT_TILE = SORT_THREADS * SORT_ITEMS;
+constexpr int RLE_THREADS = 256, RLE_ITEMS = 16, RLE_TILE = RLE_THREADS * RLE_ITEMS;
+constexpr int PROBE_THREADS = 256, PROBE_ITEMS = 8, PROBE_TILE = PROBE_THREADS * PROBE_ITEMS;
+constexpr int EMIT_THREADS = 256, EMIT_TILE = EMIT_THREADS * 8;
+constexpr int PIDX_THREADS = 256, PIDX_ITEMS = 8, PIDX_TILE = PIDX_THREADS * PIDX_ITEMS;
+
+template <bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
+static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
+  using S = PassSmem<SORT_THREADS, SORT_ITEMS, FROM_SEQ>;
+  auto kern = scatter_pass_kernel<SORT_THREADS, SORT_ITEMS, FROM_SEQ, BinFn, NextFn, HAS_NEXT>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
+  const int64_t tiles = ceil_div<int64_t>(n_upper, SORT_TILE);
+  if (tiles == 0) return KMG_OK;
+  LAUNCH(name, s, kern<<<(unsigned)tiles, SORT_THREADS, sizeof(S), s>>>(P));
+  return KMG_OK;
+}
+
+// Scratch shared by the sort passes of one build.
+struct SortScratch {
+  uint32_t *small = nullptr;     // hist[(MAX_PASSES+1)][RADIX] | tickets[16] | IndexStats
+  uint64_t *status = nullptr;    // [tiles][RADIX]
+  size_t small_words = 0;
+  uint32_t *hist(int r) const { return small + (size_t)r * RADIX; }
+  uint32_t *ticket(int i) const { return small + (size_t)(MAX_PASSES + 1) * RADIX + i; }
+  IndexStats *stats() const { return reinterpret_cast<IndexStats *>(small + (size_t)(MAX_PASSES + 1) * RADIX + 16); }
+};
+static int scratch_alloc(SortScratch &sc, int64_t n_upper, cudaStream_t s) {
+  sc.small_words = (size_t)(MAX_PASSES + 1) * RADIX + 16 + sizeof(IndexStats) / 4;
+  TRY(dalloc(&sc.small, sc.small_words, s));
+  CU(cudaMemsetAsync(sc.small, 0, sc.small_words * 4, s));
+  const size_t tiles = (size_t)ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, SORT_TILE);
+  TRY(dalloc(&sc.status, tiles * RADIX, s));
+  CU(cudaMemsetAsync(sc.status, 0, tiles * RADIX * sizeof(uint64_t), s));
+  return KMG_OK;
+}
+static void scratch_free(SortScratch &sc, cudaStream_t s) { dfree(sc.small, s); dfree(sc.status, s); }
+
+// Sorted records -> CSR; reads the stats back (one synchronisation) and fills the handle.
+static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, uint32_t *pos_sorted,
+                        int64_t n_upper, cudaStream_t s) {
+  IndexStats *st = sc.stats();
+  uint64_t *ukeys = nullptr;
+  uint32_t *ustart = nullptr;
+  Pair64 *status2 = nullptr;
+  const int64_t tiles = ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, RLE_TILE);
+  TRY(dalloc(&ukeys, (size_t)n_upper, s));
+  TRY(dalloc(&ustart, (size_t)n_upper + 1, s));
+  TRY(dalloc(&status2, (size_t)tiles, s));
+  CU(cudaMemsetAsync(status2, 0, (size_t)tiles * sizeof(Pair64), s));
+  LAUNCH("rle", s, rle_kernel<RLE_THREADS, RLE_ITEMS><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(
+                       keys_sorted, st, ukeys, ustart, status2, sc.ticket(MAX_PASSES + 1)));
+  const unsigned sgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, 256 * 8), g_ctx.sms * 8);
+  LAUNCH("stats", s, stats_kernel<256><<<sgrid, 256, 0, s>>>(ustart, st));
+  IndexStats h;
+  CU(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  ix->N = h.n; ix->U = h.U; ix->P = h.P; ix->multi = h.multi; ix->maxc = h.maxc;
+  dfree(status2, s);
+  // keep exact-size arrays when the over-allocation is large
+  if (h.U * 2 < (uint64_t)n_upper) {
+    uint64_t *uk2; uint32_t *us2;
+    TRY(dalloc(&uk2, (size_t)h.U, s));
+    TRY(dalloc(&us2, (size_t)h.U + 1, s));
+    CU(cudaMemcpyAsync(uk2, ukeys, h.U * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(us2, ustart, (h.U + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    dfree(ukeys, s); dfree(ustart, s);
+    ukeys = uk2; ustart = us2;
+  }
+  ix->ukeys = ukeys; ix->ustart = ustart; ix->pos = pos_sorted;
+  const double N = (double)h.n, U = (double)h.U;
+  prof_bytes("rle", 8 * N + 12 * U);
+  prof_bytes("stats", 4 * U);
+  return KMG_OK;
+}
+
+// LSD passes 1..R-1 over record buffers (pass 0 has already filled buffer A and hist[1]).
+static int sort_tail(SortScratch &sc, int k, int first_pass, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
+                     uint32_t *&pb, int64_t n_upper, cudaStream_t s) {
+  const int R = num_passes(k);
+  for (int r = first_pass; r < R; ++r) {
+    PassParams<DigitBin, DigitBin> P{};
+    P.keys_in = ka; P.pos_in = pa; P.keys_out = kb; P.pos_out = pb;
+    P.hist_cur = sc.hist(r); P.hist_next = sc.hist(r + 1);
+    P.status = sc.status; P.ticket = sc.ticket(r); P.epoch = (uint32_t)(r + 1);
+    P.bin = DigitBin{r * RADIX_BITS}; P.next = DigitBin{(r + 1) * RADIX_BITS};
+    if (r + 1 < R) TRY((launch_pass<false, DigitBin, DigitBin, true>("sort_pass", P, n_upper, s)));
+    else TRY((launch_pass<false, DigitBin, DigitBin, false>("sort_pass_last", P, n_upper, s)));
+    std::swap(ka, kb);
+    std::swap(pa, pb);
+  }
+  return KMG_OK;
+}
+
+static int build_from_view(const SeqView &sv, int k, kmg_index **out) {
+  cudaStream_t s = g_ctx.stream();
+  kmg_index *ix = new (std::nothrow) kmg_index();
+  if (!ix) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  ix->device = g_ctx.device;
+  ix->k = k;
+  const int64_t n_upper = sv.nstarts;
+  if (n_upper <= 0) {                      // shorter than k: an empty index, as the C core gives
+    int rc = dalloc(&ix->ustart, 1, s);
+    if (rc == KMG_OK && cudaMemsetAsync(ix->ustart, 0, 4, s) != cudaSuccess) rc = fail(KMG_ERR_CUDA, "memset failed");
+    if (rc != KMG_OK) { delete ix; return rc; }
+    cudaStreamSynchronize(s);
+    *out = ix;
+    return KMG_OK;
+  }
+  if (n_upper > (int64_t)INT32_MAX) { delete ix; return fail(KMG_ERR_RANGE, "%lld windows exceed the 32-bit coordinates of the reference", (long long)n_upper); }
+
+  SortScratch sc;
+  uint64_t *ka = nullptr, *kb = nullptr;
+  uint32_t *pa = nullptr, *pb = nullptr;
+  int rc = KMG_OK;
+  auto body = [&]() -> int {
+    TRY(scratch_alloc(sc, n_upper, s));
+    TRY(dalloc(&ka, (size_t)n_upper, s));
+    TRY(dalloc(&pa, (size_t)n_upper, s));
+    const int R = num_passes(k);
+    if (R > 1) { TRY(dalloc(&kb, (size_t)n_upper, s)); TRY(dalloc(&pb, (size_t)n_upper, s)); }
+    const int64_t tiles = ceil_div<int64_t>(n_upper, SORT_TILE);
+    const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
+    LAUNCH("hist_seq", s, hist_seq_kernel<SORT_THREADS, SORT_ITEMS, DigitBin><<<hgrid, SORT_THREADS, 0, s>>>(sv, sc.hist(0), DigitBin{0}));
+    LAUNCH("sum_hist", s, sum_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.stats()));
+    {
+      PassParams<DigitBin, DigitBin> P{};
+      P.sv = sv; P.keys_out = ka; P.pos_out = pa;
+      P.hist_cur = sc.hist(0); P.hist_next = sc.hist(1);
+      P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
+      P.bin = DigitBin{0}; P.next = DigitBin{RADIX_BITS};
+      if (R > 1) TRY((launch_pass<true, DigitBin, DigitBin, true>("sort_pass_seq", P, n_upper, s)));
+      else TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq_last", P, n_upper, s)));
+    }
+    TRY(sort_tail(sc, k, 1, ka, pa, kb, pb, n_upper, s));   // result ends in (ka, pa)
+    TRY(finish_index(ix, sc, ka, pa, n_upper, s));
+    pa = nullptr;                                          // now owned by the index
+    const double N = (double)ix->N, L = (double)sv.avail;
+    prof_bytes("hist_seq", L);
+    prof_bytes(R > 1 ? "sort_pass_seq" : "sort_pass_seq_last", L + 12 * N);
+    if (R > 2) prof_bytes("sort_pass", 24 * N * (R - 2));
+    if (R > 1) prof_bytes("sort_pass_last", 24 * N);
+    return KMG_OK;
+  };
+  rc = body();
+  dfree(ka, s); dfree(kb, s); dfree(pa, s); dfree(pb, s);
+  scratch_free(sc, s);
+  if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_free(ix); return rc; }
+  *out = ix;
+  return KMG_OK;
+}
+
+extern "C" int kmg_build(const char *seq, int64_t len, int k, kmg_index **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be a positive integer less than 1+MAX_K");
+  if (len < 0 || (len > 0 && !seq)) return fail(KMG_ERR_ARG, "bad sequence pointer/length");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  DevSeq ds;
+  TRY(upload_seq(seq, len, s, &ds));
+  SeqView sv;
+  sv.base = ds.base; sv.nstarts = len - k + 1 > 0 ? len - k + 1 : 0; sv.avail = len; sv.s0 = 0; sv.L = len; sv.k = k;
+  int rc = build_from_view(sv, k, out);
+  dfree(ds.buf, s);
+  return rc;
+}
+
+extern "C" int kmg_free(kmg_index *ix) {
+  if (!ix) return KMG_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(ix->device);
+  cudaFree(ix->ukeys); cudaFree(ix->ustart); cudaFree(ix->pos);
+  cudaFree(ix->lut); cudaFree(ix->multi_u); cudaFree(ix->pair_off);
+  cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
+  delete ix;
+  return KMG_OK;
+}
+
+extern "C" int kmg_sizes(const kmg_index *ix, uint64_t *U, uint64_t *N, uint64_t *P) {
+  if (!ix) return fail(KMG_ERR_ARG, "index is NULL");
+  if (U) *U = ix->U;
+  if (N) *N = ix->N;
+  if (P) *P = ix->P;
+  return KMG_OK;
+}
+extern "C" int kmg_index_k(const kmg_index *ix) { return ix ? ix->k : fail(KMG_ERR_ARG, "index is NULL"); }
+extern "C" int kmg_index_stats(const kmg_index *ix, uint64_t *multi, uint32_t *max_count) {
+  if (!ix) return fail(KMG_ERR_ARG, "index is NULL");
+  if (multi) *multi = ix->multi;
+  if (max_count) *max_count = ix->maxc;
+  return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// extraction
+// ------------------------------------------------------------------------------------------------
+static int use_index(const kmg_index *ix) {
+  if (!ix) return fail(KMG_ERR_ARG, "index is NULL");
+  TRY(ctx_init());
+  if (ix->device != g_ctx.device) CU(cudaSetDevice(ix->device));
+  return KMG_OK;
+}
+
+// Run `emit(first, rows, d_dst)` over [0,total) rows of `row_bytes` each and land them at `out`.
+// Device destinations are written in place; host destinations go through two device chunks so the
+// copy of chunk c overlaps the kernel of chunk c+1.
+template <class Emit>
+static int stream_rows(uint64_t total, size_t row_bytes, void *out, uint64_t chunk_rows, Emit emit) {
+  if (total == 0) return KMG_OK;
+  cudaStream_t s = g_ctx.stream();
+  if (ptr_kind(out) == PK_DEVICE) {
+    TRY(emit((uint64_t)0, total, out, s));
+    CU(cudaStreamSynchronize(s));
+    return KMG_OK;
+  }
+  chunk_rows = std::min<uint64_t>(chunk_rows, total);
+  char *buf[2] = {nullptr, nullptr};
+  TRY(dalloc(&buf[0], chunk_rows * row_bytes, s));
+  if (total > chunk_rows) TRY(dalloc(&buf[1], chunk_rows * row_bytes, s));
+  cudaStream_t cs = g_ctx.copy;
+  cudaEvent_t *ev = g_ctx.ev;                        // ev[0..1] kernel done, ev[2..3] copy done
+  int rc = KMG_OK;
+  uint64_t done = 0;
+  for (int c = 0; done < total && rc == KMG_OK; ++c, done += chunk_rows) {
+    const int b = c & 1;
+    const uint64_t rows = std::min<uint64_t>(chunk_rows, total - done);
+    if (c >= 2) cudaStreamWaitEvent(s, ev[2 + b], 0);          // buffer b free again
+    rc = emit(done, rows, (void *)buf[b], s);
+    if (rc != KMG_OK) break;
+    cudaEventRecord(ev[b], s);
+    cudaStreamWaitEvent(cs, ev[b], 0);
+    if (cudaMemcpyAsync((char *)out + done * row_bytes, buf[b], rows * row_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+      rc = fail(KMG_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaEventRecord(ev[2 + b], cs);
+  }
+  cudaStreamSynchronize(cs);
+  cudaStreamSynchronize(s);
+  dfree(buf[0], s); dfree(buf[1], s);
+  if (rc == KMG_OK) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(KMG_ERR_CUDA, "extraction failed: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
+constexpr uint64_t CHUNK_BYTES = uint64_t(256) << 20;
+
+extern "C" int kmg_kmers_u64(const kmg_index *ix, uint64_t *keys) {
+  TRY(use_index(ix));
+  if (!keys && ix->U) return fail(KMG_ERR_ARG, "keys is NULL");
+  if (ix->U == 0) return KMG_OK;
+  cudaStream_t s = g_ctx.stream();
+  CU(cudaMemcpyAsync(keys, ix->ukeys, ix->U * sizeof(uint64_t), cudaMemcpyDefault, s));
+  CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+extern "C" int kmg_kmers_ascii(const kmg_index *ix, char *out) {
+  TRY(use_index(ix));
+  if (!out && ix->U) return fail(KMG_ERR_ARG, "buf is NULL");
+  const size_t stride = (size_t)ix->k + 1;
+  const int k = ix->k;
+  const uint64_t *ukeys = ix->ukeys;
+  const int sms = g_ctx.sms;
+  int rc = stream_rows(ix->U, stride, out, CHUNK_BYTES / stride, [=](uint64_t first, uint64_t rows, void *dst, cudaStream_t s) -> int {
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(rows * stride, 256), (uint64_t)sms * 16);
+    LAUNCH("kmers_ascii", s, kmers_ascii_kernel<<<grid, 256, 0, s>>>(ukeys + first, rows, k, (char *)dst));
+    return KMG_OK;
+  });
+  prof_bytes("kmers_ascii", (double)ix->U * (8 + stride));
+  return rc;
+}
+
+extern "C" int kmg_counts(const kmg_index *ix, int32_t *out) {
+  TRY(use_index(ix));
+  if (!out && ix->U) return fail(KMG_ERR_ARG, "counts is NULL");
+  if (ix->maxc > (uint32_t)INT32_MAX) return fail(KMG_ERR_RANGE, "a count exceeds int");
+  const uint32_t *ustart = ix->ustart;
+  const int sms = g_ctx.sms;
+  int rc = stream_rows(ix->U, 4, out, CHUNK_BYTES / 4, [=](uint64_t first, uint64_t rows, void *dst, cudaStream_t s) -> int {
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(rows, 256), (uint64_t)sms * 16);
+    LAUNCH("counts", s, counts_kernel<<<grid, 256, 0, s>>>(ustart + first, rows, (int32_t *)dst));
+    return KMG_OK;
+  });
+  prof_bytes("counts", 8.0 * ix->U);
+  return rc;
+}
+
+extern "C" int kmg_positions(const kmg_index *ix, int32_t *out) {
+  TRY(use_index(ix));
+  if (!out && ix->N) return fail(KMG_ERR_ARG, "out is NULL");
+  const uint32_t *ustart = ix->ustart, *pos = ix->pos;
+  const uint64_t U = ix->U, N = ix->N;
+  int rc = stream_rows(N, 8, out, CHUNK_BYTES / 8, [=](uint64_t first, uint64_t rows, void *dst, cudaStream_t s) -> int {
+    const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
+    LAUNCH("positions", s, positions_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, U, pos, first, rows, (int2 *)dst));
+    return KMG_OK;
+  });
+  prof_bytes("positions", 4.0 * U + 12.0 * N);
+  return rc;
+}
+
+static int ensure_pair_index(kmg_index *ix) {
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->pair_off || ix->multi == 0) return KMG_OK;
+  cudaStream_t s = g_ctx.stream();
+  uint32_t *multi_u = nullptr, *ticket = nullptr;
+  uint64_t *pair_off = nullptr;
+  Pair64 *status = nullptr;
+  const uint64_t tiles = ceil_div<uint64_t>(ix->U, PIDX_TILE);
+  TRY(dalloc(&multi_u, ix->multi, s));
+  TRY(dalloc(&pair_off, ix->multi, s));
+  TRY(dalloc(&status, tiles, s));
+  TRY(dalloc(&ticket, 1, s));
+  CU(cudaMemsetAsync(status, 0, tiles * sizeof(Pair64), s));
+  CU(cudaMemsetAsync(ticket, 0, 4, s));
+  LAUNCH("pair_index", s, pair_index_kernel<PIDX_THREADS, PIDX_ITEMS><<<(unsigned)tiles, PIDX_THREADS, 0, s>>>(
+                              ix->ustart, ix->U, multi_u, pair_off, status, ticket));
+  CU(cudaStreamSynchronize(s));
+  dfree(status, s); dfree(ticket, s);
+  ix->multi_u = multi_u; ix->pair_off = pair_off;
+  prof_bytes("pair_index", 4.0 * ix->U + 12.0 * ix->multi);
+  return KMG_OK;
+}
+
+extern "C" int kmg_pairs_chunk(const kmg_index *cix, uint64_t first, uint64_t n, int32_t *out) {
+  TRY(use_index(cix));
+  kmg_index *ix = const_cast<kmg_index *>(cix);
+  if (first > ix->P || n > ix->P - first) return fail(KMG_ERR_ARG, "pair rows [%llu,+%llu) outside [0,%llu)", (unsigned long long)first, (unsigned long long)n, (unsigned long long)ix->P);
+  if (n == 0) return KMG_OK;
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  TRY(ensure_pair_index(ix));
+  const uint32_t *ustart = ix->ustart, *pos = ix->pos, *multi_u = ix->multi_u;
+  const uint64_t *pair_off = ix->pair_off;
+  const uint64_t n_multi = ix->multi;
+  int rc = stream_rows(n, 12, out, CHUNK_BYTES / 12, [=](uint64_t f, uint64_t rows, void *dst, cudaStream_t s) -> int {
+    const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
+    LAUNCH("pairs", s, pairs_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, pos, multi_u, pair_off, n_multi, first + f, rows, (int32_t *)dst));
+    return KMG_OK;
+  });
+  prof_bytes("pairs", 12.0 * n);
+  return rc;
+}
+extern "C" int kmg_pairs(const kmg_index *ix, int32_t *out) {
+  if (!ix) return fail(KMG_ERR_ARG, "index is NULL");
+  return kmg_pairs_chunk(ix, 0, ix->P, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe
+// ------------------------------------------------------------------------------------------------
+static int ensure_lut(kmg_index *ix) {
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->lut || ix->U == 0) return KMG_OK;
+  cudaStream_t s = g_ctx.stream();
+  int lg = 0;
+  while ((uint64_t(1) << (lg + 1)) <= ix->U) ++lg;           // floor(log2 U)
+  int bits = lg - 1;                                           // ~2-4 keys per bucket
+  bits = std::max(1, std::min(bits, std::min(2 * ix->k, 27)));
+  const uint64_t nb = uint64_t(1) << bits;
+  uint32_t *lut = nullptr;
+  TRY(dalloc(&lut, nb + 1, s));
+  const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(ix->U, 256), (uint64_t)g_ctx.sms * 16);
+  const int shift = 2 * ix->k - bits;
+  LAUNCH("lut", s, lut_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->U, shift, nb, lut));
+  CU(cudaStreamSynchronize(s));
+  ix->lut = lut; ix->lut_bits = bits; ix->lut_shift = shift;
+  prof_bytes("lut", 8.0 * ix->U + 4.0 * nb);
+  return KMG_OK;
+}
+
+static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, const uint64_t *d_keys,
+                        const int32_t *d_i, int64_t n, kmg_query **out, uint64_t *M) {
+  kmg_index *ix = const_cast<kmg_index *>(cix);
+  cudaStream_t s = g_ctx.stream();
+  kmg_query *q = new (std::nothrow) kmg_query();
+  if (!q) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  q->idx = ix;
+  const int64_t total = from_seq ? sv.nstarts : n;
+  if (total <= 0 || ix->U == 0) { *out = q; if (M) *M = 0; return KMG_OK; }
+  int rc = ensure_lut(ix);
+  if (rc != KMG_OK) { delete q; return rc; }
+  QueryStats *qs = nullptr;
+  Pair64 *status = nullptr;
+  uint32_t *ticket = nullptr;
+  auto body = [&]() -> int {
+    const uint64_t tiles = ceil_div<uint64_t>((uint64_t)total, PROBE_TILE);
+    TRY(dalloc(&q->hit_i, (size_t)total, s));
+    TRY(dalloc(&q->hit_u, (size_t)total, s));
+    TRY(dalloc(&q->row_off, (size_t)total, s));
+    TRY(dalloc(&qs, 1, s));
+    TRY(dalloc(&status, tiles, s));
+    TRY(dalloc(&ticket, 1, s));
+    CU(cudaMemsetAsync(qs, 0, sizeof(QueryStats), s));
+    CU(cudaMemsetAsync(status, 0, tiles * sizeof(Pair64), s));
+    CU(cudaMemsetAsync(ticket, 0, 4, s));
+    KeyTable kt{ix->ukeys, ix->ustart, ix->lut, ix->U, uint64_t(1) << ix->lut_bits, ix->lut_shift};
+    if (from_seq)
+      LAUNCH("probe_match", s, probe_match_kernel<PROBE_THREADS, PROBE_ITEMS, true><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+                                   sv, nullptr, nullptr, 0, kt, q->hit_i, q->hit_u, q->row_off, qs, status, ticket));
+    else
+      LAUNCH("probe_match_rec", s, probe_match_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+                                       sv, d_keys, d_i, n, kt, q->hit_i, q->hit_u, q->row_off, qs, status, ticket));
+    QueryStats h;
+    CU(cudaMemcpyAsync(&h, qs, sizeof h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    q->H = h.H; q->M = h.M;
+    return KMG_OK;
+  };
+  rc = body();
+  dfree(qs, s); dfree(status, s); dfree(ticket, s);
+  if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_query_free(q); return rc; }
+  prof_bytes(from_seq ? "probe_match" : "probe_match_rec", (from_seq ? (double)sv.avail : 12.0 * total) + 8.0 * ix->U + 16.0 * q->H);
+  *out = q;
+  if (M) *M = q->M;
+  return KMG_OK;
+}
+
+extern "C" int kmg_query_begin(const kmg_index *ix, const char *qseq, int64_t qlen, int k, kmg_query **st, uint64_t *M) {
+  if (!st) return fail(KMG_ERR_ARG, "st is NULL");
+  *st = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (qlen < 0 || (qlen > 0 && !qseq)) return fail(KMG_ERR_ARG, "bad query pointer/length");
+  if (qlen + 1 > (int64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "query longer than int coordinates");
+  TRY(use_index(ix));
+  cudaStream_t s = g_ctx.stream();
+  DevSeq ds;
+  TRY(upload_seq(qseq, qlen, s, &ds));
+  SeqView sv;
+  sv.base = ds.base; sv.nstarts = qlen - k + 1 > 0 ? qlen - k + 1 : 0; sv.avail = qlen; sv.s0 = 0; sv.L = qlen; sv.k = k;
+  int rc = query_common(ix, true, sv, nullptr, nullptr, 0, st, M);
+  dfree(ds.buf, s);
+  return rc;
+}
+
+extern "C" int kmg_query_records(const kmg_index *ix, const uint64_t *d_keys, const int32_t *d_i, int64_t n, kmg_query **st, uint64_t *M) {
+  if (!st) return fail(KMG_ERR_ARG, "st is NULL");
+  *st = nullptr;
+  if (n < 0 || (n > 0 && (!d_keys || !d_i))) return fail(KMG_ERR_ARG, "bad record arrays");
+  TRY(use_index(ix));
+  SeqView sv{};
+  return query_common(ix, false, sv, d_keys, d_i, n, st, M);
+}
+
+extern "C" int kmg_query_emit_chunk(kmg_query *q, uint64_t first, uint64_t n, int32_t *out) {
+  if (!q) return fail(KMG_ERR_ARG, "query is NULL");
+  TRY(use_index(q->idx));
+  if (first > q->M || n > q->M - first) return fail(KMG_ERR_ARG, "rows outside the result");
+  if (n == 0) return KMG_OK;
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  const kmg_index *ix = q->idx;
+  const int32_t *hit_i = q->hit_i;
+  const uint32_t *hit_u = q->hit_u, *ustart = ix->ustart, *pos = ix->pos;
+  const uint64_t *row_off = q->row_off;
+  const uint64_t H = q->H;
+  int rc = stream_rows(n, 8, out, CHUNK_BYTES / 8, [=](uint64_t f, uint64_t rows, void *dst, cudaStream_t s) -> int {
+    const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
+    LAUNCH("probe_emit", s, probe_emit_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(hit_i, hit_u, row_off, H, ustart, pos, first + f, rows, (int2 *)dst));
+    return KMG_OK;
+  });
+  prof_bytes("probe_emit", 12.0 * n);
+  return rc;
+}
+extern "C" int kmg_query_emit(kmg_query *q, int32_t *out) {
+  if (!q) return fail(KMG_ERR_ARG, "query is NULL");
+  return kmg_query_emit_chunk(q, 0, q->M, out);
+}
+extern "C" int kmg_query_free(kmg_query *q) {
+  if (!q) return KMG_OK;
+  if (q->idx) cudaSetDevice(q->idx->device);
+  cudaFree(q->hit_i); cudaFree(q->hit_u); cudaFree(q->row_off);
+  cudaGetLastError();
+  delete q;
+  return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded build
+// ------------------------------------------------------------------------------------------------
+// The caller's shard [g0,g1) is copied into an aligned, padded buffer whose byte 16 is window start s0.
+static int shard_view(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t s0, int64_t s1, int k,
+                      cudaStream_t s, DevSeq *ds, SeqView *sv) {
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (!(0 <= g0 && g0 <= g1 && g1 <= L && 0 <= s0 && s0 <= s1)) return fail(KMG_ERR_ARG, "inconsistent shard bounds");
+  const int64_t need_lo = s0 > 0 ? s0 - 1 : 0, need_hi = std::min<int64_t>(L, s1 + k - 1);
+  if (s1 > s0 && (g0 > need_lo || g1 < need_hi)) return fail(KMG_ERR_ARG, "shard bytes [%lld,%lld) do not cover [%lld,%lld)", (long long)g0, (long long)g1, (long long)need_lo, (long long)need_hi);
+  const int64_t avail = std::max<int64_t>(0, need_hi - s0);
+  size_t cap = 16 + (size_t)((avail + 15) / 16) * 16 + 16;
+  TRY(dalloc(&ds->buf, cap, s));
+  ds->base = ds->buf + 16;
+  CU(cudaMemsetAsync(ds->buf, 0, 16, s));
+  CU(cudaMemsetAsync(ds->buf + cap - 32, 0, 32, s));
+  if (avail > 0) {
+    const int64_t lead = s0 > 0 ? 1 : 0;        // one byte of left context for rule (iii)
+    CU(cudaMemcpyAsync(ds->base - lead, (const uint8_t *)d_seq + (s0 - lead - g0), (size_t)(avail + lead), cudaMemcpyDefault, s));
+  }
+  int64_t nstarts = std::min<int64_t>(s1, L - k + 1) - s0;
+  sv->base = ds->base; sv->nstarts = nstarts > 0 ? nstarts : 0; sv->avail = avail; sv->s0 = s0; sv->L = L; sv->k = k;
+  return KMG_OK;
+}
+
+__global__ void sample_kernel(const SeqView sv, int n, uint64_t *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // evenly spaced windows; breakers are encoded like any byte (a sample only steers load balance)
+  const int64_t q = sv.nstarts > 0 ? ((int64_t)i * sv.nstarts) / n : 0;
+  uint64_t w = 0;
+  for (int j = 0; j < sv.k; ++j) {
+    const int64_t o = q + j;
+    const uint8_t c = o < sv.avail ? sv.base[o] : 0;
+    w = (w << 2) | ((c >> 1) & 3u);
+  }
+  out[i] = w & key_mask(sv.k);
+}
+
+extern "C" int kmg_shard_sample(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t s0, int64_t s1, int k, int n, uint64_t *d_samples) {
+  if (n <= 0 || !d_samples) return fail(KMG_ERR_ARG, "bad sample request");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  DevSeq ds; SeqView sv;
+  TRY(shard_view(d_seq, g0, g1, L, s0, s1, k, s, &ds, &sv));
+  LAUNCH("sample", s, sample_kernel<<<ceil_div(n, 256), 256, 0, s>>>(sv, n, d_samples));
+  CU(cudaStreamSynchronize(s));
+  dfree(ds.buf, s);
+  return KMG_OK;
+}
+
+extern "C" int kmg_shard_partition(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t s0, int64_t s1, int k,
+                                   const uint64_t *splitters, int nparts, uint64_t *d_keys, uint32_t *d_pos, uint64_t *counts) {
+  if (nparts < 1 || nparts > RADIX || !counts) return fail(KMG_ERR_ARG, "nparts must be in [1,%d]", RADIX);
+  if (nparts > 1 && !splitters) return fail(KMG_ERR_ARG, "splitters is NULL");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  DevSeq ds; SeqView sv;
+  TRY(shard_view(d_seq, g0, g1, L, s0, s1, k, s, &ds, &sv));
+  for (int i = 0; i < nparts; ++i) counts[i] = 0;
+  if (sv.nstarts == 0) { dfree(ds.buf, s); return KMG_OK; }
+  if (!d_keys || !d_pos) { dfree(ds.buf, s); return fail(KMG_ERR_ARG, "record arrays are NULL"); }
+  if (s0 + sv.nstarts > (int64_t)INT32_MAX) { dfree(ds.buf, s); return fail(KMG_ERR_RANGE, "positions exceed int"); }
+  SortScratch sc;
+  uint64_t *d_spl = nullptr;
+  auto body = [&]() -> int {
+    TRY(scratch_alloc(sc, sv.nstarts, s));
+    TRY(dalloc(&d_spl, (size_t)RADIX, s));
+    if (nparts > 1) CU(cudaMemcpyAsync(d_spl, splitters, (size_t)(nparts - 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    OwnerBin ob{d_spl, nparts};
+    const int64_t tiles = ceil_div<int64_t>(sv.nstarts, SORT_TILE);
+    const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
+    LAUNCH("hist_seq_owner", s, hist_seq_kernel<SORT_THREADS, SORT_ITEMS, OwnerBin><<<hgrid, SORT_THREADS, 0, s>>>(sv, sc.hist(0), ob));
+    PassParams<OwnerBin, NoBin> P{};
+    P.sv = sv; P.keys_out = d_keys; P.pos_out = d_pos;
+    P.hist_cur = sc.hist(0); P.hist_next = nullptr;
+    P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
+    P.bin = ob;
+    TRY((launch_pass<true, OwnerBin, NoBin, false>("partition", P, sv.nstarts, s)));
+    std::vector<uint32_t> h(RADIX);
+    CU(cudaMemcpyAsync(h.data(), sc.hist(0), RADIX * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    double tot = 0;
+    for (int i = 0; i < nparts; ++i) { counts[i] = h[i]; tot += h[i]; }
+    prof_bytes("hist_seq_owner", (double)sv.avail);
+    prof_bytes("partition", (double)sv.avail + 12.0 * tot);
+    return KMG_OK;
+  };
+  int rc = body();
+  dfree(d_spl, s); dfree(ds.buf, s);
+  scratch_free(sc, s);
+  if (rc != KMG_OK) cudaStreamSynchronize(s);
+  return rc;
+}
+
+extern "C" int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, int k, kmg_index **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (n < 0 || (n > 0 && (!d_keys || !d_pos))) return fail(KMG_ERR_ARG, "bad record arrays");
+  if (n > (int64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "too many records");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  kmg_index *ix = new (std::nothrow) kmg_index();
+  if (!ix) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  ix->device = g_ctx.device;
+  ix->k = k;
+  if (n == 0) {
+    int rc = dalloc(&ix->ustart, 1, s);
+    if (rc == KMG_OK) cudaMemsetAsync(ix->ustart, 0, 4, s);
+    cudaStreamSynchronize(s);
+    if (rc != KMG_OK) { delete ix; return rc; }
+    *out = ix;
+    return KMG_OK;
+  }
+  SortScratch sc;
+  uint64_t *ka = d_keys, *kb = nullptr;
+  uint32_t *pa = d_pos, *pb = nullptr, *pfinal = nullptr;
+  auto body = [&]() -> int {
+    TRY(scratch_alloc(sc, n, s));
+    TRY(dalloc(&kb, (size_t)n, s));
+    TRY(dalloc(&pb, (size_t)n, s));
+    const unsigned hgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 16), (int64_t)g_ctx.sms * 8);
+    LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, sc.hist(0), DigitBin{0}));
+    LAUNCH("sum_hist", s, sum_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.stats()));
+    TRY(sort_tail(sc, k, 0, ka, pa, kb, pb, n, s));      // result in (ka, pa); may be the caller's arrays
+    // the index must own its positions
+    TRY(dalloc(&pfinal, (size_t)n, s));
+    CU(cudaMemcpyAsync(pfinal, pa, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    TRY(finish_index(ix, sc, ka, pfinal, n, s));
+    pfinal = nullptr;
+    const int R = num_passes(k);
+    prof_bytes("hist_rec", 8.0 * n);
+    if (R > 1) prof_bytes("sort_pass", 24.0 * n * (R - 1));
+    prof_bytes("sort_pass_last", 24.0 * n);
+    return KMG_OK;
+  };
+  int rc = body();
+  // free whichever of the ping-pong buffers are ours
+  if (ka != d_keys) dfree(ka, s);
+  if (kb != d_keys) dfree(kb, s);
+  if (pa != d_pos) dfree(pa, s);
+  if (pb != d_pos) dfree(pb, s);
+  dfree(pfinal, s);
+  scratch_free(sc, s);
+  if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_free(ix); return rc; }
+  *out = ix;
+  return KMG_OK;
+}

@@ -1,0 +1,80 @@
+// common.cuh -- shared device/host helpers of libkmergpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef __CUDACC__
+#error "libkmergpu is CUDA-only: there is no CPU path"
+#endif
+
+namespace kmg {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;   // bins of one sort pass
+constexpr int MAX_PASSES = 8;            // ceil(64 / RADIX_BITS)
+constexpr unsigned FULL = 0xffffffffu;
+
+__host__ __device__ inline uint64_t key_mask(int k) {
+  return k < 32 ? ((uint64_t(1) << (2 * k)) - 1) : ~uint64_t(0);
+}
+__host__ __device__ inline int num_passes(int k) { return (2 * k + RADIX_BITS - 1) / RADIX_BITS; }
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// streaming loads/stores: every array on this path is touched once per kernel
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
+  uint64_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+  uint64_t r;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// warp-level inclusive scans
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(FULL, v, d);
+    if (lane_id() >= (unsigned)d) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_incl_scan64(uint64_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t t = __shfl_up_sync(FULL, v, d);
+    if (lane_id() >= (unsigned)d) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+}  // namespace kmg

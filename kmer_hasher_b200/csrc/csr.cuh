@@ -1,0 +1,309 @@
+// csr.cuh -- sorted (key,pos) records -> CSR index {ukeys[U], ustart[U+1], pos[N]} and the kernels
+// that read it back out in the layouts of kmer_positions (src/kmer_hash.c:1054-1147).
+#pragma once
+#include "common.cuh"
+#include "lookback.cuh"
+
+namespace kmg {
+
+// Device-resident facts about an index; the host reads them once at the end of the build.
+struct IndexStats {
+  uint64_t n;        // records (= rows of `pos`)
+  uint64_t U;        // distinct k-mers
+  uint64_t P;        // sum n(n-1)/2 (= rows of `pair.pos`)
+  uint64_t multi;    // k-mers with more than one position
+  uint32_t maxc;     // longest position list
+  uint32_t pad;
+};
+
+__global__ void sum_hist_kernel(const uint32_t *hist, IndexStats *st) {
+  uint32_t v = hist[threadIdx.x];               // launched with RADIX threads
+  __shared__ uint64_t part[RADIX / 32];
+  uint64_t s = warp_sum64(v);
+  if (lane_id() == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int i = 0; i < RADIX / 32; ++i) t += part[i];
+    st->n = t;
+  }
+}
+
+// ---- run-length pass: one head per distinct key, in order (single pass, chained scan) ----------------
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+rle_kernel(const uint64_t *__restrict__ keys, IndexStats *st, uint64_t *__restrict__ ukeys,
+           uint32_t *__restrict__ ustart, Pair64 *status, uint32_t *ticket) {
+  constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32;
+  __shared__ uint32_t s_tile, s_wsum[WARPS];
+  __shared__ uint64_t s_base;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t n = st->n;
+  const uint64_t q0 = (uint64_t)tile * TILE;
+  if (q0 >= n) {
+    if (n == 0 && tile == 0 && tid == 0) { ustart[0] = 0; st->U = 0; }
+    return;
+  }
+  const uint64_t w0 = q0 + (uint64_t)warp * (32 * ITEMS);
+  uint64_t key[ITEMS];
+  uint32_t heads = 0, before[ITEMS], running = 0;
+  uint64_t carry = 0;                                  // key just before this warp item (lane 0's predecessor)
+  if (lane == 0 && w0 > 0 && w0 < n) carry = ld_stream_u64(keys + w0 - 1);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint64_t idx = w0 + i * 32 + lane;
+    const bool ok = idx < n;
+    key[i] = ok ? ld_stream_u64(keys + idx) : 0;
+    uint64_t prev = __shfl_up_sync(FULL, key[i], 1);
+    if (lane == 0) prev = carry;
+    const bool head = ok && (idx == 0 || key[i] != prev);
+    const unsigned bal = __ballot_sync(FULL, head);
+    before[i] = running + __popc(bal & lanemask_lt());
+    running += __popc(bal);
+    if (head) heads |= 1u << i;
+    carry = __shfl_sync(FULL, key[i], 31);             // lane 0 uses it next round
+  }
+  if (lane == 0) s_wsum[warp] = running;
+  __syncthreads();
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    uint32_t c = s_wsum[w];
+    if (w < (int)warp) wbase += c;
+    total += c;
+  }
+  if (warp == 0) {
+    uint64_t ea, eb;
+    pair_lookback(status, tile, total, 0, ea, eb);
+    if (lane == 0) s_base = ea;
+  }
+  __syncthreads();
+  const uint64_t base = s_base + wbase;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    if ((heads >> i) & 1u) {
+      const uint64_t u = base + before[i];
+      ukeys[u] = key[i];
+      ustart[u] = (uint32_t)(w0 + i * 32 + lane);
+    }
+  }
+  if (q0 + TILE >= n && tid == 0) {                    // the last tile closes the CSR
+    const uint64_t U = s_base + total;
+    ustart[U] = (uint32_t)n;
+    st->U = U;
+  }
+}
+
+// ---- per-k-mer facts: P, multi, max count -------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+stats_kernel(const uint32_t *__restrict__ ustart, IndexStats *st) {
+  const uint64_t U = st->U;
+  uint64_t P = 0, multi = 0;
+  uint32_t maxc = 0;
+  for (uint64_t u = (uint64_t)blockIdx.x * THREADS + threadIdx.x; u < U; u += (uint64_t)gridDim.x * THREADS) {
+    const uint64_t c = ustart[u + 1] - ustart[u];
+    P += c * (c - 1) / 2;
+    multi += c > 1;
+    maxc = max(maxc, (uint32_t)c);
+  }
+  P = warp_sum64(P);
+  multi = warp_sum64(multi);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(FULL, maxc, d));
+  if (lane_id() == 0) {
+    if (P) atomicAdd((unsigned long long *)&st->P, (unsigned long long)P);
+    if (multi) atomicAdd((unsigned long long *)&st->multi, (unsigned long long)multi);
+    if (maxc) atomicMax(&st->maxc, maxc);
+  }
+}
+
+// ---- shared helper: which segment does each of a block's rows fall in? -----------------------------------
+// off[0..cnt) strictly increasing, off[0] <= r0.  For rows r0 .. r0+T the block computes
+// seg[s] = (largest m with off[m] <= r0+s) - m_first, and returns m_first.
+template <int THREADS, int PER, typename OffT>
+__device__ __forceinline__ uint64_t block_segments(const OffT *__restrict__ off, uint64_t cnt, uint64_t r0,
+                                                   uint8_t *s_flag /* THREADS*PER */, uint32_t *s_seg /* THREADS*PER */,
+                                                   uint32_t *s_warp /* THREADS/32 */, uint64_t *s_first) {
+  static_assert(PER == 8, "flags are read as one 64-bit word per thread");
+  constexpr int T = THREADS * PER, WARPS = THREADS / 32;
+  const unsigned tid = threadIdx.x;
+  if (tid == 0) {                                        // largest m with off[m] <= r0
+    uint64_t lo = 0, hi = cnt;                           // invariant: off[lo] <= r0 < off[hi]
+    while (hi - lo > 1) {
+      uint64_t mid = (lo + hi) >> 1;
+      if ((uint64_t)off[mid] <= r0) lo = mid; else hi = mid;
+    }
+    *s_first = lo;
+  }
+  reinterpret_cast<uint64_t *>(s_flag)[tid] = 0;
+  __syncthreads();
+  const uint64_t m_first = *s_first;
+  for (uint64_t m = m_first + 1 + tid; m < cnt; m += THREADS) {
+    const uint64_t o = (uint64_t)off[m];
+    if (o >= r0 + T) break;
+    s_flag[o - r0] = 1;
+  }
+  __syncthreads();
+  const uint64_t f = reinterpret_cast<const uint64_t *>(s_flag)[tid];
+  uint32_t mine = __popcll(f);
+  uint32_t incl = warp_incl_scan(mine);
+  if (lane_id() == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t run = incl - mine;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) if (w < (int)(tid >> 5)) run += s_warp[w];
+  uint32_t out[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { run += (uint32_t)((f >> (8 * j)) & 1u); out[j] = run; }
+  uint4 *dst = reinterpret_cast<uint4 *>(s_seg + tid * PER);
+  dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  __syncthreads();
+  return m_first;
+}
+
+// ---- flag 8: counts ---------------------------------------------------------------------------------------
+__global__ void counts_kernel(const uint32_t *__restrict__ ustart, uint64_t U, int32_t *__restrict__ out) {
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x)
+    out[u] = (int32_t)(ustart[u + 1] - ustart[u]);
+}
+
+// ---- flag 2: interleaved (i,pos), i = 1-based rank of the k-mer ------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+positions_kernel(const uint32_t *__restrict__ ustart, uint64_t U, const uint32_t *__restrict__ pos, uint64_t first,
+                 uint64_t nrows, int2 *__restrict__ out) {
+  constexpr int PER = 8, T = THREADS * PER;
+  __shared__ __align__(16) uint8_t s_flag[T];
+  __shared__ __align__(16) uint32_t s_seg[T];
+  __shared__ uint32_t s_warp[THREADS / 32];
+  __shared__ uint64_t s_first;
+  const uint64_t b0 = (uint64_t)blockIdx.x * T;
+  if (b0 >= nrows) return;
+  const uint64_t r0 = first + b0;
+  const uint64_t u0 = block_segments<THREADS, PER, uint32_t>(ustart, U, r0, s_flag, s_seg, s_warp, &s_first);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const uint32_t s = j * THREADS + threadIdx.x;
+    if (b0 + s < nrows) out[b0 + s] = make_int2((int)(u0 + s_seg[s] + 1), (int)ld_stream_u32(pos + r0 + s));
+  }
+}
+
+// ---- flag 4: pairs ----------------------------------------------------------------------------------------
+// Step 1 (once per index): list the k-mers that have pairs and prefix-sum their pair counts.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+pair_index_kernel(const uint32_t *__restrict__ ustart, uint64_t U, uint32_t *__restrict__ multi_u,
+                  uint64_t *__restrict__ pair_off, Pair64 *status, uint32_t *ticket) {
+  constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32;
+  __shared__ uint32_t s_tile, s_wcnt[WARPS];
+  __shared__ uint64_t s_wsum[WARPS], s_base_cnt, s_base_sum;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t q0 = (uint64_t)tile * TILE;
+  if (q0 >= U) return;
+  // blocked arrangement: thread owns ITEMS consecutive k-mers
+  const uint64_t u0 = q0 + (uint64_t)tid * ITEMS;
+  uint32_t c[ITEMS], cnt = 0;
+  uint64_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint64_t u = u0 + i;
+    c[i] = u < U ? ustart[u + 1] - ustart[u] : 0;
+    if (c[i] > 1) { cnt++; sum += (uint64_t)c[i] * (c[i] - 1) / 2; }
+  }
+  const uint32_t icnt = warp_incl_scan(cnt);
+  const uint64_t isum = warp_incl_scan64(sum);
+  if (lane == 31) { s_wcnt[warp] = icnt; s_wsum[warp] = isum; }
+  __syncthreads();
+  uint64_t bcnt = 0, bsum = 0, tcnt = 0, tsum = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    if (w < (int)warp) { bcnt += s_wcnt[w]; bsum += s_wsum[w]; }
+    tcnt += s_wcnt[w]; tsum += s_wsum[w];
+  }
+  if (warp == 0) {
+    uint64_t ea, eb;
+    pair_lookback(status, tile, tcnt, tsum, ea, eb);
+    if (lane == 0) { s_base_cnt = ea; s_base_sum = eb; }
+  }
+  __syncthreads();
+  uint64_t m = s_base_cnt + bcnt + (icnt - cnt);
+  uint64_t o = s_base_sum + bsum + (isum - sum);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    if (c[i] > 1) {
+      multi_u[m] = (uint32_t)(u0 + i);
+      pair_off[m] = o;
+      ++m;
+      o += (uint64_t)c[i] * (c[i] - 1) / 2;
+    }
+  }
+}
+
+// pair t of a list of n positions, enumerated (0,1),(0,2)..(0,n-1),(1,2).. as the reference's nested
+// loops do (src/kmer_hash.c:1108,1114): rows before first index j: S(j) = j(2n-j-1)/2.
+__device__ __forceinline__ void unrank_pair(uint64_t t, uint64_t n, uint32_t &a, uint32_t &b) {
+  const uint64_t m = 2 * n - 1;
+  const uint64_t D = m * m - 8 * t;                 // exact in 64 bits for n <= 2^31
+  uint64_t r = (uint64_t)sqrt((double)D);
+  while (r * r > D) --r;
+  while ((r + 1) * (r + 1) <= D) ++r;
+  uint64_t j = (m - r) / 2;                         // candidate, then settle exactly
+  if (j > n - 2) j = n - 2;
+  while (j > 0 && j * (2 * n - j - 1) / 2 > t) --j;
+  while (j + 1 <= n - 2 && (j + 1) * (2 * n - j - 2) / 2 <= t) ++j;
+  a = (uint32_t)j;
+  b = (uint32_t)(j + 1 + (t - j * (2 * n - j - 1) / 2));
+}
+
+// Step 2: rows [first, first+nrows) of the pair matrix.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pairs_kernel(const uint32_t *__restrict__ ustart, const uint32_t *__restrict__ pos,
+             const uint32_t *__restrict__ multi_u, const uint64_t *__restrict__ pair_off, uint64_t n_multi,
+             uint64_t first, uint64_t nrows, int32_t *__restrict__ out) {
+  constexpr int PER = 8, T = THREADS * PER;
+  __shared__ __align__(16) uint8_t s_flag[T];
+  __shared__ __align__(16) uint32_t s_seg[T];
+  __shared__ uint32_t s_warp[THREADS / 32];
+  __shared__ uint64_t s_first;
+  const uint64_t b0 = (uint64_t)blockIdx.x * T;
+  if (b0 >= nrows) return;
+  const uint64_t r0 = first + b0;
+  const uint64_t m0 = block_segments<THREADS, PER, uint64_t>(pair_off, n_multi, r0, s_flag, s_seg, s_warp, &s_first);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const uint32_t s = j * THREADS + threadIdx.x;
+    if (b0 + s >= nrows) continue;
+    const uint64_t m = m0 + s_seg[s];
+    const uint32_t u = multi_u[m];
+    const uint32_t a0 = ustart[u], cnt = ustart[u + 1] - a0;
+    uint32_t a, b;
+    unrank_pair(r0 + s - pair_off[m], cnt, a, b);
+    int32_t *row = out + 3 * (b0 + s);
+    row[0] = (int32_t)(u + 1);
+    row[1] = (int32_t)pos[a0 + a];
+    row[2] = (int32_t)pos[a0 + b];
+  }
+}
+
+// ---- flag 1: k-mer strings (kmer_seq, src/kmer_hash.c:123-133; alphabet A,C,T,G, :21) --------------------
+__global__ void kmers_ascii_kernel(const uint64_t *__restrict__ ukeys, uint64_t U, int k, char *__restrict__ out) {
+  const uint64_t total = U * (uint64_t)(k + 1);
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t u = b / (uint64_t)(k + 1);
+    const int j = (int)(b - u * (uint64_t)(k + 1));
+    char c = 0;
+    if (j < k) c = "ACTG"[(ukeys[u] >> (2 * (k - 1 - j))) & 3u];
+    out[b] = c;
+  }
+}
+
+}  // namespace kmg

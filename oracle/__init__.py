@@ -1,0 +1,239 @@
+"""oracle -- TEST INFRASTRUCTURE ONLY (ctypes front ends of the two CPU checkers).
+
+* ``Oracle``    : oracle/_build/libkmer_oracle.so, the plain-C restatement
+                  (oracle/kmer_oracle.c).  Travels to the GPU box.
+* ``Reference`` : oracle/_ref/libkmer_ref.so, the UNMODIFIED reference engine
+                  (/root/reference/src/kmer_pos.c + kmer_util.c) behind
+                  oracle/ref_driver.c.  Built only where /root/reference exists;
+                  the prebuilt .so travels to the GPU box.
+
+Only tests/, bench.py's cpu_baseline / ``--impl reference`` leg and
+``__graft_entry__.smoke()`` may import this package.  Nothing under
+``kmer_hasher_b200/`` does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "_build", "libkmer_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libkmer_ref.so")
+
+_u64p = C.POINTER(C.c_uint64)
+_i32p = C.POINTER(C.c_int32)
+_dblp = C.POINTER(C.c_double)
+
+
+def build(quiet: bool = True) -> None:
+    """Compile the checkers (``make -C oracle``). Building is not using."""
+    subprocess.run(["make", "-C", _HERE], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(ty) if a is not None else None
+
+
+def _as_bytes(seq) -> bytes:
+    if isinstance(seq, str):
+        return seq.encode("latin-1")
+    if isinstance(seq, np.ndarray):
+        return seq.tobytes()
+    return bytes(seq)
+
+
+class OracleIndex:
+    """Canonical CSR index made by the plain-C restatement."""
+
+    def __init__(self, lib, handle, k):
+        self._lib, self._h, self.k = lib, handle, k
+        U, N, P = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.ko_sizes(handle, C.byref(U), C.byref(N), C.byref(P))
+        self.U, self.N, self.P = U.value, N.value, P.value
+
+    def extract(self, flag: int = 15, with_keys: bool = True):
+        """dict(keys, kmer, pos, pair_pos, count) in canonical order."""
+        k = self.k
+        keys = np.empty(self.U, np.uint64) if with_keys else None
+        kmers = np.empty(self.U * (k + 1), np.uint8) if flag & 1 else None
+        pos = np.empty(2 * self.N, np.int32) if flag & 2 else None
+        pairs = np.empty(3 * self.P, np.int32) if flag & 4 else None
+        counts = np.empty(self.U, np.int32) if flag & 8 else None
+        self._lib.ko_extract(self._h, _ptr(keys, _u64p), _ptr(kmers, C.c_char_p), _ptr(pos, _i32p),
+                             _ptr(pairs, _i32p), _ptr(counts, _i32p))
+        return dict(keys=keys, kmer=kmers, pos=pos, pair_pos=pairs, count=counts)
+
+    def query(self, seq, k: int) -> np.ndarray:
+        b = _as_bytes(seq)
+        rows = _i32p()
+        n = self._lib.ko_query(self._h, b, len(b), k, C.byref(rows))
+        out = np.ctypeslib.as_array(rows, shape=(2 * n,)).copy() if n else np.empty(0, np.int32)
+        if n:
+            self._lib.ko_free_buf(rows)
+        return out
+
+    def query_count(self, seq, k: int) -> int:
+        b = _as_bytes(seq)
+        return self._lib.ko_query(self._h, b, len(b), k, None)
+
+    def close(self):
+        if self._h:
+            self._lib.ko_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build()
+        lib = C.CDLL(ORACLE_SO)
+        lib.ko_windows.restype = C.c_int64
+        lib.ko_windows.argtypes = [C.c_char_p, C.c_int64, C.c_int, _u64p, _i32p]
+        lib.ko_build.restype = C.c_void_p
+        lib.ko_build.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        lib.ko_build_from_records.restype = C.c_void_p
+        lib.ko_build_from_records.argtypes = [_u64p, _i32p, C.c_int64, C.c_int]
+        lib.ko_free.argtypes = [C.c_void_p]
+        lib.ko_sizes.argtypes = [C.c_void_p, _u64p, _u64p, _u64p]
+        lib.ko_extract.argtypes = [C.c_void_p, _u64p, C.c_char_p, _i32p, _i32p, _i32p]
+        lib.ko_query.restype = C.c_int64
+        lib.ko_query.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int, C.POINTER(_i32p)]
+        lib.ko_free_buf.argtypes = [C.c_void_p]
+        self.lib = lib
+
+    def windows(self, seq, k: int):
+        """(keys, pos) stream in emission order."""
+        b = _as_bytes(seq)
+        cap = max(len(b) - k + 1, 1)
+        keys = np.empty(cap, np.uint64)
+        pos = np.empty(cap, np.int32)
+        n = self.lib.ko_windows(b, len(b), k, _ptr(keys, _u64p), _ptr(pos, _i32p))
+        return keys[:n].copy(), pos[:n].copy()
+
+    def build(self, seq, k: int, guard: bool = True) -> OracleIndex:
+        b = _as_bytes(seq)
+        err = C.c_int(0)
+        h = self.lib.ko_build(b, len(b), k, int(guard), C.byref(err))
+        if not h:
+            raise ValueError({1: "k must be a positive integer less than 1+MAX_K",
+                              2: "the length of the sequence must be at least k"}[err.value])
+        return OracleIndex(self.lib, h, k)
+
+    def build_from_records(self, keys: np.ndarray, pos: np.ndarray, k: int) -> OracleIndex:
+        keys = np.ascontiguousarray(keys, np.uint64)
+        pos = np.ascontiguousarray(pos, np.int32)
+        h = self.lib.ko_build_from_records(_ptr(keys, _u64p), _ptr(pos, _i32p), len(keys), k)
+        return OracleIndex(self.lib, h, k)
+
+
+class ReferenceIndex:
+    """An index held by the reference's own khash (through ref_driver.c)."""
+
+    def __init__(self, lib, handle, k, seconds):
+        self._lib, self._h, self.k, self.build_seconds = lib, handle, k, seconds
+        U, N, P, B, W = (C.c_uint64() for _ in range(5))
+        lib.ref_sizes(handle, C.byref(U), C.byref(N), C.byref(P), C.byref(B), C.byref(W))
+        self.U, self.N, self.P, self.buckets, self.new_kmers = U.value, N.value, P.value, B.value, W.value
+
+    def _alloc(self, flag, with_keys=True):
+        k = self.k
+        keys = np.empty(self.U, np.uint64) if with_keys else None
+        kmers = np.empty(self.U * (k + 1), np.uint8) if flag & 1 else None
+        pos = np.empty(2 * self.N, np.int32) if flag & 2 else None
+        pairs = np.empty(3 * self.P, np.int32) if flag & 4 else None
+        counts = np.empty(self.U, np.int32) if flag & 8 else None
+        return keys, kmers, pos, pairs, counts
+
+    def extract_raw(self, flag: int = 15):
+        """kmer.pos exactly as R would receive it (khash bucket order) + seconds."""
+        keys, kmers, pos, pairs, counts = self._alloc(flag)
+        sec = C.c_double(0)
+        self._lib.ref_extract_raw(self._h, _ptr(keys, _u64p), _ptr(kmers, C.c_char_p), _ptr(pos, _i32p),
+                                  _ptr(pairs, _i32p), _ptr(counts, _i32p), C.byref(sec))
+        return dict(keys=keys, kmer=kmers, pos=pos, pair_pos=pairs, count=counts, seconds=sec.value)
+
+    def extract(self, flag: int = 15):
+        """kmer.pos in canonical order (k-mers by ascending key, i remapped)."""
+        keys, kmers, pos, pairs, counts = self._alloc(flag)
+        self._lib.ref_extract_canonical(self._h, _ptr(keys, _u64p), _ptr(kmers, C.c_char_p),
+                                        _ptr(pos, _i32p), _ptr(pairs, _i32p), _ptr(counts, _i32p))
+        return dict(keys=keys, kmer=kmers, pos=pos, pair_pos=pairs, count=counts)
+
+    def query(self, seq, k: int, want_rows: bool = True):
+        b = _as_bytes(seq)
+        rows = _i32p()
+        sec = C.c_double(0)
+        n = self._lib.ref_query(self._h, b, k, C.byref(rows), C.byref(sec))
+        self.query_seconds = sec.value
+        out = None
+        if want_rows:
+            out = np.ctypeslib.as_array(rows, shape=(2 * n,)).copy() if n else np.empty(0, np.int32)
+        if rows:
+            self._lib.ref_query_free(rows)
+        return out if want_rows else n
+
+    def close(self):
+        if self._h:
+            self._lib.ref_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Reference:
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            if os.path.isdir("/root/reference/src"):
+                build()
+            else:
+                raise FileNotFoundError(f"{REF_SO} missing and /root/reference absent")
+        lib = C.CDLL(REF_SO)
+        lib.ref_build.restype = C.c_void_p
+        lib.ref_build.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), _dblp]
+        lib.ref_build_core.restype = C.c_void_p
+        lib.ref_build_core.argtypes = [C.c_char_p, C.c_int]
+        lib.ref_free.argtypes = [C.c_void_p]
+        lib.ref_sizes.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p, _u64p]
+        lib.ref_extract_raw.argtypes = [C.c_void_p, _u64p, C.c_char_p, _i32p, _i32p, _i32p, _dblp]
+        lib.ref_extract_canonical.argtypes = [C.c_void_p, _u64p, C.c_char_p, _i32p, _i32p, _i32p]
+        lib.ref_query.restype = C.c_int64
+        lib.ref_query.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(_i32p), _dblp]
+        lib.ref_query_free.argtypes = [_i32p]
+        lib.ref_window_stream.restype = C.c_int64
+        lib.ref_window_stream.argtypes = [C.c_char_p, C.c_int, C.POINTER(_u64p), C.POINTER(_i32p)]
+        lib.ref_free_buf.argtypes = [C.c_void_p]
+        self.lib = lib
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_SO) or os.path.isdir("/root/reference/src")
+
+    def build(self, seq, k: int, do_sort: bool = False, guard: bool = True) -> ReferenceIndex:
+        b = _as_bytes(seq)  # ctypes appends the NUL the reference scans for
+        assert b"\0" not in b
+        if guard:
+            err, sec = C.c_int(0), C.c_double(0)
+            h = self.lib.ref_build(b, k, int(do_sort), C.byref(err), C.byref(sec))
+            if not h:
+                raise ValueError({1: "k must be a positive integer less than 1+MAX_K",
+                                  2: "the length of the sequence must be at least k"}[err.value])
+            return ReferenceIndex(self.lib, h, k, sec.value)
+        return ReferenceIndex(self.lib, self.lib.ref_build_core(b, k), k, 0.0)
+
+    def windows(self, seq, k: int):
+        b = _as_bytes(seq)
+        kp, pp = _u64p(), _i32p()
+        n = self.lib.ref_window_stream(b, k, C.byref(kp), C.byref(pp))
+        keys = np.ctypeslib.as_array(kp, shape=(max(n, 1),))[:n].copy()
+        pos = np.ctypeslib.as_array(pp, shape=(max(n, 1),))[:n].copy()
+        self.lib.ref_free_buf(kp)
+        self.lib.ref_free_buf(pp)
+        return keys, pos

@@ -1,0 +1,53 @@
+"""CPU tests of the drop-in boundary: libkmergpu.so loads, exports every symbol that
+include/kmergpu.h declares, and fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "kmergpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kmg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kmer_hasher_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in kmergpu.h but not exported"
+    # the ctypes table binds exactly the header's surface
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_no_cpu_fallback_and_argument_errors():
+    import kmer_hasher_b200 as kh
+    import torch
+    # argument guards mirror the reference's messages and are raised before any device work
+    with pytest.raises(ValueError, match="less than 1\\+MAX_K"):
+        kh.make_kmer_hash("ACGT" * 20, 33)
+    with pytest.raises(ValueError, match="at least k"):
+        kh.make_kmer_hash("ACGT", 4)
+    with pytest.raises(TypeError, match="external pointer"):
+        kh.kmer_pos("not a pointer", 15)
+    if not torch.cuda.is_available():
+        with pytest.raises(kh.KmgError) as ei:
+            kh.make_kmer_hash("ACGT" * 20, 4)
+        assert ei.value.code in (-4, -6)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under kmer_hasher_b200/ may import, link or execute oracle/."""
+    pkg = os.path.join(ROOT, "kmer_hasher_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".c", ".h", "Makefile")):
+                text = open(os.path.join(dp, fn), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), (dp, fn)
+                assert "libkmer_oracle" not in text and "libkmer_ref" not in text and "kmer_oracle.c" not in text, (dp, fn)

@@ -1,0 +1,97 @@
+"""CPU tests: the plain-C oracle (oracle/kmer_oracle.c) is pinned against
+  (1) golden vectors generated from the unmodified reference engine (tests/golden/), and
+  (2) the reference engine itself (oracle/_ref) on seeded random inputs, when it is available.
+"""
+import numpy as np
+import pytest
+
+from conftest import random_dna, sha
+
+FIELDS = ("keys", "kmer", "count", "pos", "pair_pos")
+
+
+def test_golden_test_fa(oracle, golden, test_fa):
+    assert len(test_fa) == 59940
+    for k, g in golden["test_fa"].items():
+        ix = oracle.build(test_fa, int(k))
+        assert (ix.U, ix.N, ix.P) == (g["U"], g["N"], g["P"])
+        e = ix.extract(15)
+        assert int(e["count"].max()) == g["max_count"]
+        assert int(e["keys"][e["count"].argmax()]) == g["max_key"]
+        assert int((e["count"] > 1).sum()) == g["multi"]
+        for f in FIELDS:
+            assert sha(e[f]) == g["sha_" + f], (k, f)
+        q = ix.query(test_fa, int(k))
+        assert len(q) // 2 == g["self_query_rows"]
+        assert sha(q) == g["sha_self_query"]
+
+
+def test_golden_small(oracle, golden):
+    for c in golden["small"]:
+        k, s = c["k"], c["seq"]
+        wk, wp = oracle.windows(s, k)
+        assert wk.tolist() == c["window_keys"] and wp.tolist() == c["window_pos"], (k, s)
+        ix = oracle.build(s, k, guard=False)
+        assert (ix.U, ix.N, ix.P) == (c["U"], c["N"], c["P"])
+        e = ix.extract(15)
+        assert e["keys"].tolist() == c["keys"]
+        assert e["count"].tolist() == c["count"]
+        assert e["pos"].tolist() == c["pos"]
+        assert e["pair_pos"].tolist() == c["pair_pos"]
+        kmers = [bytes(e["kmer"][i * (k + 1):i * (k + 1) + k]).decode() for i in range(ix.U)]
+        assert kmers == c["kmer"]
+        assert ix.query(s, k).tolist() == c["self_query"]
+
+
+def test_guards(oracle):
+    with pytest.raises(ValueError, match="less than 1\\+MAX_K"):
+        oracle.build("ACGT" * 20, 33)
+    with pytest.raises(ValueError, match="less than 1\\+MAX_K"):
+        oracle.build("ACGT" * 20, 0)
+    with pytest.raises(ValueError, match="at least k"):
+        oracle.build("ACGT", 4)
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 12, 16, 21, 31, 32])
+def test_against_reference_engine(oracle, reference, k):
+    for seed, kw in enumerate([dict(), dict(p_n=0.01), dict(p_n=0.002, p_lower=0.3, p_other=0.01, n_runs=5),
+                               dict(n_runs=30)]):
+        s = random_dna(20000 if k > 3 else 3000, 100 + seed, **kw)
+        a = reference.build(s, k)
+        b = oracle.build(s, k)
+        assert (a.U, a.N, a.P) == (b.U, b.N, b.P)
+        ea, eb = a.extract(15), b.extract(15)
+        for f in FIELDS:
+            assert np.array_equal(ea[f], eb[f]), (k, seed, f)
+        q = random_dna(5000, 900 + seed, **kw)
+        q[1000:3000] = s[500:2500]
+        assert np.array_equal(a.query(q, k), b.query(q, k))
+        wa, wb = reference.windows(s, k), oracle.windows(s, k)
+        assert np.array_equal(wa[0], wb[0]) and np.array_equal(wa[1], wb[1])
+
+
+def test_raw_bucket_order_is_a_permutation(reference):
+    """The reference's own (bucket-order) output equals the canonical one up to the k-mer permutation."""
+    s = random_dna(5000, 7, p_n=0.003)
+    ix = reference.build(s, 6)
+    raw, can = ix.extract_raw(15), ix.extract(15)
+    order = np.argsort(raw["keys"], kind="stable")
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    assert np.array_equal(raw["keys"][order], can["keys"])
+    assert np.array_equal(raw["count"][order], can["count"])
+    pos = raw["pos"].reshape(-1, 2).copy()
+    pos[:, 0] = rank[pos[:, 0] - 1] + 1
+    pos = pos[np.argsort(pos[:, 0], kind="stable")]
+    assert np.array_equal(pos.ravel(), can["pos"])
+    pp = raw["pair_pos"].reshape(-1, 3).copy()
+    pp[:, 0] = rank[pp[:, 0] - 1] + 1
+    pp = pp[np.argsort(pp[:, 0], kind="stable")]
+    assert np.array_equal(pp.ravel(), can["pair_pos"])
+
+
+def test_query_k_independent_of_index_k(oracle, reference):
+    s = random_dna(4000, 11)
+    a, b = reference.build(s, 8), oracle.build(s, 8)
+    for kq in (4, 8, 12):
+        assert np.array_equal(a.query(s[:2000], kq), b.query(s[:2000], kq))

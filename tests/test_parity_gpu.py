@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA library, called through its C ABI (ctypes mirror of the R API), must be
+bit-exact with the oracle on the same inputs -- k-mer set, counts, per-k-mer positions, pair triples,
+query (i,j) rows."""
+import numpy as np
+import pytest
+
+from conftest import random_dna, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kh():
+    import kmer_hasher_b200 as kh
+    return kh
+
+
+def kmers_of(e, U, k):
+    return e["kmer"].reshape(U, k + 1)[:, :k] if e["kmer"].ndim == 1 and e["kmer"].dtype == np.uint8 else e["kmer"]
+
+
+def compare_index(kh, oracle, seq, k, flags=15, guard=True):
+    o = oracle.build(seq, k, guard=guard)
+    g = kh.make_kmer_hash(seq, k)
+    assert g.sizes == (o.U, o.N, o.P), (g.sizes, (o.U, o.N, o.P))
+    eo = o.extract(flags)
+    eg = kh.kmer_pos(g, flags)
+    assert np.array_equal(kh.kmer_keys(g), eo["keys"])
+    if flags & 1:
+        want = np.ascontiguousarray(eo["kmer"].reshape(o.U, k + 1)[:, :k]).view(f"S{k}").ravel()
+        assert np.array_equal(eg["kmer"], want)
+    if flags & 2:
+        assert np.array_equal(eg["pos"].ravel(), eo["pos"])
+    if flags & 4:
+        assert np.array_equal(eg["pair.pos"].ravel(), eo["pair_pos"])
+    if flags & 8:
+        assert np.array_equal(eg["count"], eo["count"])
+    return g, o
+
+
+def test_golden_small(kh, oracle, golden):
+    for c in golden["small"]:
+        k, s = c["k"], c["seq"]
+        if len(s) <= k:      # the R-level guard rejects these; the C ABI itself must agree with the C core
+            import ctypes as C
+            from kmer_hasher_b200 import _lib
+            L = _lib.load()
+            h = C.c_void_p()
+            _lib.check(L.kmg_build(s.encode(), len(s), k, C.byref(h)))
+            U, N, P = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            _lib.check(L.kmg_sizes(h, C.byref(U), C.byref(N), C.byref(P)))
+            assert (U.value, N.value, P.value) == (c["U"], c["N"], c["P"]) == (0, 0, 0)
+            L.kmg_free(h)
+            continue
+        g = kh.make_kmer_hash(s, k)
+        assert g.sizes == (c["U"], c["N"], c["P"]), (k, s)
+        e = kh.kmer_pos(g, 15)
+        assert kh.kmer_keys(g).tolist() == c["keys"]
+        assert [x.decode() for x in e["kmer"]] == c["kmer"]
+        assert e["count"].tolist() == c["count"]
+        assert e["pos"].ravel().tolist() == c["pos"]
+        assert e["pair.pos"].ravel().tolist() == c["pair_pos"]
+        q = kh.seq_kmer_pos(g, s, k, allow_k32=True)
+        assert q.ravel().tolist() == c["self_query"], (k, s)
+
+
+@pytest.mark.parametrize("k", [10, 12, 16, 21, 31, 32])
+def test_golden_test_fa(kh, golden, test_fa, k):
+    """BASELINE config 1: test.fa, make.kmer.hash + kmer.pos(opt.flag=15) (+ self seq.kmer.pos)."""
+    g = golden["test_fa"][str(k)]
+    ix = kh.make_kmer_hash(test_fa, k)
+    assert ix.sizes == (g["U"], g["N"], g["P"])
+    e = kh.kmer_pos(ix, 15)
+    assert sha(kh.kmer_keys(ix)) == g["sha_keys"]
+    assert sha(e["count"]) == g["sha_count"]
+    assert sha(e["pos"]) == g["sha_pos"]
+    assert sha(e["pair.pos"]) == g["sha_pair_pos"]
+    U = g["U"]
+    buf = np.zeros((U, k + 1), np.uint8)
+    buf[:, :k] = e["kmer"].view(np.uint8).reshape(U, k)
+    assert sha(buf) == g["sha_kmer"]
+    q = kh.seq_kmer_pos(ix, test_fa, k, allow_k32=True)
+    assert len(q) == g["self_query_rows"]
+    assert sha(q) == g["sha_self_query"]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 8, 11, 13, 16, 17, 21, 24, 27, 31, 32])
+def test_random_with_breakers(kh, oracle, k):
+    n = 60000 if k >= 8 else 6000       # small k => huge pair counts
+    for seed, kw in enumerate([dict(), dict(p_n=0.01), dict(p_n=0.001, p_lower=0.3, p_other=0.01, n_runs=8),
+                               dict(n_runs=100)]):
+        s = random_dna(n, 1000 * k + seed, **kw)
+        g, o = compare_index(kh, oracle, s, k)
+        q = random_dna(20000 if k >= 8 else 2000, 77 + seed, **kw)
+        m = len(q) // 3
+        q[m:2 * m] = s[100:100 + m]
+        assert np.array_equal(kh.seq_kmer_pos(g, q, k, allow_k32=True).ravel(), o.query(q, k))
+
+
+@pytest.mark.parametrize("n", [33, 64, 100, 8191, 8192, 8193, 8192 + 31, 16384 + 17, 50001])
+def test_tile_boundaries(kh, oracle, n):
+    """Lengths around the 8192-window tile and 16-byte group sizes, breakers at the edges."""
+    k = 32 if n > 40 else 8
+    s = random_dna(n, n)
+    for variant in range(4):
+        t = s.copy()
+        if variant == 1:
+            t[0] = ord("N"); t[-1] = ord("n")
+        elif variant == 2:
+            t[n - k - 1] = ord("N")          # final run of length exactly k: dropped (end-of-string rule)
+        elif variant == 3:
+            t[n - k - 2] = ord("N")          # final run of length k+1: two windows... one kept
+            t[8191 % n] = ord("n")
+        g, o = compare_index(kh, oracle, t, k, flags=2 | 8)
+        assert np.array_equal(kh.seq_kmer_pos(g, t, k, allow_k32=True).ravel(), o.query(t, k))
+
+
+def test_skew_homopolymer_and_microsatellite(kh, oracle):
+    s = np.concatenate([np.full(30000, ord("A"), np.uint8), np.frombuffer(b"CA" * 10000, np.uint8),
+                        np.frombuffer(b"CCCTAA" * 4000, np.uint8), random_dna(20000, 5)])
+    for k in (4, 12, 32):
+        g, o = compare_index(kh, oracle, s, k, flags=1 | 2 | 8)
+        assert g.sizes[2] == o.P
+    # pair rows on a lighter version (pairs grow quadratically)
+    s2 = np.concatenate([np.full(700, ord("A"), np.uint8), np.frombuffer(b"CA" * 600, np.uint8), random_dna(3000, 6)])
+    compare_index(kh, oracle, s2, 6, flags=15)
+
+
+def test_pairs_chunked_equals_whole(kh, oracle, test_fa):
+    import ctypes as C
+    from kmer_hasher_b200 import _lib
+    L = _lib.load()
+    ix = kh.make_kmer_hash(test_fa, 16)
+    U, N, P = ix.sizes
+    whole = kh.kmer_pos(ix, 4)["pair.pos"]
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        first = int(rng.integers(0, P))
+        n = int(min(P - first, rng.integers(1, 3_000_000)))
+        out = np.empty((n, 3), np.int32)
+        _lib.check(L.kmg_pairs_chunk(ix._handle(), first, n, out.ctypes.data))
+        assert np.array_equal(out, whole[first:first + n])
+
+
+def test_query_k_differs_from_index_k(kh, oracle):
+    s = random_dna(30000, 21, p_n=0.002)
+    g = kh.make_kmer_hash(s, 8)
+    o = oracle.build(s, 8)
+    for kq in (4, 8, 12, 31):
+        assert np.array_equal(kh.seq_kmer_pos(g, s[:9000], kq).ravel(), o.query(s[:9000], kq))
+
+
+def test_r_level_guards(kh):
+    s = "ACGT" * 100
+    ix = kh.make_kmer_hash([s, "ignored second element"], 8, do_sort=True)   # first element only; do.sort no-op
+    with pytest.raises(ValueError, match="not be longer than 31"):
+        kh.seq_kmer_pos(ix, s, 32)
+    with pytest.raises(ValueError, match="longer than k"):
+        kh.seq_kmer_pos(ix, "ACGTACGT", 8)
+    with pytest.raises(ValueError, match="single sequence"):
+        kh.seq_kmer_pos(ix, [s, s], 8)
+    r = kh.kmer_pos(ix, 8)
+    assert r["kmer"] is None and r["pos"] is None and r["pair.pos"] is None and r["count"] is not None
+    r = kh.kmer_pos(ix, 0)
+    assert all(v is None for v in r.values())
+
+
+def test_handles_coexist_and_free(kh, oracle):
+    seqs = [random_dna(5000 + 100 * i, 40 + i, p_n=0.001) for i in range(5)]
+    hs = [kh.make_kmer_hash(s, 9 + i) for i, s in enumerate(seqs)]
+    for i in (3, 0, 4, 1, 2):
+        o = oracle.build(seqs[i], 9 + i)
+        assert np.array_equal(kh.kmer_pos(hs[i], 2)["pos"].ravel(), o.extract(2)["pos"])
+    hs[2].free()
+    hs[2].free()                         # finaliser tolerates a cleared pointer
+    with pytest.raises(ValueError):
+        kh.kmer_pos(hs[2], 2)
+
+
+def test_pinned_and_device_buffers(kh, oracle):
+    import torch
+    s = random_dna(100000, 9, p_n=0.001)
+    o = oracle.build(s, 21)
+    # pinned host input + pinned outputs
+    pin = kh.pinned_empty(len(s), np.uint8)
+    pin[:] = s
+    g = kh.make_kmer_hash(pin, 21)
+    out = {"pos": kh.pinned_empty((o.N, 2), np.int32), "count": kh.pinned_empty(o.U, np.int32)}
+    e = kh.kmer_pos(g, 10, out=out)
+    assert np.array_equal(e["pos"].ravel(), o.extract(2)["pos"])
+    assert np.array_equal(e["count"], o.extract(8)["count"])
+    # device-resident input and output
+    d = torch.from_numpy(s).cuda()
+    g2 = kh.make_kmer_hash(d, 21)
+    dout = torch.empty((o.N, 2), dtype=torch.int32, device="cuda")
+    e2 = kh.kmer_pos(g2, 2, out={"pos": dout})
+    torch.cuda.synchronize()
+    assert np.array_equal(dout.cpu().numpy().ravel(), o.extract(2)["pos"])
+
+
+@pytest.mark.parametrize("name,k", [("c2", 32), ("c3", 21), ("c5", 12)])
+def test_scaled_configs(kh, oracle, name, k):
+    """The BASELINE configurations at 1/20 scale, bit-exact against the oracle."""
+    from kmer_hasher_b200 import synth
+    s = {"c2": lambda: synth.config_c2(2_000_000), "c3": lambda: synth.config_c3(4_000_000, tail_k=21),
+         "c5": lambda: synth.generate(1_000_000, 0xC5, tandem=0.01, tandem_unit_max=40, tandem_len_max=3000)}[name]()
+    flags = 15 if name == "c5" else 1 | 2 | 8
+    g, o = compare_index(kh, oracle, s, k, flags=flags)
+    if name == "c3":
+        q = synth.config_c4_query(s, 1_000_000)
+        g32 = kh.make_kmer_hash(s, 32)
+        o32 = oracle.build(s, 32)
+        assert np.array_equal(kh.seq_kmer_pos(g32, q, 32, allow_k32=True).ravel(), o32.query(q, 32))
+
+
+def test_full_size_properties(kh):
+    """40 Mbp (config 2 size), k = 32: size-independent properties of the result."""
+    from kmer_hasher_b200 import synth
+    s = synth.config_c2(40_000_000)
+    k = 32
+    g = kh.make_kmer_hash(s, k)
+    U, N, P = g.sizes
+    assert N == len(s) - k + 1                       # no N in config 2
+    e = kh.kmer_pos(g, 2 | 8)
+    keys = kh.kmer_keys(g)
+    assert np.all(keys[1:] > keys[:-1])              # distinct, ascending
+    cnt = e["count"].astype(np.int64)
+    assert cnt.sum() == N and cnt.min() >= 1
+    assert P == int((cnt * (cnt - 1) // 2).sum())
+    pos = e["pos"]
+    assert np.array_equal(pos[:, 0], np.repeat(np.arange(1, U + 1, dtype=np.int32), cnt))
+    p = pos[:, 1]
+    assert np.array_equal(np.sort(p), np.arange(1, N + 1, dtype=np.int32))   # every window exactly once
+    same = pos[1:, 0] == pos[:-1, 0]
+    assert np.all(p[1:][same] > p[:-1][same])        # ascending inside each k-mer
+    # every position's window re-encodes to its k-mer's key (checked on a sample)
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, N, 200000)
+    code = ((s >> 1) & 3).astype(np.uint64)
+    want = np.zeros(len(idx), np.uint64)
+    starts = p[idx].astype(np.int64) - 1
+    for j in range(k):
+        want = (want << np.uint64(2)) | code[starts + j]
+    assert np.array_equal(want, keys[pos[idx, 0] - 1])
+    # self-probe of a 1 Mbp slice: each hit row must pair equal windows
+    q = s[5_000_000:6_000_000]
+    rows = kh.seq_kmer_pos(g, q, k, allow_k32=True)
+    assert len(rows) >= len(q) - k + 1
+    i0 = rows[:, 0].astype(np.int64) - k             # 0-based start in q
+    j0 = rows[:, 1].astype(np.int64) - 1
+    assert np.all(np.diff(rows[:, 0]) >= 0)
+    sel = rng.integers(0, len(rows), 100000)
+    for j in (0, 7, 15, 31):
+        assert np.array_equal(code[5_000_000 + i0[sel] + j], code[j0[sel] + j])
