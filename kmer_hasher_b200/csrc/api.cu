@@ -446,11 +446,17 @@ extern "C" int kmg_build(const char *seq, int64_t len, int k, kmg_index **out) {
 
 extern "C" int kmg_free(kmg_index *ix) {
   if (!ix) return KMG_OK;
+  // stream-ordered frees keep the pool warm and avoid a device-wide synchronisation; this also
+  // works from a finaliser thread that never used the library (falls back to cudaFree)
   int prev = -1;
   cudaGetDevice(&prev);
   cudaSetDevice(ix->device);
-  cudaFree(ix->ukeys); cudaFree(ix->ustart); cudaFree(ix->pos);
-  cudaFree(ix->lut); cudaFree(ix->multi_u); cudaFree(ix->pair_off);
+  void *ptrs[6] = {ix->ukeys, ix->ustart, ix->pos, ix->lut, ix->multi_u, ix->pair_off};
+  const bool async = g_ctx.ready && g_ctx.device == ix->device;
+  for (void *p : ptrs) {
+    if (!p) continue;
+    if (async) cudaFreeAsync(p, g_ctx.stream()); else cudaFree(p);
+  }
   cudaGetLastError();
   if (prev >= 0) cudaSetDevice(prev);
   delete ix;
@@ -748,7 +754,12 @@ extern "C" int kmg_query_emit(kmg_query *q, int32_t *out) {
 extern "C" int kmg_query_free(kmg_query *q) {
   if (!q) return KMG_OK;
   if (q->idx) cudaSetDevice(q->idx->device);
-  cudaFree(q->hit_i); cudaFree(q->hit_u); cudaFree(q->row_off);
+  void *ptrs[3] = {q->hit_i, q->hit_u, q->row_off};
+  const bool async = g_ctx.ready && q->idx && g_ctx.device == q->idx->device;
+  for (void *p : ptrs) {
+    if (!p) continue;
+    if (async) cudaFreeAsync(p, g_ctx.stream()); else cudaFree(p);
+  }
   cudaGetLastError();
   delete q;
   return KMG_OK;

@@ -1,0 +1,270 @@
+"""Sharded k-mer position index: one process per GPU, torch.distributed for the plumbing.
+
+The path shards with ONE exchange step:
+
+  1. the global sequence is cut into G contiguous shards; a rank needs k-1 bytes of its right
+     neighbour (windows straddling the cut) and one byte of its left neighbour (end-of-string rule),
+     fetched by a halo exchange;
+  2. every rank samples window keys, the samples are all-gathered and G-1 splitters are taken at
+     the quantiles, so key ranges are balanced on repeat-rich input;
+  3. the shard is encoded and its (key,pos) records are grouped by owner (CUDA, libkmergpu
+     kmg_shard_partition: the sort pass with a key-range bin function, order-preserving);
+  4. one all-to-all of the records over NVLink; receivers get the groups in source-rank order, i.e.
+     ascending positions, so the stable local sort keeps every k-mer's list ascending;
+  5. each owner sorts its records and builds its CSR slice (kmg_build_records); the global 1-based
+     k-mer index is local rank + the exclusive prefix of U over ranks.
+
+The device work sits behind a small engine object so the host logic can be exercised on CPU with
+gloo (tests/test_dist_cpu.py plugs in a test double); the product engine is CudaEngine.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class CudaEngine:
+    """Device operations through the C ABI of libkmergpu (no CPU path)."""
+
+    def __init__(self, device: torch.device):
+        from . import _lib
+        self._lib = _lib
+        self.L = _lib.load()
+        self.device = device
+        _lib.check(self.L.kmg_set_device(device.index or 0))
+        _lib.check(self.L.kmg_set_stream(torch.cuda.current_stream(device).cuda_stream))
+
+    def upload(self, a: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=False)
+
+    def sample(self, shard, g0, g1, L, s0, s1, k, n):
+        out = torch.empty(n, dtype=torch.int64, device=self.device)
+        self._lib.check(self.L.kmg_shard_sample(shard.data_ptr(), g0, g1, L, s0, s1, k, n, out.data_ptr()))
+        return out
+
+    def partition(self, shard, g0, g1, L, s0, s1, k, splitters: np.ndarray, nparts: int):
+        cap = max(s1 - s0, 1)
+        keys = torch.empty(cap, dtype=torch.int64, device=self.device)
+        pos = torch.empty(cap, dtype=torch.int32, device=self.device)
+        counts = (C.c_uint64 * nparts)()
+        spl = np.ascontiguousarray(splitters, np.uint64)
+        self._lib.check(self.L.kmg_shard_partition(shard.data_ptr(), g0, g1, L, s0, s1, k,
+                                                   spl.ctypes.data_as(C.POINTER(C.c_uint64)), nparts,
+                                                   keys.data_ptr(), pos.data_ptr(), counts))
+        return keys, pos, [int(c) for c in counts]
+
+    def build_records(self, keys, pos, n, k):
+        from . import KmerHash
+        h = C.c_void_p()
+        self._lib.check(self.L.kmg_build_records(keys.data_ptr(), pos.data_ptr(), n, k, C.byref(h)))
+        return KmerHash(h.value, k)
+
+    def query_records(self, index, keys, coords, n):
+        st, M = C.c_void_p(), C.c_uint64()
+        self._lib.check(self.L.kmg_query_records(index._handle(), keys.data_ptr(), coords.data_ptr(), n,
+                                                 C.byref(st), C.byref(M)))
+        rows = torch.empty((M.value, 2), dtype=torch.int32, device=self.device)
+        try:
+            self._lib.check(self.L.kmg_query_emit(st, rows.data_ptr()))
+        finally:
+            self.L.kmg_query_free(st)
+        return rows
+
+
+def shard_bounds(L: int, world: int, rank: int, k: int):
+    """Window starts [s0,s1) owned by `rank` and the bytes [g0,g1) it must hold."""
+    per = (L + world - 1) // world
+    s0 = min(rank * per, L)
+    s1 = min((rank + 1) * per, L)
+    g0 = max(s0 - 1, 0)
+    g1 = min(L, s1 + k - 1)
+    return s0, s1, g0, g1
+
+
+def exchange_halo(own: torch.Tensor, L: int, k: int, rank: int, world: int, group=None) -> tuple[torch.Tensor, int, int]:
+    """own = this rank's bytes [s0,s1) of the global sequence (device of the backend).  Returns the
+    bytes [g0,g1) after fetching k-1 bytes from the right neighbour(s) and one byte from the left."""
+    s0, s1, g0, g1 = shard_bounds(L, world, rank, k)
+    per = (L + world - 1) // world
+    assert own.numel() == s1 - s0
+    if world == 1:
+        return own, g0, g1
+    # left context: last byte of the left neighbour; right context: first k-1 bytes to the right.
+    # (k-1 <= 31 bytes always come from one neighbour unless shards are shorter than k; handle the
+    # general case by all-gathering fixed-size heads/tails, which is tiny.)
+    head = torch.zeros(k, dtype=torch.uint8, device=own.device)
+    tail = torch.zeros(1, dtype=torch.uint8, device=own.device)
+    n_head = min(k - 1, own.numel())
+    if n_head:
+        head[:n_head] = own[:n_head]
+    if own.numel():
+        tail[0] = own[-1]
+    heads = [torch.empty_like(head) for _ in range(world)]
+    tails = [torch.empty_like(tail) for _ in range(world)]
+    dist.all_gather(heads, head, group=group)
+    dist.all_gather(tails, tail, group=group)
+    parts = []
+    if g0 < s0:
+        parts.append(tails[rank - 1] if per >= 1 else tail)
+    parts.append(own)
+    need = g1 - s1
+    r = rank + 1
+    while need > 0 and r < world:
+        rs0, rs1, _, _ = shard_bounds(L, world, r, k)
+        take = min(need, rs1 - rs0, k - 1)
+        parts.append(heads[r][:take])
+        need -= take
+        r += 1
+    return torch.cat(parts), g0, g1
+
+
+def choose_splitters(samples_all: np.ndarray, world: int) -> np.ndarray:
+    """G-1 splitters at the quantiles of the gathered sample (uint64, ascending)."""
+    s = np.sort(samples_all.astype(np.uint64))
+    if world == 1 or s.size == 0:
+        return np.zeros(0, np.uint64)
+    idx = [(i * s.size) // world for i in range(1, world)]
+    return s[idx].astype(np.uint64)
+
+
+class ShardedIndex:
+    """One rank's slice of a sharded index: the k-mers whose key falls in this rank's range."""
+
+    def __init__(self, local, k, rank, world, U_all, N_all, splitters, engine):
+        self.local, self.k, self.rank, self.world = local, k, rank, world
+        self.U_all, self.N_all, self.splitters, self.engine = U_all, N_all, splitters, engine
+        self.i_offset = int(sum(U_all[:rank]))          # global k-mer index = local + i_offset
+        self.U_total, self.N_total = int(sum(U_all)), int(sum(N_all))
+
+    def free(self):
+        self.local.free()
+
+
+def sharded_build(own_bytes, L: int, k: int, engine, group=None, n_samples: int = 4096) -> ShardedIndex:
+    """Collective: every rank passes its bytes [s0,s1) of the global sequence (numpy uint8 or a tensor
+    on the engine's device).  Returns this rank's ShardedIndex."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    s0, s1, _, _ = shard_bounds(L, world, rank, k)
+    own = own_bytes if isinstance(own_bytes, torch.Tensor) else engine.upload(np.asarray(own_bytes, np.uint8))
+    shard, g0, g1 = exchange_halo(own, L, k, rank, world, group)
+
+    # splitters from an all-gathered key sample
+    if world > 1:
+        smp = engine.sample(shard, g0, g1, L, s0, s1, k, n_samples)
+        gathered = [torch.empty_like(smp) for _ in range(world)]
+        dist.all_gather(gathered, smp, group=group)
+        allsmp = torch.cat(gathered).cpu().numpy().view(np.uint64)
+        splitters = choose_splitters(allsmp, world)
+    else:
+        splitters = np.zeros(0, np.uint64)
+
+    keys, pos, counts = engine.partition(shard, g0, g1, L, s0, s1, k, splitters, world)
+    n_local = sum(counts)
+    if world == 1:
+        local = engine.build_records(keys, pos, n_local, k)
+        U, N, _ = local.sizes
+        return ShardedIndex(local, k, 0, 1, [U], [N], splitters, engine)
+
+    # counts all-gather sizes the receive buffers; then ONE all-to-all per array
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=keys.device)
+    all_counts = [torch.empty_like(send_counts) for _ in range(world)]
+    dist.all_gather(all_counts, send_counts, group=group)
+    matrix = torch.stack(all_counts).cpu().numpy()            # [source][owner]
+    recv_counts = [int(matrix[src][rank]) for src in range(world)]
+    n_recv = sum(recv_counts)
+    rkeys = torch.empty(max(n_recv, 1), dtype=torch.int64, device=keys.device)
+    rpos = torch.empty(max(n_recv, 1), dtype=torch.int32, device=keys.device)
+    dist.all_to_all_single(rkeys[:n_recv], keys[:n_local], recv_counts, counts, group=group)
+    dist.all_to_all_single(rpos[:n_recv], pos[:n_local], recv_counts, counts, group=group)
+    del keys, pos
+    local = engine.build_records(rkeys, rpos, n_recv, k)
+    U, N, _ = local.sizes
+    sizes = torch.tensor([U, N], dtype=torch.int64, device=rkeys.device)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    return ShardedIndex(local, k, rank, world, all_sizes[:, 0].tolist(), all_sizes[:, 1].tolist(), splitters, engine)
+
+
+def sharded_query(index: ShardedIndex, own_query_bytes, Lq: int, k: int, group=None) -> torch.Tensor:
+    """Collective seq.kmer.pos against a sharded index: every rank passes its slice of the query.
+    Query windows are routed to the key's owner exactly like index records; each owner returns its
+    (i,j) rows ordered by i then j (rows of one i live on one owner, so merging the owners' outputs by i
+    reproduces the reference order)."""
+    engine = index.engine
+    world, rank = index.world, index.rank
+    s0, s1, _, _ = shard_bounds(Lq, world, rank, k)
+    own = own_query_bytes if isinstance(own_query_bytes, torch.Tensor) else engine.upload(np.asarray(own_query_bytes, np.uint8))
+    shard, g0, g1 = exchange_halo(own, Lq, k, rank, world, group)
+    keys, pos, counts = engine.partition(shard, g0, g1, Lq, s0, s1, k, index.splitters, world)
+    n_local = sum(counts)
+    coords = pos[:n_local] + (k - 1)                       # 1-based start -> 1-based END (src/kmer_pos.c:127)
+    if world == 1:
+        return engine.query_records(index.local, keys, coords, n_local)
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=keys.device)
+    all_counts = [torch.empty_like(send_counts) for _ in range(world)]
+    dist.all_gather(all_counts, send_counts, group=group)
+    matrix = torch.stack(all_counts).cpu().numpy()
+    recv_counts = [int(matrix[src][rank]) for src in range(world)]
+    n_recv = sum(recv_counts)
+    rkeys = torch.empty(max(n_recv, 1), dtype=torch.int64, device=keys.device)
+    rco = torch.empty(max(n_recv, 1), dtype=torch.int32, device=keys.device)
+    dist.all_to_all_single(rkeys[:n_recv], keys[:n_local], recv_counts, counts, group=group)
+    dist.all_to_all_single(rco[:n_recv], coords.contiguous(), recv_counts, counts, group=group)
+    return engine.query_records(index.local, rkeys, rco, n_recv)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bench.py's N>1 leg
+# ---------------------------------------------------------------------------------------------------------
+def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
+    import kmer_hasher_b200 as kh
+    from . import synth
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    engine = CudaEngine(dev)
+    # weak scaling: every rank owns L bases of an (N x L)-base sequence; shards are independent draws
+    Ltot = L * world
+    if Ltot > 2**31 - 2:
+        raise SystemExit("global sequence exceeds the reference's int coordinates")
+    seed_seq = synth.generate(L, 0xC2 + 7919 * rank, repeat=0.30, tandem=0.10, homo=0.05, lower=0.20)
+    own = engine.upload(seed_seq)
+
+    def step():
+        ix = sharded_build(own, Ltot, k, engine)
+        U, N, _ = ix.local.sizes
+        pos = torch.empty((max(N, 1), 2), dtype=torch.int32, device=dev)
+        cnt = torch.empty(max(U, 1), dtype=torch.int32, device=dev)
+        kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos, "count": cnt})
+        tot = ix.N_total
+        ix.free()
+        return tot
+
+    for _ in range(warm):
+        step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = kh.launch_count()
+    a.record()
+    for _ in range(steps):
+        ntot = step()
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = kh.launch_count() - l0
+    if rank != 0:
+        return None
+    return {"metric": "kmers_indexed_per_s", "value": ntot / (ms * 1e-3), "unit": "k-mers/s", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": w["name"] + f" per GPU; {world} shards of one {Ltot}-base sequence, records routed to "
+                       "key-range owners by NCCL all-to-all", "k": k, "bases": Ltot, "kmers": int(ntot),
+                       "l2": "inputs_exceed_l2"},
+            "e2e": None, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None}

@@ -242,13 +242,83 @@ def test_full_size_properties(kh):
     for j in range(k):
         want = (want << np.uint64(2)) | code[starts + j]
     assert np.array_equal(want, keys[pos[idx, 0] - 1])
-    # self-probe of a 1 Mbp slice: each hit row must pair equal windows
-    q = s[5_000_000:6_000_000]
-    rows = kh.seq_kmer_pos(g, q, k, allow_k32=True)
-    assert len(rows) >= len(q) - k + 1
-    i0 = rows[:, 0].astype(np.int64) - k             # 0-based start in q
-    j0 = rows[:, 1].astype(np.int64) - 1
-    assert np.all(np.diff(rows[:, 0]) >= 0)
-    sel = rng.integers(0, len(rows), 100000)
-    for j in (0, 7, 15, 31):
-        assert np.array_equal(code[5_000_000 + i0[sel] + j], code[j0[sel] + j])
+    # self-probe of a 1 Mbp slice.  Repeats make the full result astronomically large (an R matrix could
+    # not hold it), so count it, then stream and check two windows of rows through the chunk API.
+    import ctypes as C
+    from kmer_hasher_b200 import _lib
+    L = _lib.load()
+    q = np.ascontiguousarray(s[5_000_000:6_000_000])
+    st, M = C.c_void_p(), C.c_uint64()
+    _lib.check(L.kmg_query_begin(g._handle(), q.ctypes.data, len(q), k, C.byref(st), C.byref(M)))
+    assert M.value >= len(q) - k + 1
+    for first in (0, M.value // 2):
+        n = min(2_000_000, M.value - first)
+        rows = np.empty((n, 2), np.int32)
+        _lib.check(L.kmg_query_emit_chunk(st, first, n, rows.ctypes.data))
+        i0 = rows[:, 0].astype(np.int64) - k             # 0-based start in q
+        j0 = rows[:, 1].astype(np.int64) - 1
+        assert np.all(np.diff(rows[:, 0]) >= 0)
+        same = rows[1:, 0] == rows[:-1, 0]
+        assert np.all(rows[1:, 1][same] > rows[:-1, 1][same])
+        sel = rng.integers(0, n, 100000)
+        for j in (0, 7, 15, 31):
+            assert np.array_equal(code[5_000_000 + i0[sel] + j], code[j0[sel] + j])
+    L.kmg_query_free(st)
+
+
+@pytest.mark.parametrize("world,k", [(1, 16), (2, 32), (4, 21), (8, 12)])
+def test_sharded_engine_single_process(kh, oracle, world, k):
+    """The CUDA side of the sharded build (kmg_shard_sample / kmg_shard_partition / kmg_build_records /
+    kmg_query_records), with the ranks played one after another on one GPU: shard -> partition by
+    splitters -> concatenate per owner in source order -> per-owner index == slices of the whole index."""
+    import torch
+    from kmer_hasher_b200 import dist as kdist, synth
+    eng = kdist.CudaEngine(torch.device("cuda", 0))
+    seq = synth.config_c3(600_000, tail_k=k)
+    L = len(seq)
+    per = (L + world - 1) // world
+    seq[per - 2:per + 1] = np.frombuffer(b"nAC", np.uint8)          # breaker at the first cut
+    whole = oracle.build(seq, k)
+    want = whole.extract(2 | 8)
+    shards, samples = [], []
+    for r in range(world):
+        s0, s1, g0, g1 = kdist.shard_bounds(L, world, r, k)
+        t = eng.upload(seq[g0:g1])
+        shards.append((t, g0, g1, s0, s1))
+        samples.append(eng.sample(t, g0, g1, L, s0, s1, k, 512).cpu().numpy().view(np.uint64))
+    spl = kdist.choose_splitters(np.concatenate(samples), world)
+    per_owner_k = [[] for _ in range(world)]
+    per_owner_p = [[] for _ in range(world)]
+    for (t, g0, g1, s0, s1) in shards:
+        keys, pos, counts = eng.partition(t, g0, g1, L, s0, s1, k, spl, world)
+        assert sum(counts) <= s1 - s0
+        off = 0
+        for o, c in enumerate(counts):
+            per_owner_k[o].append(keys[off:off + c])
+            per_owner_p[o].append(pos[off:off + c])
+            off += c
+    got_keys, got_cnt, got_pos, offs = [], [], [], 0
+    q = synth.config_c4_query(seq, 100_000)
+    qo = whole.query(q, k)
+    qkeys, qpos = oracle.windows(q, k)
+    rows_all = []
+    for o in range(world):
+        kk = torch.cat(per_owner_k[o]); pp = torch.cat(per_owner_p[o])
+        ix = eng.build_records(kk.clone(), pp.clone(), kk.numel(), k)
+        U, N, _ = ix.sizes
+        e = kh.kmer_pos(ix, 2 | 8)
+        got_keys.append(kh.kmer_keys(ix)); got_cnt.append(e["count"])
+        p = e["pos"].copy(); p[:, 0] += offs; got_pos.append(p)
+        offs += U
+        # routed probe: this owner's share of the query windows
+        own = np.searchsorted(spl, qkeys, side="right") == o if world > 1 else np.ones(len(qkeys), bool)
+        dk = torch.from_numpy(qkeys[own].view(np.int64).copy()).cuda()
+        di = torch.from_numpy((qpos[own] + (k - 1)).astype(np.int32)).cuda()
+        rows_all.append(eng.query_records(ix, dk, di, dk.numel()).cpu().numpy())
+        ix.free()
+    assert np.array_equal(np.concatenate(got_keys), want["keys"])
+    assert np.array_equal(np.concatenate(got_cnt), want["count"])
+    assert np.array_equal(np.concatenate(got_pos).ravel(), want["pos"])
+    rows = np.concatenate(rows_all)
+    rows = rows[np.argsort(rows[:, 0], kind="stable")]
+    assert np.array_equal(rows.ravel(), qo)
