@@ -277,21 +277,75 @@ struct kmg_query {
   uint64_t *row_off = nullptr;
 };
 
-constexpr int SORT_THREADS = 512, SORT_ITEMS = 16, SORT_TILE = SORT_THREADS * SORT_ITEMS;
+constexpr int HIST_THREADS = 512, HIST_ITEMS = 16, HIST_TILE = HIST_THREADS * HIST_ITEMS;
 constexpr int RLE_THREADS = 256, RLE_ITEMS = 16, RLE_TILE = RLE_THREADS * RLE_ITEMS;
 constexpr int PROBE_THREADS = 256, PROBE_ITEMS = 8, PROBE_TILE = PROBE_THREADS * PROBE_ITEMS;
 constexpr int EMIT_THREADS = 256, EMIT_TILE = EMIT_THREADS * 8;
 constexpr int PIDX_THREADS = 256, PIDX_ITEMS = 8, PIDX_TILE = PIDX_THREADS * PIDX_ITEMS;
 
+// Pass configurations selectable at run time (KMG_SORT_CFG=<index>, for tuning runs).
+using Cfg0 = PassCfg<256, 24, 2, false, 1>;   // default: best on B200 (profiles/r01_sort_pass_tuning.md)
+using Cfg1 = PassCfg<256, 24, 2, true, 1>;
+using Cfg2 = PassCfg<256, 16, 3, false, 1>;
+using Cfg3 = PassCfg<256, 16, 3, true, 1>;
+using Cfg4 = PassCfg<256, 24, 2, false, 2>;
+using Cfg5 = PassCfg<512, 16, 1, false, 1>;
+using Cfg6 = PassCfg<384, 16, 2, false, 1>;
+using Cfg7 = PassCfg<256, 32, 1, false, 1>;
+constexpr int N_SORT_CFG = 8;
+static int g_sort_cfg = -1;
+static uint32_t g_sort_dbg = 0;
+static int sort_cfg() {
+  if (g_sort_cfg < 0) {
+    const char *e = getenv("KMG_SORT_CFG");
+    int v = e ? atoi(e) : 0;
+    g_sort_cfg = (v >= 0 && v < N_SORT_CFG) ? v : 0;
+  }
+  return g_sort_cfg;
+}
+static unsigned long long *g_trace = nullptr;
+static int g_trace_tiles = 0;
+extern "C" int kmg_trace_read(unsigned long long *host, int tiles) {
+  if (!g_trace || tiles > g_trace_tiles) return -1;
+  return cudaMemcpy(host, g_trace, (size_t)tiles * 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -4;
+}
+extern "C" int kmg_tune(const char *key, int value) {
+  if (key && !strcmp(key, "sort_cfg")) {
+    if (value < 0 || value >= N_SORT_CFG) return fail(KMG_ERR_ARG, "sort_cfg out of range");
+    g_sort_cfg = value;
+    return KMG_OK;
+  }
+  if (key && !strcmp(key, "sort_dbg")) { g_sort_dbg = (uint32_t)value; return KMG_OK; }
+  if (key && !strcmp(key, "sort_trace")) {          // value = tiles to trace (0 = off); buffer read by kmg_trace_read
+    if (g_trace) { cudaFree(g_trace); g_trace = nullptr; }
+    g_trace_tiles = value;
+    if (value > 0) { if (cudaMalloc(&g_trace, (size_t)value * 64) != cudaSuccess) return fail(KMG_ERR_NOMEM, "trace alloc"); cudaMemset(g_trace, 0, (size_t)value * 64); }
+    return KMG_OK;
+  }
+  return fail(KMG_ERR_ARG, "unknown tuning key");
+}
+constexpr int SORT_TILE_MIN = 2048;   // status/scratch sizing: smallest tile of any configuration
+
+template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
+static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
+  using S = PassSmem<Cfg, FROM_SEQ>;
+  auto kern = scatter_pass_kernel<Cfg, FROM_SEQ, BinFn, NextFn, HAS_NEXT>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
+  const int64_t tiles = ceil_div<int64_t>(n_upper, Cfg::TILE);
+  if (tiles == 0) return KMG_OK;
+  LAUNCH(name, s, kern<<<(unsigned)tiles, Cfg::THREADS, sizeof(S), s>>>(P));
+  return KMG_OK;
+}
 template <bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
 static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
-  using S = PassSmem<SORT_THREADS, SORT_ITEMS, FROM_SEQ>;
-  auto kern = scatter_pass_kernel<SORT_THREADS, SORT_ITEMS, FROM_SEQ, BinFn, NextFn, HAS_NEXT>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
-  const int64_t tiles = ceil_div<int64_t>(n_upper, SORT_TILE);
-  if (tiles == 0) return KMG_OK;
-  LAUNCH(name, s, kern<<<(unsigned)tiles, SORT_THREADS, sizeof(S), s>>>(P));
-  return KMG_OK;
+  int cfg = sort_cfg();
+  if (!FROM_SEQ && (reinterpret_cast<uintptr_t>(P.pos_in) & 15u) && (cfg == 1 || cfg == 3)) cfg -= 1;   // cp.async needs 16-byte alignment
+  switch (cfg) {
+#define KMG_CASE(i) case i: return launch_pass_cfg<Cfg##i, FROM_SEQ, BinFn, NextFn, HAS_NEXT>(name, P, n_upper, s);
+    KMG_CASE(0) KMG_CASE(1) KMG_CASE(2) KMG_CASE(3) KMG_CASE(4) KMG_CASE(5) KMG_CASE(6) KMG_CASE(7)
+#undef KMG_CASE
+  }
+  return fail(KMG_ERR_ARG, "bad sort configuration");
 }
 
 // Scratch shared by the sort passes of one build.
@@ -307,7 +361,7 @@ static int scratch_alloc(SortScratch &sc, int64_t n_upper, cudaStream_t s) {
   sc.small_words = (size_t)(MAX_PASSES + 1) * RADIX + 16 + sizeof(IndexStats) / 4;
   TRY(dalloc(&sc.small, sc.small_words, s));
   CU(cudaMemsetAsync(sc.small, 0, sc.small_words * 4, s));
-  const size_t tiles = (size_t)ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, SORT_TILE);
+  const size_t tiles = (size_t)ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, SORT_TILE_MIN);
   TRY(dalloc(&sc.status, tiles * RADIX, s));
   CU(cudaMemsetAsync(sc.status, 0, tiles * RADIX * sizeof(uint64_t), s));
   return KMG_OK;
@@ -361,7 +415,10 @@ static int sort_tail(SortScratch &sc, int k, int first_pass, uint64_t *&ka, uint
     P.keys_in = ka; P.pos_in = pa; P.keys_out = kb; P.pos_out = pb;
     P.hist_cur = sc.hist(r); P.hist_next = sc.hist(r + 1);
     P.status = sc.status; P.ticket = sc.ticket(r); P.epoch = (uint32_t)(r + 1);
+    P.n_records = &sc.stats()->n;
     P.bin = DigitBin{r * RADIX_BITS}; P.next = DigitBin{(r + 1) * RADIX_BITS};
+    P.dbg = g_sort_dbg;
+    P.trace = (r == 2 && g_trace && ceil_div<int64_t>(n_upper, 2048) <= g_trace_tiles) ? g_trace : nullptr;   // trace the third pass
     if (r + 1 < R) TRY((launch_pass<false, DigitBin, DigitBin, true>("sort_pass", P, n_upper, s)));
     else TRY((launch_pass<false, DigitBin, DigitBin, false>("sort_pass_last", P, n_upper, s)));
     std::swap(ka, kb);
@@ -397,9 +454,9 @@ static int build_from_view(const SeqView &sv, int k, kmg_index **out) {
     TRY(dalloc(&pa, (size_t)n_upper, s));
     const int R = num_passes(k);
     if (R > 1) { TRY(dalloc(&kb, (size_t)n_upper, s)); TRY(dalloc(&pb, (size_t)n_upper, s)); }
-    const int64_t tiles = ceil_div<int64_t>(n_upper, SORT_TILE);
+    const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
     const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
-    LAUNCH("hist_seq", s, hist_seq_kernel<SORT_THREADS, SORT_ITEMS, DigitBin><<<hgrid, SORT_THREADS, 0, s>>>(sv, sc.hist(0), DigitBin{0}));
+    LAUNCH("hist_seq", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, DigitBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), DigitBin{0}));
     LAUNCH("sum_hist", s, sum_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.stats()));
     {
       PassParams<DigitBin, DigitBin> P{};
@@ -835,9 +892,9 @@ extern "C" int kmg_shard_partition(const void *d_seq, int64_t g0, int64_t g1, in
     TRY(dalloc(&d_spl, (size_t)RADIX, s));
     if (nparts > 1) CU(cudaMemcpyAsync(d_spl, splitters, (size_t)(nparts - 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     OwnerBin ob{d_spl, nparts};
-    const int64_t tiles = ceil_div<int64_t>(sv.nstarts, SORT_TILE);
+    const int64_t tiles = ceil_div<int64_t>(sv.nstarts, HIST_TILE);
     const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
-    LAUNCH("hist_seq_owner", s, hist_seq_kernel<SORT_THREADS, SORT_ITEMS, OwnerBin><<<hgrid, SORT_THREADS, 0, s>>>(sv, sc.hist(0), ob));
+    LAUNCH("hist_seq_owner", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, OwnerBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), ob));
     PassParams<OwnerBin, NoBin> P{};
     P.sv = sv; P.keys_out = d_keys; P.pos_out = d_pos;
     P.hist_cur = sc.hist(0); P.hist_next = nullptr;

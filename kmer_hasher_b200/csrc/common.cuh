@@ -13,6 +13,7 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;   // bins of one sort pass
 constexpr int MAX_PASSES = 8;            // ceil(64 / RADIX_BITS)
 constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned FULL_MASK_ = 0xffffffffu;   // for scopes where a template parameter is named FULL
 
 __host__ __device__ inline uint64_t key_mask(int k) {
   return k < 32 ? ((uint64_t(1) << (2 * k)) - 1) : ~uint64_t(0);

@@ -277,7 +277,8 @@ def test_sharded_engine_single_process(kh, oracle, world, k):
     seq = synth.config_c3(600_000, tail_k=k)
     L = len(seq)
     per = (L + world - 1) // world
-    seq[per - 2:per + 1] = np.frombuffer(b"nAC", np.uint8)          # breaker at the first cut
+    if world > 1:
+        seq[per - 2:per + 1] = np.frombuffer(b"nAC", np.uint8)      # breaker at the first cut
     whole = oracle.build(seq, k)
     want = whole.extract(2 | 8)
     shards, samples = [], []
