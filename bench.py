@@ -207,9 +207,14 @@ def bench_single(args, kh, torch, w, k, L, steps, warm, hbm_peak, peak_src, dev)
         h.free()
 
     def step_e2e():
+        t0 = time.perf_counter()
         h = kh.make_kmer_hash(seq_pin, k)
+        t1 = time.perf_counter()
         kh.kmer_pos(h, 2 | 8, out={"pos": pos_pin, "count": cnt_pin})
+        t2 = time.perf_counter()
         h.free()
+        if os.environ.get("KMG_BENCH_DEBUG"):
+            print("e2e step: build %.2f extract %.2f free %.2f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3), file=sys.stderr)
 
     def timed(fn, n):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

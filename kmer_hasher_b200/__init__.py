@@ -55,7 +55,7 @@ class _Pinned:
             raise MemoryError(_L.kmg_last_error().decode())
 
     def __del__(self):
-        if getattr(self, "ptr", None):
+        if getattr(self, "ptr", None) and _L is not None:      # _L is gone at interpreter shutdown
             _L.kmg_host_free(self.ptr)
             self.ptr = None
 

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <algorithm>
 #include <map>
 #include <mutex>
@@ -86,10 +87,6 @@ static int ctx_init() {
   CU(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
   for (auto &ev : c.ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  cudaMemPool_t pool;
-  CU(cudaDeviceGetDefaultMemPool(&pool, c.device));
-  uint64_t keep = ~uint64_t(0);                  // keep freed blocks: builds reuse them
-  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   c.ready = true;
   return KMG_OK;
 }
@@ -210,17 +207,82 @@ extern "C" uint64_t kmg_launch_count(void) { std::lock_guard<std::mutex> g(g_pro
 // ------------------------------------------------------------------------------------------------
 // memory helpers
 // ------------------------------------------------------------------------------------------------
+// Device memory comes from a small caching arena (per device, thread safe): freed blocks are kept
+// and handed back to requests of (nearly) the same size.  Index builds repeat the same sizes, so
+// after the first build nothing touches the driver allocator.  (The driver's stream-ordered pool
+// was tried first: its block reuse across differing request patterns stalled builds for 10 ms to
+// seconds, see profiles/r01_notes.md.)
+struct Arena {
+  struct Block { void *p; size_t cap; cudaStream_t last; bool synced; };
+  std::mutex mu;
+  std::multimap<size_t, Block> cache;            // free blocks by capacity
+  std::map<void *, Block> live;
+  size_t cached_bytes = 0, limit = 0;
+
+  static size_t round_up(size_t bytes) {
+    if (bytes < (size_t(1) << 20)) return (bytes + 511) & ~size_t(511);
+    return (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+  }
+  void trim_locked() {
+    for (auto &kv : cache) cudaFree(kv.second.p);
+    cache.clear();
+    cached_bytes = 0;
+  }
+  int get(void **out, size_t bytes, cudaStream_t s) {
+    const size_t cap = round_up(bytes ? bytes : 1);
+    std::unique_lock<std::mutex> g(mu);
+    auto it = cache.lower_bound(cap);
+    if (it != cache.end() && it->first <= cap + std::max(cap / 4, size_t(1) << 20)) {
+      Block b = it->second;
+      cache.erase(it);
+      cached_bytes -= b.cap;
+      g.unlock();
+      if (!b.synced && b.last != s) cudaStreamSynchronize(b.last);   // last user was another stream
+      g.lock();
+      b.last = s; b.synced = false;
+      live[b.p] = b;
+      *out = b.p;
+      return KMG_OK;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {                       // give the cache back to the driver and retry once
+      cudaGetLastError();
+      trim_locked();
+      e = cudaMalloc(&p, cap);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(KMG_ERR_NOMEM, "device allocation of %zu bytes failed: %s", cap, cudaGetErrorString(e)); }
+    live[p] = Block{p, cap, s, false};
+    *out = p;
+    return KMG_OK;
+  }
+  void put(void *p, cudaStream_t s, bool synced) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = live.find(p);
+    if (it == live.end()) { cudaFree(p); return; }
+    Block b = it->second;
+    live.erase(it);
+    b.last = s; b.synced = synced;
+    if (limit == 0) {
+      size_t fr = 0, tot = 0;
+      limit = cudaMemGetInfo(&fr, &tot) == cudaSuccess ? tot / 2 : (size_t(32) << 30);
+    }
+    if (cached_bytes + b.cap > limit) trim_locked();
+    cache.emplace(b.cap, b);
+    cached_bytes += b.cap;
+  }
+};
+static Arena g_arena[64];
+
 template <typename T>
 static int dalloc(T **p, size_t count, cudaStream_t s) {
   *p = nullptr;
-  size_t bytes = (count ? count : 1) * sizeof(T);
-  cudaError_t e = cudaMallocAsync((void **)p, bytes, s);
-  if (e != cudaSuccess) { cudaGetLastError(); return fail(KMG_ERR_NOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); }
-  return KMG_OK;
+  return g_arena[g_ctx.device & 63].get((void **)p, (count ? count : 1) * sizeof(T), s);
 }
 template <typename T>
 static void dfree(T *&p, cudaStream_t s) {
-  if (p) cudaFreeAsync((void *)p, s);
+  if (p) g_arena[g_ctx.device & 63].put((void *)p, s, false);
   p = nullptr;
 }
 
@@ -485,35 +547,47 @@ static int build_from_view(const SeqView &sv, int k, kmg_index **out) {
   return KMG_OK;
 }
 
+static double wall_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static bool log_on() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("KMERGPU_LOG"); on = e && e[0] == '1'; }
+  return on == 1;
+}
+
 extern "C" int kmg_build(const char *seq, int64_t len, int k, kmg_index **out) {
   if (!out) return fail(KMG_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be a positive integer less than 1+MAX_K");
   if (len < 0 || (len > 0 && !seq)) return fail(KMG_ERR_ARG, "bad sequence pointer/length");
+  const double t0 = wall_ms();
   TRY(ctx_init());
   cudaStream_t s = g_ctx.stream();
   DevSeq ds;
   TRY(upload_seq(seq, len, s, &ds));
+  const double t1 = wall_ms();
   SeqView sv;
   sv.base = ds.base; sv.nstarts = len - k + 1 > 0 ? len - k + 1 : 0; sv.avail = len; sv.s0 = 0; sv.L = len; sv.k = k;
   int rc = build_from_view(sv, k, out);
   dfree(ds.buf, s);
+  if (log_on())
+    fprintf(stderr, "[kmergpu] build len=%lld k=%d: upload(enqueue) %.3f ms, build %.3f ms (host wall clock)\n", (long long)len, k, t1 - t0, wall_ms() - t1);
   return rc;
 }
 
 extern "C" int kmg_free(kmg_index *ix) {
   if (!ix) return KMG_OK;
-  // stream-ordered frees keep the pool warm and avoid a device-wide synchronisation; this also
-  // works from a finaliser thread that never used the library (falls back to cudaFree)
+  // may run on a finaliser thread that never used the library: make the blocks reusable by anyone
   int prev = -1;
   cudaGetDevice(&prev);
   cudaSetDevice(ix->device);
+  const bool mine = g_ctx.ready && g_ctx.device == ix->device;
+  if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
   void *ptrs[6] = {ix->ukeys, ix->ustart, ix->pos, ix->lut, ix->multi_u, ix->pair_off};
-  const bool async = g_ctx.ready && g_ctx.device == ix->device;
-  for (void *p : ptrs) {
-    if (!p) continue;
-    if (async) cudaFreeAsync(p, g_ctx.stream()); else cudaFree(p);
-  }
+  for (void *p : ptrs) g_arena[ix->device & 63].put(p, nullptr, true);
   cudaGetLastError();
   if (prev >= 0) cudaSetDevice(prev);
   delete ix;
@@ -810,13 +884,12 @@ extern "C" int kmg_query_emit(kmg_query *q, int32_t *out) {
 }
 extern "C" int kmg_query_free(kmg_query *q) {
   if (!q) return KMG_OK;
-  if (q->idx) cudaSetDevice(q->idx->device);
+  const int dev = q->idx ? q->idx->device : g_ctx.device;
+  cudaSetDevice(dev);
+  const bool mine = g_ctx.ready && g_ctx.device == dev;
+  if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
   void *ptrs[3] = {q->hit_i, q->hit_u, q->row_off};
-  const bool async = g_ctx.ready && q->idx && g_ctx.device == q->idx->device;
-  for (void *p : ptrs) {
-    if (!p) continue;
-    if (async) cudaFreeAsync(p, g_ctx.stream()); else cudaFree(p);
-  }
+  for (void *p : ptrs) g_arena[dev & 63].put(p, nullptr, true);
   cudaGetLastError();
   delete q;
   return KMG_OK;

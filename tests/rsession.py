@@ -37,6 +37,7 @@ class RSession:
                                 ("R_ExternalPtrTag", vp, [vp])]:
             fn = getattr(s, name)
             fn.restype, fn.argtypes = res, args
+        self.char_addr = C.CFUNCTYPE(C.c_void_p, C.c_void_p)(("CHAR", s))     # CHAR() as a raw address
         self.nil = C.c_void_p.in_dll(s, "R_NilValue").value
         self.names_sym = C.c_void_p.in_dll(s, "R_NamesSymbol").value
         self.glue.R_init_kmer_hash(None)          # what dyn.load() does

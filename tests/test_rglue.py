@@ -94,15 +94,16 @@ def test_glue_guards_on_device(R, oracle, monkeypatch):
     other = R.make_kmer_hash(s, 8)
     tag = R.stub.R_ExternalPtrTag(other)
     import ctypes as C
-    C.memmove(R.stub.CHAR(R.stub.STRING_ELT(tag, 0)), b"suffix_hash_2509", 16)
+    C.memmove(R.char_addr(R.stub.STRING_ELT(tag, 0)), b"suffix_hash_2509", 16)
     with pytest.raises(RError, match="External pointer has incorrect tag"):
         R.kmer_pos(other, 8)
     # pair.pos beyond an R matrix: refused before allocating anything
     big = np.full(70000, ord("A"), np.uint8)             # one 12-mer, n = 69989 -> P = 2.4e9 > 2^31-1
     pb = R.make_kmer_hash(big, 12)
+    flag = R.integer(4)
     live = R.stub.rstub_live_objects()
     with pytest.raises(RError, match="more than an R matrix can hold"):
-        R.kmer_pos(pb, 4)
-    assert R.stub.rstub_live_objects() == live
+        R.call("kmer_positions", pb, flag)
+    assert R.stub.rstub_live_objects() == live           # nothing was allocated before the refusal
     assert R.kmer_pos(pb, 8)["count"].tolist() == [69989]
     R.stub.rstub_finalize(ptr); R.stub.rstub_finalize(pb)
