@@ -231,40 +231,81 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     Ltot = L * world
     if Ltot > 2**31 - 2:
         raise SystemExit("global sequence exceeds the reference's int coordinates")
-    seed_seq = synth.generate(L, 0xC2 + 7919 * rank, repeat=0.30, tandem=0.10, homo=0.05, lower=0.20)
-    own = engine.upload(seed_seq)
+    own_pin = kh.pinned_empty(L, np.uint8)
+    synth.generate(L, 0xC2 + 7919 * rank, repeat=0.30, tandem=0.10, homo=0.05, lower=0.20, out=own_pin)
+    own_host = torch.from_numpy(own_pin)                   # page-locked by kmg_host_alloc: async DMA source
+    own_dev = own_host.to(dev)
 
-    def step():
-        ix = sharded_build(own, Ltot, k, engine)
-        U, N, _ = ix.local.sizes
-        pos = torch.empty((max(N, 1), 2), dtype=torch.int32, device=dev)
-        cnt = torch.empty(max(U, 1), dtype=torch.int32, device=dev)
-        kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos, "count": cnt})
-        tot = ix.N_total
+    ix = sharded_build(own_dev, Ltot, k, engine)
+    U, N, _ = ix.local.sizes
+    ntot = ix.N_total
+    ix.free()
+    pos_dev = torch.empty((max(N, 1), 2), dtype=torch.int32, device=dev)
+    cnt_dev = torch.empty(max(U, 1), dtype=torch.int32, device=dev)
+    pos_pin, cnt_pin = kh.pinned_empty((max(N, 1), 2), np.int32), kh.pinned_empty(max(U, 1), np.int32)
+
+    def step_device():
+        ix = sharded_build(own_dev, Ltot, k, engine)
+        kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos_dev, "count": cnt_dev})
         ix.free()
-        return tot
+
+    def step_e2e():
+        ix = sharded_build(own_host.to(dev, non_blocking=True), Ltot, k, engine)
+        kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos_pin, "count": cnt_pin})
+        ix.free()
+
+    def timed(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
+        return float(t.item())
 
     for _ in range(warm):
-        step()
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_device()
+    kh.profile(enable=True, reset=True)
+    kh.profile(reset=True)
     l0 = kh.launch_count()
-    a.record()
-    for _ in range(steps):
-        ntot = step()
-    b.record()
-    barrier()
-    ms = a.elapsed_time(b) / steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    from bench import ClockSampler
+    with ClockSampler(dev.index or 0) as clk:
+        ms = timed(step_device, steps)
     launches = kh.launch_count() - l0
+    prof = kh.profile(enable=False)
+    kh.profile(reset=True)
+    for _ in range(warm):
+        step_e2e()
+    ms_e2e = timed(step_e2e, steps)
+
+    sizes = torch.tensor([N, U], dtype=torch.int64, device=dev)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
     if rank != 0:
         return None
+    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    roof = None
+    sp = prof.get("sort_pass")
+    if sp and sp[0] > 0:
+        ach = sp[2] / (sp[0] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "sort_pass (rank 0)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src, "launches": int(sp[1]),
+                "avg_launch_ms": sp[0] / max(sp[1], 1), "algo_bytes_per_launch": sp[2] / max(sp[1], 1)}
+    kernels = {n: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for n, v in sorted(prof.items())}
+    exchanged = 12.0 * ntot / world * (world - 1) / world     # bytes leaving each GPU per step (uniform keys)
     return {"metric": "kmers_indexed_per_s", "value": ntot / (ms * 1e-3), "unit": "k-mers/s", "n_gpus": world,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": w["name"] + f" per GPU; {world} shards of one {Ltot}-base sequence, records routed to "
-                       "key-range owners by NCCL all-to-all", "k": k, "bases": Ltot, "kmers": int(ntot),
+            "config": {"workload": w["name"] + f" per GPU; {world} shards of one {Ltot}-base sequence, (key,pos) records "
+                       "routed to key-range owners by one NCCL all-to-all", "k": k, "bases": Ltot, "kmers": int(ntot),
+                       "per_rank_kmers": all_sizes[:, 0].tolist(), "per_rank_distinct": all_sizes[:, 1].tolist(),
                        "l2": "inputs_exceed_l2"},
-            "e2e": None, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None}
+            "e2e": {"value": ntot / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(L * world),
+                    "d2h_bytes_per_step": int((8 * all_sizes[:, 0] + 4 * all_sizes[:, 1]).sum()), "ms_per_step": ms_e2e,
+                    "what": "per rank: pinned host shard -> device, sharded build, kmer_pos(2|8) into pinned host arrays"},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": None,
+            "exchange": {"bytes_per_gpu_per_step": exchanged, "what": "12-byte records leaving each GPU (estimate, uniform owners)"},
+            "kernels": kernels}
