@@ -50,9 +50,10 @@ static void fill_random(uint8_t *out, int64_t n, rng_t *r) {
  *  [8] tail_k        if > 0, put an N so that the final N-free run has length exactly tail_k
  *  [9] tandem_unit_max  (default 60)   [10] tandem_len_max (default 200000)
  *  [11] n_families (default 200)
+ *  [12] tandem_len_min (default 1000)   [13] homo_len_max (default 500)
  */
 int kms_generate(uint8_t *out, int64_t L, uint64_t seed, const double *p, int np) {
-  if (!out || L < 0 || np < 12) return -1;
+  if (!out || L < 0 || np < 14) return -1;
   rng_t r = {seed ? seed : 0x9E3779B97F4A7C15ULL};
   for (int i = 0; i < 8; ++i) rng_next(&r);
   fill_random(out, L, &r);
@@ -65,6 +66,8 @@ int kms_generate(uint8_t *out, int64_t L, uint64_t seed, const double *p, int np
     const int unit_max = p[9] > 1 ? (int)p[9] : 60;
     const int64_t tlen_max = p[10] > 1 ? (int64_t)p[10] : 200000;
     const int n_fam = p[11] >= 1 ? (int)p[11] : 200;
+    const int64_t tlen_min = p[12] >= 1 ? (int64_t)p[12] : 1000;
+    const int64_t hlen_max = p[13] >= 21 ? (int64_t)p[13] : 500;
 
     /* interspersed repeat families */
     if (repeat_frac > 0) {
@@ -101,7 +104,7 @@ int kms_generate(uint8_t *out, int64_t L, uint64_t seed, const double *p, int np
         if (a == 0) { memcpy(unit, "CA", 2); ul = 2; }
         else if (a == 1) { memcpy(unit, "CCCTAA", 6); ul = 6; }
         else { ul = 2 + (int)rng_below(&r, (uint64_t)(unit_max - 1)); fill_random(unit, ul, &r); }
-        int64_t alen = rng_loguniform(&r, 1000, tlen_max);
+        int64_t alen = rng_loguniform(&r, tlen_min < tlen_max ? tlen_min : tlen_max, tlen_max);
         if (alen > L / 2) alen = L / 2;
         int64_t at = (int64_t)rng_below(&r, (uint64_t)(L - alen + 1));
         for (int64_t j = 0; j < alen; ++j) out[at + j] = unit[j % ul];
@@ -113,7 +116,7 @@ int kms_generate(uint8_t *out, int64_t L, uint64_t seed, const double *p, int np
     if (homo_frac > 0) {
       int64_t target = (int64_t)(homo_frac * (double)L), covered = 0;
       while (covered < target) {
-        int64_t rl = 20 + (int64_t)rng_below(&r, 481);
+        int64_t rl = 20 + (int64_t)rng_below(&r, (uint64_t)(hlen_max - 19));
         int64_t at = (int64_t)rng_below(&r, (uint64_t)(L - rl + 1));
         memset(out + at, ACGT[rng_below(&r, 4)], (size_t)rl);
         covered += rl;

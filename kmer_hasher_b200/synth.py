@@ -30,14 +30,14 @@ def _load():
 
 def generate(L: int, seed: int, *, repeat=0.0, tandem=0.0, homo=0.0, lower=0.0, n_gaps=0, gap_min=10,
              gap_max=500000, n_single=0, tail_k=0, tandem_unit_max=60, tandem_len_max=200000,
-             n_families=200, out: np.ndarray | None = None) -> np.ndarray:
+             n_families=200, tandem_len_min=1000, homo_len_max=500, out: np.ndarray | None = None) -> np.ndarray:
     """A deterministic synthetic sequence as a uint8 array of ASCII bases."""
     if out is None:
         out = np.empty(L, np.uint8)
     assert out.dtype == np.uint8 and out.size >= L and out.flags.c_contiguous
-    p = (C.c_double * 12)(repeat, tandem, homo, lower, n_gaps, gap_min, gap_max, n_single, tail_k,
-                          tandem_unit_max, tandem_len_max, n_families)
-    rc = _load().kms_generate(out.ctypes.data, L, seed, p, 12)
+    p = (C.c_double * 14)(repeat, tandem, homo, lower, n_gaps, gap_min, gap_max, n_single, tail_k,
+                          tandem_unit_max, tandem_len_max, n_families, tandem_len_min, homo_len_max)
+    rc = _load().kms_generate(out.ctypes.data, L, seed, p, 14)
     if rc:
         raise ValueError("kms_generate failed")
     return out[:L]
@@ -62,9 +62,12 @@ def config_c2(L: int = 40_000_000, out=None) -> np.ndarray:
 
 
 def config_c3(L: int = 250_000_000, tail_k: int = 0, out=None) -> np.ndarray:
-    """250 Mbp chromosome with N gaps (index at k=21; also C4's index at k=32)."""
+    """250 Mbp chromosome with N gaps (index at k=21; also C4's index at k=32).  Tandem arrays and
+    homopolymer runs are kept short (microsatellite scale) so that the C4 dot plot stays below the
+    2^31-1 rows an R matrix can hold; config 2 carries the heavy satellite arrays instead."""
     scale = L / 250_000_000
-    return generate(L, 0xC3, repeat=0.30, tandem=0.10, homo=0.05, lower=0.20,
+    return generate(L, 0xC3, repeat=0.30, tandem=0.02, homo=0.0005, lower=0.20, tandem_len_min=100,
+                    tandem_len_max=2000, homo_len_max=60,
                     n_gaps=max(1, int(60 * scale)), gap_min=10, gap_max=max(10, int(500_000 * scale)),
                     n_single=max(1, int(2000 * scale)), tail_k=tail_k, out=out)
 
@@ -82,4 +85,4 @@ def config_c5(L: int = 40_000_000, out=None) -> np.ndarray:
                     tandem_unit_max=40, tandem_len_max=60_000, out=out)
 
 
-C5_TANDEM_FRAC = 0.02
+C5_TANDEM_FRAC = 0.035
