@@ -345,16 +345,15 @@ constexpr int PROBE_THREADS = 256, PROBE_ITEMS = 8, PROBE_TILE = PROBE_THREADS *
 constexpr int EMIT_THREADS = 256, EMIT_TILE = EMIT_THREADS * 8;
 constexpr int PIDX_THREADS = 256, PIDX_ITEMS = 8, PIDX_TILE = PIDX_THREADS * PIDX_ITEMS;
 
-// Pass configurations selectable at run time (KMG_SORT_CFG=<index>, for tuning runs).
-using Cfg0 = PassCfg<256, 24, 2, false, 1>;   // default: best on B200 (profiles/r01_sort_pass_tuning.md)
-using Cfg1 = PassCfg<256, 24, 2, true, 1>;
-using Cfg2 = PassCfg<256, 16, 3, false, 1>;
-using Cfg3 = PassCfg<256, 16, 3, true, 1>;
-using Cfg4 = PassCfg<256, 24, 2, false, 2>;
-using Cfg5 = PassCfg<512, 16, 1, false, 1>;
-using Cfg6 = PassCfg<384, 16, 2, false, 1>;
-using Cfg7 = PassCfg<256, 32, 1, false, 1>;
-constexpr int N_SORT_CFG = 8;
+// Pass configurations selectable at run time (KMG_SORT_CFG=<index>, for tuning runs):
+// <threads, records per thread, CTAs per SM, rank variant (1 ballots, 0 bitmap), look-back width>.
+using Cfg0 = PassCfg<256, 24, 2, 0, 8>;   // default (profiles/r01_sort_pass_tuning.md)
+using Cfg1 = PassCfg<256, 24, 2, 1, 8>;
+using Cfg2 = PassCfg<256, 24, 2, 2, 8>;
+using Cfg3 = PassCfg<256, 16, 3, 0, 8>;
+using Cfg4 = PassCfg<256, 16, 3, 1, 8>;
+using Cfg5 = PassCfg<256, 20, 2, 0, 8>;
+constexpr int N_SORT_CFG = 6;
 static int g_sort_cfg = -1;
 static uint32_t g_sort_dbg = 0;
 static int sort_cfg() {
@@ -400,11 +399,9 @@ static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P,
 }
 template <bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
 static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
-  int cfg = sort_cfg();
-  if (!FROM_SEQ && (reinterpret_cast<uintptr_t>(P.pos_in) & 15u) && (cfg == 1 || cfg == 3)) cfg -= 1;   // cp.async needs 16-byte alignment
-  switch (cfg) {
+  switch (sort_cfg()) {
 #define KMG_CASE(i) case i: return launch_pass_cfg<Cfg##i, FROM_SEQ, BinFn, NextFn, HAS_NEXT>(name, P, n_upper, s);
-    KMG_CASE(0) KMG_CASE(1) KMG_CASE(2) KMG_CASE(3) KMG_CASE(4) KMG_CASE(5) KMG_CASE(6) KMG_CASE(7)
+    KMG_CASE(0) KMG_CASE(1) KMG_CASE(2) KMG_CASE(3) KMG_CASE(4) KMG_CASE(5)
 #undef KMG_CASE
   }
   return fail(KMG_ERR_ARG, "bad sort configuration");
@@ -412,15 +409,18 @@ static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int
 
 // Scratch shared by the sort passes of one build.
 struct SortScratch {
-  uint32_t *small = nullptr;     // hist[(MAX_PASSES+1)][RADIX] | tickets[16] | IndexStats
+  uint32_t *small = nullptr;     // hist[(MAX_PASSES+1)][RADIX] | gbase[(MAX_PASSES+1)][RADIX] | common[RADIX] | tickets[16] | IndexStats
   uint64_t *status = nullptr;    // [tiles][RADIX]
   size_t small_words = 0;
+  static constexpr size_t H = (size_t)(MAX_PASSES + 1) * RADIX;
   uint32_t *hist(int r) const { return small + (size_t)r * RADIX; }
-  uint32_t *ticket(int i) const { return small + (size_t)(MAX_PASSES + 1) * RADIX + i; }
-  IndexStats *stats() const { return reinterpret_cast<IndexStats *>(small + (size_t)(MAX_PASSES + 1) * RADIX + 16); }
+  uint32_t *gbase(int r) const { return small + H + (size_t)r * RADIX; }
+  uint32_t *common() const { return small + 2 * H; }
+  uint32_t *ticket(int i) const { return small + 2 * H + RADIX + i; }
+  IndexStats *stats() const { return reinterpret_cast<IndexStats *>(small + 2 * H + RADIX + 16); }
 };
 static int scratch_alloc(SortScratch &sc, int64_t n_upper, cudaStream_t s) {
-  sc.small_words = (size_t)(MAX_PASSES + 1) * RADIX + 16 + sizeof(IndexStats) / 4;
+  sc.small_words = 2 * SortScratch::H + RADIX + 16 + sizeof(IndexStats) / 4;
   TRY(dalloc(&sc.small, sc.small_words, s));
   CU(cudaMemsetAsync(sc.small, 0, sc.small_words * 4, s));
   const size_t tiles = (size_t)ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, SORT_TILE_MIN);
@@ -468,21 +468,27 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
   return KMG_OK;
 }
 
-// LSD passes 1..R-1 over record buffers (pass 0 has already filled buffer A and hist[1]).
-static int sort_tail(SortScratch &sc, int k, int first_pass, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
+// LSD passes first_pass..R-1 over record buffers.  has_next: only hist/gbase of first_pass exist, each
+// pass takes the next one's histogram as it writes (builds from records); otherwise every pass's
+// gbase is already there (builds from the sequence, hist_all_kernel).
+static int sort_tail(SortScratch &sc, int k, int first_pass, bool has_next, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
                      uint32_t *&pb, int64_t n_upper, cudaStream_t s) {
   const int R = num_passes(k);
   for (int r = first_pass; r < R; ++r) {
     PassParams<DigitBin, DigitBin> P{};
     P.keys_in = ka; P.pos_in = pa; P.keys_out = kb; P.pos_out = pb;
-    P.hist_cur = sc.hist(r); P.hist_next = sc.hist(r + 1);
+    P.gbase = sc.gbase(r); P.hist_next = sc.hist(r + 1);
     P.status = sc.status; P.ticket = sc.ticket(r); P.epoch = (uint32_t)(r + 1);
     P.n_records = &sc.stats()->n;
     P.bin = DigitBin{r * RADIX_BITS}; P.next = DigitBin{(r + 1) * RADIX_BITS};
     P.dbg = g_sort_dbg;
     P.trace = (r == 2 && g_trace && ceil_div<int64_t>(n_upper, 2048) <= g_trace_tiles) ? g_trace : nullptr;   // trace the third pass
-    if (r + 1 < R) TRY((launch_pass<false, DigitBin, DigitBin, true>("sort_pass", P, n_upper, s)));
-    else TRY((launch_pass<false, DigitBin, DigitBin, false>("sort_pass_last", P, n_upper, s)));
+    if (has_next && r + 1 < R) {
+      TRY((launch_pass<false, DigitBin, DigitBin, true>("sort_pass_hist", P, n_upper, s)));
+      LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(r + 1), sc.gbase(r + 1), nullptr));
+    } else {
+      TRY((launch_pass<false, DigitBin, DigitBin, false>("sort_pass", P, n_upper, s)));
+    }
     std::swap(ka, kb);
     std::swap(pa, pb);
   }
@@ -518,25 +524,23 @@ static int build_from_view(const SeqView &sv, int k, kmg_index **out) {
     if (R > 1) { TRY(dalloc(&kb, (size_t)n_upper, s)); TRY(dalloc(&pb, (size_t)n_upper, s)); }
     const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
     const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
-    LAUNCH("hist_seq", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, DigitBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), DigitBin{0}));
-    LAUNCH("sum_hist", s, sum_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.stats()));
+    LAUNCH("hist_all", s, hist_all_kernel<HIST_THREADS, HIST_ITEMS><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.common(), sc.hist(0)));
+    LAUNCH("hist_finish", s, hist_finish_kernel<<<R, RADIX, 0, s>>>(k, sc.common(), sc.hist(0), sc.gbase(0), &sc.stats()->n));
     {
       PassParams<DigitBin, DigitBin> P{};
       P.sv = sv; P.keys_out = ka; P.pos_out = pa;
-      P.hist_cur = sc.hist(0); P.hist_next = sc.hist(1);
+      P.gbase = sc.gbase(0);
       P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
       P.bin = DigitBin{0}; P.next = DigitBin{RADIX_BITS};
-      if (R > 1) TRY((launch_pass<true, DigitBin, DigitBin, true>("sort_pass_seq", P, n_upper, s)));
-      else TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq_last", P, n_upper, s)));
+      TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq", P, n_upper, s)));
     }
-    TRY(sort_tail(sc, k, 1, ka, pa, kb, pb, n_upper, s));   // result ends in (ka, pa)
+    TRY(sort_tail(sc, k, 1, false, ka, pa, kb, pb, n_upper, s));   // result ends in (ka, pa)
     TRY(finish_index(ix, sc, ka, pa, n_upper, s));
     pa = nullptr;                                          // now owned by the index
     const double N = (double)ix->N, L = (double)sv.avail;
-    prof_bytes("hist_seq", L);
-    prof_bytes(R > 1 ? "sort_pass_seq" : "sort_pass_seq_last", L + 12 * N);
-    if (R > 2) prof_bytes("sort_pass", 24 * N * (R - 2));
-    if (R > 1) prof_bytes("sort_pass_last", 24 * N);
+    prof_bytes("hist_all", L);
+    prof_bytes("sort_pass_seq", L + 12 * N);
+    if (R > 1) prof_bytes("sort_pass", 24 * N * (R - 1));
     return KMG_OK;
   };
   rc = body();
@@ -968,9 +972,10 @@ extern "C" int kmg_shard_partition(const void *d_seq, int64_t g0, int64_t g1, in
     const int64_t tiles = ceil_div<int64_t>(sv.nstarts, HIST_TILE);
     const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
     LAUNCH("hist_seq_owner", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, OwnerBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), ob));
+    LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), nullptr));
     PassParams<OwnerBin, NoBin> P{};
     P.sv = sv; P.keys_out = d_keys; P.pos_out = d_pos;
-    P.hist_cur = sc.hist(0); P.hist_next = nullptr;
+    P.gbase = sc.gbase(0); P.hist_next = nullptr;
     P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
     P.bin = ob;
     TRY((launch_pass<true, OwnerBin, NoBin, false>("partition", P, sv.nstarts, s)));
@@ -1019,8 +1024,8 @@ extern "C" int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, i
     TRY(dalloc(&pb, (size_t)n, s));
     const unsigned hgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 16), (int64_t)g_ctx.sms * 8);
     LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, sc.hist(0), DigitBin{0}));
-    LAUNCH("sum_hist", s, sum_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.stats()));
-    TRY(sort_tail(sc, k, 0, ka, pa, kb, pb, n, s));      // result in (ka, pa); may be the caller's arrays
+    LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), &sc.stats()->n));
+    TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s));      // result in (ka, pa); may be the caller's arrays
     // the index must own its positions
     TRY(dalloc(&pfinal, (size_t)n, s));
     CU(cudaMemcpyAsync(pfinal, pa, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
@@ -1028,8 +1033,8 @@ extern "C" int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, i
     pfinal = nullptr;
     const int R = num_passes(k);
     prof_bytes("hist_rec", 8.0 * n);
-    if (R > 1) prof_bytes("sort_pass", 24.0 * n * (R - 1));
-    prof_bytes("sort_pass_last", 24.0 * n);
+    if (R > 1) prof_bytes("sort_pass_hist", 24.0 * n * (R - 1));
+    prof_bytes("sort_pass", 24.0 * n);
     return KMG_OK;
   };
   int rc = body();

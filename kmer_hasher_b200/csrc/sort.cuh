@@ -9,12 +9,15 @@
 //   - records come either from HBM arrays or straight from the ASCII sequence (the 2-bit encoder
 //     of windows.cuh is fused into the first pass: keys are never written unsorted, and windows
 //     that contain an N are dropped by simply not being ranked);
-//   - ranks inside the tile come from warp ballots (match on the 8 bin bits), so the pass is
-//     insensitive to skew (homopolymers, microsatellites);
+//   - ranks inside the tile come from warp-level matching of the 8 bin bits (ballots; a
+//     shared-memory bitmap variant is kept for comparison), so the pass is insensitive to skew
+//     (homopolymers, microsatellites);
 //   - the tile is regrouped by bin in shared memory and written out in runs;
-//   - tile offsets chain through a decoupled look-back, one status word per (tile, bin);
-//   - while the regrouped keys stream out, the histogram of the NEXT pass's digit is taken, so
-//     keys are read once per pass and there is no separate multi-digit histogram kernel.
+//   - tile offsets chain through a decoupled look-back, one status word per (tile, bin).
+// Bin bases come from histograms that are complete before the pass starts: for a build from the
+// sequence all passes' histograms are taken up front by one kernel (hist_all_kernel); for a build
+// from records (sharded build) the histogram of the NEXT pass's digit is taken while the regrouped
+// keys stream out (HAS_NEXT).
 // The same kernel with OwnerBin (key-range owner instead of digit) is the multi-GPU partitioner.
 #pragma once
 #include "common.cuh"
@@ -24,11 +27,13 @@
 namespace kmg {
 
 struct DigitBin {
+  static constexpr bool CHEAP = true;    // two instructions: recomputed wherever the bin is needed
   int shift;
   __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(key >> shift) & (RADIX - 1); }
 };
 // owner r holds keys in [spl[r-1], spl[r]): bin = number of splitters <= key
 struct OwnerBin {
+  static constexpr bool CHEAP = false;   // a binary search: computed once per record and kept (packed bytes)
   const uint64_t *spl;
   int nparts;
   __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
@@ -41,6 +46,7 @@ struct OwnerBin {
   }
 };
 struct NoBin {
+  static constexpr bool CHEAP = true;
   __device__ __forceinline__ uint32_t operator()(uint64_t) const { return 0; }
 };
 
@@ -51,52 +57,28 @@ struct PassParams {
   const uint32_t *pos_in;
   uint64_t *keys_out;
   uint32_t *pos_out;
-  const uint32_t *hist_cur;   // [RADIX] global histogram of this pass's bins (complete)
-  uint32_t *hist_next;        // [RADIX] accumulates the next pass's histogram, or nullptr
+  const uint32_t *gbase;      // [RADIX] exclusive scan of this pass's (complete) bin histogram
+  uint32_t *hist_next;        // [RADIX] accumulates the next pass's histogram (HAS_NEXT), or nullptr
   uint64_t *status;           // [tiles][RADIX] look-back words
   uint32_t *ticket;           // tile id dispenser (zero before launch)
   const uint64_t *n_records;  // record source: exact number of records (device scalar)
   uint32_t epoch;
   unsigned long long *trace;  // tuning runs only: 8 clock64 stamps per tile, or nullptr
-  uint32_t dbg;               // tuning runs only (wrong results): 1 no look-back wait, 2 no global stores, 4 no next-histogram
+  uint32_t dbg;               // tuning runs only (wrong results): 1 no look-back wait, 2 no global stores
   BinFn bin;
   NextFn next;
 };
 
-// block-wide exclusive scan of one value per bin (thread b < RADIX holds bin b). scratch: 8 words.
-template <int THREADS>
-__device__ __forceinline__ uint32_t bins_excl_scan(uint32_t v, uint32_t *scratch, uint32_t &total) {
-  static_assert(THREADS >= RADIX, "one thread per bin");
-  const unsigned w = threadIdx.x >> 5;
-  uint32_t incl = warp_incl_scan(v);
-  if (threadIdx.x < RADIX && lane_id() == 31) scratch[w] = incl;
-  __syncthreads();
-  uint32_t add = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < RADIX / 32; ++i) {
-    uint32_t s = scratch[i];
-    if (i < (int)w) add += s;
-    tot += s;
-  }
-  __syncthreads();
-  total = tot;
-  return incl - v + add;
-}
-
 // Tuning knobs of one pass (chosen per launch by the host, see api.cu).
-//   POS_ASYNC (record source only): cp.async the tile's 32-bit positions into shared memory at tile
-//   start, so they cost no registers and their latency hides behind the ranking (needs a 16-byte
-//   aligned pos array); otherwise they are loaded after the ranking.
-// Measured and dropped on B200 (profiles/r01_sort_pass_tuning.md): ballot match on the 8 bin bits
-// (4x the instructions), __match_any_sync (20 % slower than ballots), several items per match round trip.
-//   CHAINS: a warp's ITEMS are ranked as CHAINS independent sub-chunks (own bitmap + count rows),
-//   interleaved in the instruction stream, so the atomicOr -> read -> clear round trips of different
-//   sub-chunks overlap (the kernel is latency-bound on that chain, profiles/r01_sort_pass_tuning.md).
-template <int THREADS_, int ITEMS_, int MINBLOCKS_, bool POS_ASYNC_, int CHAINS_ = 1>
+//   RANK 1: peers of a record (same bin, same warp step) from 8 ballots, no shared memory;
+//   RANK 0: peers through a per-warp bitmap table (atomicOr the lane bit, read back, leader clears).
+//   LB    : status words fetched per look-back round trip.
+// Measured and dropped on B200 (profiles/r01_sort_pass_tuning.md): __match_any_sync (20 % slower
+// than ballots), several items per bitmap round trip, two interleaved rank chains, cp.async of the
+// positions.
+template <int THREADS_, int ITEMS_, int MINBLOCKS_, int RANK_ = 1, int LB_ = 8>
 struct PassCfg {
-  static constexpr int THREADS = THREADS_, ITEMS = ITEMS_, MINBLOCKS = MINBLOCKS_, CHAINS = CHAINS_;
-  static_assert(ITEMS_ % CHAINS_ == 0, "items split evenly over chains");
-  static constexpr bool POS_ASYNC = POS_ASYNC_;
+  static constexpr int THREADS = THREADS_, ITEMS = ITEMS_, MINBLOCKS = MINBLOCKS_, RANK = RANK_, LB = LB_;
   static constexpr int TILE = THREADS * ITEMS;
 };
 
@@ -104,19 +86,37 @@ template <class Cfg, bool FROM_SEQ>
 struct PassSmem {
   static constexpr int TILE = Cfg::TILE;
   static constexpr int WARPS = Cfg::THREADS / 32;
-  static constexpr int VW = WARPS * Cfg::CHAINS;   // ranked sub-chunks ("virtual warps"), in memory order
   using PosT = typename std::conditional<FROM_SEQ, uint16_t, uint32_t>::type;
   uint64_t keys[TILE];
   PosT pos[TILE];
-  uint32_t whist[VW][RADIX];      // per-sub-chunk bin counts, later its offset inside the bin
-  uint32_t match[VW][RADIX];      // lane bitmaps of the item being matched (self-clearing)
-  int32_t goff[RADIX];            // global index of the bin's first record of this tile - its tile slot
-  uint32_t start[RADIX];
+  uint32_t whist[WARPS][RADIX];                        // per-warp bin counts, later the warp's first slot of the bin
+  uint32_t match[Cfg::RANK != 1 ? WARPS * RADIX : 1];  // RANK 0: lane bitmaps of the item being matched (self-clearing)
+  int32_t goff[RADIX];                                 // global index of the bin's first record of this tile - its tile slot
   uint32_t next[RADIX];
   uint32_t scratch[8];
   uint32_t tile;
   TileCodes<FROM_SEQ ? TILE : 16> tc;
 };
+
+// lanes of the warp whose 8-bit bin equals this lane's (restricted to `active`): per bit one predicate,
+// one ballot and one predicated AND (the compiler's own select sequence is two instructions longer)
+__device__ __forceinline__ uint32_t match_bin(uint32_t d, uint32_t active) {
+  uint32_t peers = active;
+#define KMG_MATCH_BIT(B)                                         \
+  asm volatile(                                                  \
+      "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"                   \
+      "and.b32 t, %1, " #B ";\n\t"                               \
+      "setp.ne.u32 p, t, 0;\n\t"                                 \
+      "vote.sync.ballot.b32 t, p, 0xffffffff;\n\t"               \
+      "@p and.b32 %0, %0, t;\n\t"                                \
+      "@!p lop3.b32 %0, %0, t, 0, 0x30;\n\t}"                    \
+      : "+r"(peers) : "r"(d))
+  static_assert(RADIX_BITS == 8, "eight bin bits");
+  KMG_MATCH_BIT(1); KMG_MATCH_BIT(2); KMG_MATCH_BIT(4); KMG_MATCH_BIT(8);
+  KMG_MATCH_BIT(16); KMG_MATCH_BIT(32); KMG_MATCH_BIT(64); KMG_MATCH_BIT(128);
+#undef KMG_MATCH_BIT
+  return peers;
+}
 
 // One tile.  FULL: every slot of the tile holds a valid record (no predicates on the hot path).
 template <class Cfg, bool FROM_SEQ, bool FULL, class BinFn, class NextFn, bool HAS_NEXT>
@@ -124,7 +124,7 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
                                           const uint32_t tile, const int64_t q0, const int64_t n_in,
                                           const uint32_t gbase, const bool special) {
   using S = PassSmem<Cfg, FROM_SEQ>;
-  constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS, ITEMS = Cfg::ITEMS;
+  constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS, ITEMS = Cfg::ITEMS, WARPS = S::WARPS;
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const int t0 = warp * (32 * ITEMS) + lane;
 #define KMG_STAMP(slot) do { if (P.trace && tid == 0) P.trace[(size_t)tile * 8 + (slot)] = clock64(); } while (0)
@@ -133,7 +133,6 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
   // ---- load ITEMS records per thread, warp-striped (item i of lane l = element i*32+l of the
   //      warp's chunk), which is memory order => the ranks below are stable
   uint64_t key[ITEMS];
-  uint32_t val[ITEMS];
   uint32_t valid = FULL ? 0xFFFFFFFFu : 0u;
   if constexpr (FROM_SEQ) {
 #pragma unroll
@@ -144,25 +143,6 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
         if (tile_valid<TILE>(P.sv, sm.tc, q0, t, special)) valid |= 1u << i;
     }
   } else {
-    if constexpr (Cfg::POS_ASYNC) {
-      // stream the tile's positions into shared memory (tile order) while the keys are ranked
-      const uint32_t *src = P.pos_in + q0;
-      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(&sm.pos[0]);
-#pragma unroll
-      for (int c = 0; c < TILE / 4 / THREADS; ++c) {
-        const int e = (c * THREADS + tid) * 4;
-        if constexpr (FULL) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + e * 4), "l"(src + e) : "memory");
-        } else {
-          const int64_t left = n_in - q0 - e;
-          if (left > 0) {
-            const uint32_t bytes = (uint32_t)min((int64_t)16, left * 4);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + e * 4), "l"(src + e), "r"(bytes) : "memory");
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
     const uint64_t *ksrc = P.keys_in + q0 + t0;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -174,78 +154,122 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     }
   }
 
-  // ---- rank inside the warp: match equal bins through the warp's bitmap table (atomicOr the lane
-  //      bit, read the bitmap back, lowest peer clears it and bumps the warp's running bin count).
-  //      rk = bin << 16 | rank among the warp's earlier records of that bin.
+  // ---- rank inside the warp.  rk = bin << 16 | rank among the warp's earlier records of that bin.
+  //      A warp's shared-memory atomics are applied in issue order, so step i sees steps < i.
   uint32_t rk[ITEMS];
   const unsigned lt = lanemask_lt();
-  const uint32_t lanebit = 1u << lane;
   if (P.trace && tid == 0) { P.trace[(size_t)tile * 8 + 2] = (unsigned long long)(key[0] & 1) + clock64(); }   // first key has arrived
-  constexpr int CH = Cfg::CHAINS, PER = ITEMS / CH;    // item i belongs to sub-chunk i / PER
+  uint32_t dpk[BinFn::CHEAP ? 1 : (ITEMS + 3) / 4] = {};   // expensive bins: the record's bin, one byte each
+  if constexpr (!BinFn::CHEAP) {
 #pragma unroll
-  for (int st = 0; st < PER; ++st) {
-    uint32_t d[CH], peers[CH], old[CH];
-    __syncwarp();                                        // previous step's clears are visible
+    for (int i = 0; i < ITEMS; ++i) dpk[i >> 2] |= P.bin(key[i]) << (8 * (i & 3));
+  }
+#define KMG_BIN(i) (BinFn::CHEAP ? P.bin(key[i]) : ((dpk[(i) >> 2] >> (8 * ((i) & 3))) & 0xFFu))
+  if constexpr (Cfg::RANK >= 1) {
+    // RANK 2: odd items go through the bitmap table instead, so the ALU (ballots) and the
+    // shared-memory pipe (bitmaps) share the ranking work.
+    // phase A: peers of the ballot items (no memory: all steps overlap)
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int i = c * PER + st;
-      d[c] = P.bin(key[i]);
-      if (FULL || ((valid >> i) & 1u)) atomicOr(&sm.match[warp * CH + c][d[c]], lanebit);
+    for (int i = 0; i < ITEMS; ++i) {
+      if (Cfg::RANK == 2 && (i & 1)) continue;
+      const bool ok = FULL || ((valid >> i) & 1u);
+      const uint32_t peers = match_bin(KMG_BIN(i), FULL ? FULL_MASK_ : __ballot_sync(FULL_MASK_, ok));
+      rk[i] = ok ? peers : 0u;
     }
-    __syncwarp();
+    // phase B, in item order: the lowest peer bumps the warp's bin count; G atomics in flight before
+    // their results are read
+    constexpr int G = 4;
+    static_assert(ITEMS % G == 0, "items per thread in groups of G");
+    const uint32_t lanebit = 1u << lane;
+    uint32_t *mrow = sm.match + (Cfg::RANK == 2 ? warp * RADIX : 0);
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int i = c * PER + st;
-      peers[c] = (FULL || ((valid >> i) & 1u)) ? sm.match[warp * CH + c][d[c]] : 0u;
-    }
-    __syncwarp();                                        // everyone has read before the clears
+    for (int i0 = 0; i0 < ITEMS; i0 += G) {
+      uint32_t old[G];
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int i = c * PER + st;
-      old[c] = 0;
-      // a warp's shared-memory atomics are applied in issue order, so step st sees steps < st
-      if ((FULL || ((valid >> i) & 1u)) && (peers[c] & lt) == 0) {
-        sm.match[warp * CH + c][d[c]] = 0;
-        old[c] = atomicAdd(&sm.whist[warp * CH + c][d[c]], (uint32_t)__popc(peers[c]));
+      for (int j = 0; j < G; ++j) {
+        const int i = i0 + j;
+        const uint32_t d = KMG_BIN(i);
+        if (Cfg::RANK == 2 && (i & 1)) {
+          const bool ok = FULL || ((valid >> i) & 1u);
+          if (ok) atomicOr(&mrow[d], lanebit);
+          __syncwarp();
+          rk[i] = ok ? mrow[d] : 0u;
+          __syncwarp();                                    // everyone has read before the clear
+        }
+        const uint32_t peers = rk[i];
+        old[j] = 0;
+        if (peers && (peers & lt) == 0) {
+          if (Cfg::RANK == 2 && (i & 1)) mrow[d] = 0;
+          old[j] = atomicAdd(&sm.whist[warp][d], (uint32_t)__popc(peers));
+        }
+        __syncwarp();                                      // steps stay in order even if the branch diverges
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const uint32_t peers = rk[i0 + j];
+        const uint32_t base = __shfl_sync(FULL_MASK_, old[j], (FULL || peers) ? (__ffs(peers) - 1) : 0);
+        rk[i0 + j] = (KMG_BIN(i0 + j) << 16) | (base + __popc(peers & lt));
       }
     }
+  } else {
+    const uint32_t lanebit = 1u << lane;
+    uint32_t *mrow = sm.match + warp * RADIX;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int i = c * PER + st;
-      const uint32_t base = __shfl_sync(FULL_MASK_, old[c], FULL ? (__ffs(peers[c]) - 1) : (peers[c] ? __ffs(peers[c]) - 1 : 0));
-      rk[i] = (d[c] << 16) | (base + __popc(peers[c] & lt));
+    for (int i = 0; i < ITEMS; ++i) {
+      const uint32_t d = KMG_BIN(i);
+      const bool ok = FULL || ((valid >> i) & 1u);
+      __syncwarp();                                        // previous step's clears are visible
+      if (ok) atomicOr(&mrow[d], lanebit);
+      __syncwarp();
+      const uint32_t peers = ok ? mrow[d] : 0u;
+      __syncwarp();                                        // everyone has read before the clears
+      uint32_t old = 0;
+      if (ok && (peers & lt) == 0) {
+        mrow[d] = 0;
+        old = atomicAdd(&sm.whist[warp][d], (uint32_t)__popc(peers));
+      }
+      const uint32_t base = __shfl_sync(FULL_MASK_, old, (FULL || peers) ? (__ffs(peers) - 1) : 0);
+      rk[i] = (d << 16) | (base + __popc(peers & lt));
     }
   }
+#undef KMG_BIN
   KMG_STAMP(3);                                          // this warp's ranking done
-  if constexpr (!FROM_SEQ && Cfg::POS_ASYNC) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   KMG_STAMP(4);
-  if constexpr (!FROM_SEQ && Cfg::POS_ASYNC) {           // every thread's copies have landed
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) val[i] = sm.pos[t0 + i * 32];
-  }
 
-  // ---- per-bin totals of the tile; publish them, then place the tile's bins in shared memory
-  uint32_t cnt = 0;
-  if (tid < RADIX) {
+  // ---- per-bin totals of the tile; publish them, then turn whist[w][bin] into the first slot
+  //      of warp w's records of that bin in the regrouped tile
+  uint32_t cnt = 0, lstart = 0, tile_count;
+  {
+    uint32_t c[WARPS];
+    if (tid < RADIX) {
 #pragma unroll
-    for (int w = 0; w < S::VW; ++w) {
-      uint32_t c = sm.whist[w][tid];
-      sm.whist[w][tid] = cnt;                 // becomes the sub-chunk's offset inside the bin
-      cnt += c;
+      for (int w = 0; w < WARPS; ++w) { c[w] = sm.whist[w][tid]; cnt += c[w]; }
+      st_relaxed_u64(P.status + (size_t)tile * RADIX + tid, st_pack(tile == 0 ? ST_INCL : ST_AGG, P.epoch, cnt));
     }
-    st_relaxed_u64(P.status + (size_t)tile * RADIX + tid, st_pack(tile == 0 ? ST_INCL : ST_AGG, P.epoch, cnt));
+    const uint32_t incl = warp_incl_scan(cnt);
+    if (tid < RADIX && lane == 31) sm.scratch[warp] = incl;
+    __syncthreads();
+    uint32_t add = 0, tot = 0;
+#pragma unroll
+    for (int j = 0; j < RADIX / 32; ++j) {
+      const uint32_t s = sm.scratch[j];
+      if (j < (int)warp) add += s;
+      tot += s;
+    }
+    tile_count = tot;
+    lstart = incl - cnt + add;
+    if (tid < RADIX) {
+      uint32_t run = lstart;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) { sm.whist[w][tid] = run; run += c[w]; }
+    }
   }
-  uint32_t tile_count;
-  const uint32_t lstart = bins_excl_scan<THREADS>(cnt, sm.scratch, tile_count);
-  if (tid < RADIX) sm.start[tid] = lstart;
   __syncthreads();
 
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {                     // rk becomes the slot in the regrouped tile
-    const uint32_t d = rk[i] >> 16;
-    rk[i] = sm.start[d] + sm.whist[warp * CH + i / PER][d] + (rk[i] & 0xFFFFu);
-  }
+  for (int i = 0; i < ITEMS; ++i)                        // rk becomes the slot in the regrouped tile
+    rk[i] = sm.whist[warp][rk[i] >> 16] + (rk[i] & 0xFFFFu);
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i)
     if (FULL || ((valid >> i) & 1u)) sm.keys[rk[i]] = key[i];
@@ -254,32 +278,32 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     for (int i = 0; i < ITEMS; ++i)
       if (FULL || ((valid >> i) & 1u)) sm.pos[rk[i]] = (uint16_t)(t0 + i * 32);
   } else {
-    if constexpr (!Cfg::POS_ASYNC) {
+    uint32_t val[ITEMS];
 #pragma unroll
-      for (int i = 0; i < ITEMS; ++i)
-        val[i] = (FULL || ((valid >> i) & 1u)) ? ld_stream_u32(P.pos_in + q0 + t0 + i * 32) : 0;
-    }
+    for (int i = 0; i < ITEMS; ++i)
+      val[i] = (FULL || ((valid >> i) & 1u)) ? ld_stream_u32(P.pos_in + q0 + t0 + i * 32) : 0;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i)
       if (FULL || ((valid >> i) & 1u)) sm.pos[rk[i]] = val[i];
   }
 
   KMG_STAMP(5);                                          // regrouped in shared memory
-  // ---- look back over earlier tiles (one bin per thread, four status words per round trip);
+  // ---- look back over earlier tiles (one bin per thread, LB status words per round trip);
   //      predecessors have had the whole regrouping above to publish
   if (tid < RADIX) {
     uint64_t excl = 0;
     if (tile > 0 && !(P.dbg & 1u)) {
+      constexpr int LB = Cfg::LB;
       int64_t t = (int64_t)tile - 1;
       bool done = false;
       while (!done) {
-        uint64_t w[4];
+        uint64_t w[LB];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < LB; ++j)
           w[j] = t - j >= 0 ? ld_relaxed_u64(P.status + (size_t)(t - j) * RADIX + tid) : st_pack(ST_INCL, P.epoch, 0);
         if (st_flag(w[0], P.epoch) == 0) { __nanosleep(40); continue; }   // not published yet: back off, poll again
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < LB; ++j) {
           if (done) break;
           const uint64_t f = st_flag(w[j], P.epoch);
           if (f == 0) break;
@@ -307,7 +331,7 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
         if constexpr (FROM_SEQ) P.pos_out[dst] = (uint32_t)(P.sv.s0 + q0 + 1) + sm.pos[s];   // 1-based start
         else P.pos_out[dst] = sm.pos[s];
       }
-      if (HAS_NEXT && !(P.dbg & 4u)) atomicAdd(&sm.next[P.next(kk)], 1u);
+      if constexpr (HAS_NEXT) atomicAdd(&sm.next[P.next(kk)], 1u);
     }
   }
   KMG_STAMP(7);                                          // stores issued
@@ -320,7 +344,7 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   using S = PassSmem<Cfg, FROM_SEQ>;
   constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS;
   static_assert(TILE <= 65536, "tile-local positions are 16 bit");
-  static_assert(TILE % (4 * THREADS) == 0, "cp.async chunks per thread");
+  static_assert(THREADS >= RADIX, "one thread per bin");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S &sm = *reinterpret_cast<S *>(smem_raw);
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -328,17 +352,19 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   const long long t_start = clock64();
   if (tid == 0) sm.tile = atomicAdd(P.ticket, 1u);
   {
-    uint4 *zw = reinterpret_cast<uint4 *>(sm.whist[warp * Cfg::CHAINS]), *zm = reinterpret_cast<uint4 *>(sm.match[warp * Cfg::CHAINS]);
+    uint4 *zw = reinterpret_cast<uint4 *>(sm.whist[warp]);
 #pragma unroll
-    for (int j = 0; j < Cfg::CHAINS * RADIX / 4 / 32; ++j) { zw[j * 32 + lane] = make_uint4(0, 0, 0, 0); zm[j * 32 + lane] = make_uint4(0, 0, 0, 0); }
+    for (int j = 0; j < RADIX / 4 / 32; ++j) zw[j * 32 + lane] = make_uint4(0, 0, 0, 0);
+    if constexpr (Cfg::RANK != 1) {
+      uint4 *zm = reinterpret_cast<uint4 *>(sm.match + warp * RADIX);
+#pragma unroll
+      for (int j = 0; j < RADIX / 4 / 32; ++j) zm[j * 32 + lane] = make_uint4(0, 0, 0, 0);
+    }
   }
-  if (tid < RADIX) sm.next[tid] = 0;
-
-  // global exclusive base of every bin for this pass (the histogram is L2-resident, 1 KB)
-  uint32_t gcount = tid < RADIX ? P.hist_cur[tid] : 0;
+  if (HAS_NEXT && tid < RADIX) sm.next[tid] = 0;
+  const uint32_t gbase = tid < RADIX ? __ldg(P.gbase + tid) : 0;   // 1 KB, L2-resident
   const int64_t n_in = FROM_SEQ ? P.sv.nstarts : (int64_t)*P.n_records;
-  uint32_t n_total;
-  const uint32_t gbase = bins_excl_scan<THREADS>(gcount, sm.scratch, n_total);   // syncs: sm.tile visible
+  __syncthreads();
   const uint32_t tile = sm.tile;
   const int64_t q0 = (int64_t)tile * TILE;
   if (q0 >= n_in) return;
@@ -352,7 +378,7 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   else
     pass_tile<Cfg, FROM_SEQ, false, BinFn, NextFn, HAS_NEXT>(P, sm, tile, q0, n_in, gbase, special);
 
-  if (HAS_NEXT) {
+  if constexpr (HAS_NEXT) {
     __syncthreads();
     if (tid < RADIX) {
       uint32_t c = sm.next[tid];
@@ -361,8 +387,116 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   }
 }
 
-// ---- histogram of the first pass's bins -------------------------------------------------------------
-// Sequence source: a persistent grid walks the tiles, encoding on the fly (reads L bytes).
+// ---- bin bases -----------------------------------------------------------------------------------------
+// gbase = exclusive scan of one histogram; *n (if given) = its total.  One block of RADIX threads.
+__global__ void __launch_bounds__(RADIX)
+scan_hist_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ gbase, uint64_t *n) {
+  __shared__ uint32_t part[RADIX / 32];
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t v = hist[tid];
+  const uint32_t incl = warp_incl_scan(v);
+  if (lane == 31) part[warp] = incl;
+  __syncthreads();
+  uint32_t add = 0;
+  uint64_t tot = 0;
+#pragma unroll
+  for (int j = 0; j < RADIX / 32; ++j) {
+    if (j < (int)warp) add += part[j];
+    tot += part[j];
+  }
+  gbase[tid] = incl - v + add;
+  if (n && tid == 0) *n = tot;
+}
+
+// ---- all passes' histograms from the sequence, in one sweep -------------------------------------------
+// Digit r of the window that starts at p is the code of bases [p + lo_r, p + hi_r], lo_r = max(0, k-4r-4),
+// hi_r = k-4r-1: a whole 4-mer for every digit but a possibly shorter top one.  So over a stretch of
+// valid window starts [a, b) the histogram of digit r is the 4-mer histogram of sequence positions
+// [a + lo_r, b + lo_r): the same for all r up to lo_r positions at either end.  A tile without breakers
+// therefore counts each of its positions ONCE into `common` and fixes up the <= 28 positions at each
+// end per digit (ind[r], modulo 2^32); tiles with breakers or at the end of the data count every
+// window's digits directly into ind[r].  hist_finish_kernel adds the two.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+hist_all_kernel(const SeqView sv, uint32_t *common /* [RADIX] */, uint32_t *ind /* [R][RADIX] */) {
+  constexpr int TILE = THREADS * ITEMS;
+  __shared__ TileCodes<TILE> tc;
+  __shared__ uint32_t sh_common[RADIX];
+  __shared__ uint32_t sh_ind[MAX_PASSES][RADIX];
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const int k = sv.k, R = num_passes(k);
+  for (int b = tid; b < RADIX; b += THREADS) sh_common[b] = 0;
+  for (int b = tid; b < R * RADIX; b += THREADS) (&sh_ind[0][0])[b] = 0;
+  const int64_t tiles = ceil_div<int64_t>(sv.nstarts, TILE);
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t q0 = tile * TILE;
+    __syncthreads();                                   // previous tile's readers are done (and the zeroing)
+    const bool special = tile_pack<TILE, THREADS>(sv, q0, tc);
+    const int t0 = warp * (32 * ITEMS) + lane;
+    if (!special && q0 + TILE <= sv.nstarts) {
+      // every window of the tile is valid (a tile that touches the end of the data is `special`)
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) atomicAdd(&sh_common[tile_c4<TILE>(tc, t0 + i * 32)], 1u);
+      // ends: digit r uses positions [q0 + lo_r, q0 + TILE + lo_r) instead of [q0, q0 + TILE)
+      for (int e = tid; e < R * 32; e += THREADS) {
+        const int r = e >> 5, t = e & 31, lo = k - 4 * r - 4;
+        if (t < lo) {
+          atomicSub(&sh_ind[r][tile_c4<TILE>(tc, t)], 1u);
+          atomicAdd(&sh_ind[r][tile_c4<TILE>(tc, TILE + t)], 1u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int t = t0 + i * 32;
+        if (tile_valid<TILE>(sv, tc, q0, t, special)) {
+          const uint64_t key = tile_key<TILE>(tc, t, k);
+          for (int r = 0; r < R; ++r) atomicAdd(&sh_ind[r][(uint32_t)(key >> (r * RADIX_BITS)) & (RADIX - 1)], 1u);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int b = tid; b < RADIX; b += THREADS) {
+    const uint32_t c = sh_common[b];
+    if (c) atomicAdd(common + b, c);
+  }
+  for (int b = tid; b < R * RADIX; b += THREADS) {
+    const uint32_t c = (&sh_ind[0][0])[b];
+    if (c) atomicAdd(ind + b, c);
+  }
+}
+
+// hist[r] = ind[r] + common folded to digit r's width; gbase[r] = its exclusive scan; *n = windows.
+// Launched with R blocks of RADIX threads.
+__global__ void __launch_bounds__(RADIX)
+hist_finish_kernel(int k, const uint32_t *__restrict__ common, uint32_t *hist /* [R][RADIX], holds ind */,
+                   uint32_t *gbase /* [R][RADIX] */, uint64_t *n) {
+  __shared__ uint32_t part[RADIX / 32];
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const int r = blockIdx.x;
+  const int m = min(4, k - 4 * r);                      // bases in digit r
+  const int s = 2 * (4 - m);
+  uint32_t v = hist[r * RADIX + tid];
+  if (tid < (1u << (2 * m))) {
+    for (uint32_t c = tid << s; c < ((tid + 1u) << s); ++c) v += common[c];
+  }
+  hist[r * RADIX + tid] = v;
+  const uint32_t incl = warp_incl_scan(v);
+  if (lane == 31) part[warp] = incl;
+  __syncthreads();
+  uint32_t add = 0;
+  uint64_t tot = 0;
+#pragma unroll
+  for (int j = 0; j < RADIX / 32; ++j) {
+    if (j < (int)warp) add += part[j];
+    tot += part[j];
+  }
+  gbase[r * RADIX + tid] = incl - v + add;
+  if (r == 0 && tid == 0) *n = tot;
+}
+
+// ---- histogram of one pass's bins (sharded build: owner bins from the sequence, digit 0 of records) ----
 template <int THREADS, int ITEMS, class BinFn>
 __global__ void __launch_bounds__(THREADS)
 hist_seq_kernel(const SeqView sv, uint32_t *hist, BinFn bin) {

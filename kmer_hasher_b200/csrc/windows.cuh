@@ -82,6 +82,13 @@ __device__ __forceinline__ uint64_t tile_key(const TileCodes<TILE> &tc, int t, i
   uint64_t full = (a << sh) | (uint64_t(tc.codes[g + 2]) >> (32 - sh));
   return full >> (64 - 2 * k);
 }
+// code of the four bases that start at tile-local index t (t < TILE + 32: reads two groups only)
+template <int TILE>
+__device__ __forceinline__ uint32_t tile_c4(const TileCodes<TILE> &tc, int t) {
+  const int g = t >> 4, sh = (t & 15) * 2;
+  const uint64_t a = (uint64_t(tc.codes[g]) << 32) | tc.codes[g + 1];
+  return (uint32_t)((a << sh) >> 56);
+}
 template <int TILE>
 __device__ __forceinline__ bool tile_window_clean(const TileCodes<TILE> &tc, int t, int k) {
   const int g = t >> 4, o = t & 15;

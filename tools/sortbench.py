@@ -35,7 +35,7 @@ for cfg, dbg in [(c, d) for c in cfgs for d in dbgs]:
     kh.profile(reset=True)
     sp = prof.get("sort_pass", (0, 1, 0))
     line = f"cfg {cfg:2d} dbg {dbg} build {a.elapsed_time(b) / reps:7.3f} ms | sort_pass {sp[0] / max(sp[1], 1) * 1e3:7.1f} us {sp[2] / max(sp[0], 1e-9) / 1e6:7.0f} GB/s"
-    for name in ("sort_pass_seq", "sort_pass_last", "hist_seq", "rle", "stats"):
+    for name in ("sort_pass_seq", "hist_all", "hist_finish", "rle", "stats"):
         if name in prof:
             v = prof[name]
             line += f" | {name} {v[0] / max(v[1], 1) * 1e3:6.1f}us"
