@@ -123,6 +123,51 @@ int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, int k, kmg_i
 int kmg_query_records(const kmg_index *idx, const uint64_t *d_keys, const int32_t *d_i, int64_t n,
                       kmg_query **st, uint64_t *M);
 
+/* ---- sharded build over peer memory (NVLink): the fused partition + exchange -----------------------
+ * The partitioning pass writes every record straight into the arrays of the GPU that owns its key
+ * range (peer memory mapped with kmg_ipc_open), so there is no staging copy and no all-to-all; the
+ * host only all-gathers the G x G count matrix and issues one barrier.  No call below synchronises
+ * with the host except kmg_build_received / kmg_query_received (they read the result's sizes).
+ * kmg_shard_open    : aligned, padded device copy of a rank's bytes [g0,g1) (arguments as above).
+ * kmg_shard_sample_keys / kmg_shard_count : splitter sample; counts[nparts] (device) of the shard's
+ *                     records per owner for device-resident splitters.
+ * kmg_shard_scatter : encodes the shard and writes owner b's records to peer_keys[b]/peer_pos[b]
+ *                     (capacity records each) behind those of lower ranks; d_matrix[src][owner] is the
+ *                     all-gathered count matrix (device).  pos_add is added to the 1-based start
+ *                     (k-1 gives the reference's query coordinate).  d_info[0] = records this rank
+ *                     receives, d_info[1] = 1 if an owner would overflow (its surplus is dropped and
+ *                     kmg_build_received / kmg_query_received then fail with KMG_ERR_RANGE).
+ */
+typedef struct kmg_shard kmg_shard;
+int kmg_shard_open(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t s0, int64_t s1,
+                   int k, kmg_shard **out);
+ /* halo + splitter sample in ONE exchange: every rank packs its first k-1 bytes, its last byte and
+ * n_samples (a power of two <= 4096) ascending sample keys into kmg_shard_pack_bytes(n_samples) bytes;
+ * the packs are all-gathered ([world][bytes]); kmg_shard_open_packed assembles the shard of `rank`
+ * (its own bytes [rank*per, (rank+1)*per) of L, per = ceil(L/world), plus halo) and writes the
+ * world-1 splitters (element j*total/world of all samples in ascending order) to d_splitters. */
+int kmg_shard_pack_bytes(int n_samples);
+int kmg_shard_pack(const void *d_own, int64_t n_own, int k, int n_samples, void *d_pack);
+int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L, int world, int rank, int k,
+                          int n_samples, const void *d_allpack, kmg_shard **out,
+                          uint64_t *d_splitters);
+int kmg_shard_close(kmg_shard *sh);
+int kmg_shard_windows(const kmg_shard *sh, int64_t *nstarts);
+int kmg_shard_sample_keys(const kmg_shard *sh, int n, uint64_t *d_samples);
+int kmg_shard_count(const kmg_shard *sh, const uint64_t *d_splitters, int nparts, uint64_t *d_counts);
+int kmg_shard_scatter(const kmg_shard *sh, const uint64_t *d_splitters, int nparts, int rank,
+                      void *const *peer_keys, void *const *peer_pos, uint64_t capacity,
+                      const uint64_t *d_matrix, int32_t pos_add, uint64_t *d_info);
+int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, const uint64_t *d_info,
+                       int k, kmg_index **out);
+int kmg_query_received(const kmg_index *idx, const uint64_t *d_keys, const int32_t *d_i,
+                       uint64_t capacity, const uint64_t *d_info, kmg_query **st, uint64_t *M);
+/* device buffers other processes of the node can map (CUDA IPC); handle is 64 bytes */
+int kmg_ipc_alloc(size_t bytes, void **dptr, void *handle);
+int kmg_ipc_free(void *dptr);
+int kmg_ipc_open(const void *handle, void **dptr);
+int kmg_ipc_close(void *dptr);
+
 /* ---- instrumentation (bench.py / profiles) ------------------------------------------------------ */
 int kmg_profile_enable(int on);          /* bracket every kernel with CUDA events               */
 int kmg_profile_reset(void);

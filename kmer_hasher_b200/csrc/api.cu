@@ -387,10 +387,10 @@ extern "C" int kmg_tune(const char *key, int value) {
 }
 constexpr int SORT_TILE_MIN = 2048;   // status/scratch sizing: smallest tile of any configuration
 
-template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
+template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false>
 static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
   using S = PassSmem<Cfg, FROM_SEQ>;
-  auto kern = scatter_pass_kernel<Cfg, FROM_SEQ, BinFn, NextFn, HAS_NEXT>;
+  auto kern = scatter_pass_kernel<Cfg, FROM_SEQ, BinFn, NextFn, HAS_NEXT, PEER>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
   const int64_t tiles = ceil_div<int64_t>(n_upper, Cfg::TILE);
   if (tiles == 0) return KMG_OK;
@@ -471,12 +471,14 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
 // LSD passes first_pass..R-1 over record buffers.  has_next: only hist/gbase of first_pass exist, each
 // pass takes the next one's histogram as it writes (builds from records); otherwise every pass's
 // gbase is already there (builds from the sequence, hist_all_kernel).
+// final_pos (optional): the last pass writes its positions there instead of into the ping-pong buffer
+// (the array the index keeps), so `pa` is meaningless afterwards.
 static int sort_tail(SortScratch &sc, int k, int first_pass, bool has_next, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
-                     uint32_t *&pb, int64_t n_upper, cudaStream_t s) {
+                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr) {
   const int R = num_passes(k);
   for (int r = first_pass; r < R; ++r) {
     PassParams<DigitBin, DigitBin> P{};
-    P.keys_in = ka; P.pos_in = pa; P.keys_out = kb; P.pos_out = pb;
+    P.keys_in = ka; P.pos_in = pa; P.keys_out = kb; P.pos_out = (final_pos && r == R - 1) ? final_pos : pb;
     P.gbase = sc.gbase(r); P.hist_next = sc.hist(r + 1);
     P.status = sc.status; P.ticket = sc.ticket(r); P.epoch = (uint32_t)(r + 1);
     P.n_records = &sc.stats()->n;
@@ -791,7 +793,7 @@ static int ensure_lut(kmg_index *ix) {
 }
 
 static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, const uint64_t *d_keys,
-                        const int32_t *d_i, int64_t n, kmg_query **out, uint64_t *M) {
+                        const int32_t *d_i, int64_t n, kmg_query **out, uint64_t *M, const uint64_t *d_n = nullptr) {
   kmg_index *ix = const_cast<kmg_index *>(cix);
   cudaStream_t s = g_ctx.stream();
   kmg_query *q = new (std::nothrow) kmg_query();
@@ -818,10 +820,10 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
     KeyTable kt{ix->ukeys, ix->ustart, ix->lut, ix->U, uint64_t(1) << ix->lut_bits, ix->lut_shift};
     if (from_seq)
       LAUNCH("probe_match", s, probe_match_kernel<PROBE_THREADS, PROBE_ITEMS, true><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
-                                   sv, nullptr, nullptr, 0, kt, q->hit_i, q->hit_u, q->row_off, qs, status, ticket));
+                                   sv, nullptr, nullptr, 0, nullptr, kt, q->hit_i, q->hit_u, q->row_off, qs, status, ticket));
     else
       LAUNCH("probe_match_rec", s, probe_match_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
-                                       sv, d_keys, d_i, n, kt, q->hit_i, q->hit_u, q->row_off, qs, status, ticket));
+                                       sv, d_keys, d_i, n, d_n, kt, q->hit_i, q->hit_u, q->row_off, qs, status, ticket));
     QueryStats h;
     CU(cudaMemcpyAsync(&h, qs, sizeof h, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -1023,12 +1025,10 @@ extern "C" int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, i
     TRY(dalloc(&kb, (size_t)n, s));
     TRY(dalloc(&pb, (size_t)n, s));
     const unsigned hgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 16), (int64_t)g_ctx.sms * 8);
-    LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, sc.hist(0), DigitBin{0}));
+    LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, nullptr, sc.hist(0), DigitBin{0}));
     LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), &sc.stats()->n));
-    TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s));      // result in (ka, pa); may be the caller's arrays
-    // the index must own its positions
-    TRY(dalloc(&pfinal, (size_t)n, s));
-    CU(cudaMemcpyAsync(pfinal, pa, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    TRY(dalloc(&pfinal, (size_t)n, s));                    // the index must own its positions
+    TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s, pfinal));      // keys end in ka (may be the caller's array)
     TRY(finish_index(ix, sc, ka, pfinal, n, s));
     pfinal = nullptr;
     const int R = num_passes(k);
@@ -1047,5 +1047,354 @@ extern "C" int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, i
   scratch_free(sc, s);
   if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_free(ix); return rc; }
   *out = ix;
+  return KMG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// sharded build over peer memory: no host synchronisation between the halo and the finished index
+// ------------------------------------------------------------------------------------------------
+struct kmg_shard {
+  int device = 0;
+  DevSeq ds;
+  SeqView sv;
+};
+
+extern "C" int kmg_shard_open(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t s0, int64_t s1, int k, kmg_shard **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  TRY(ctx_init());
+  kmg_shard *sh = new (std::nothrow) kmg_shard();
+  if (!sh) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  sh->device = g_ctx.device;
+  int rc = shard_view(d_seq, g0, g1, L, s0, s1, k, g_ctx.stream(), &sh->ds, &sh->sv);
+  if (rc != KMG_OK) { delete sh; return rc; }
+  if (s0 + sh->sv.nstarts > (int64_t)INT32_MAX) { kmg_shard_close(sh); return fail(KMG_ERR_RANGE, "positions exceed int"); }
+  *out = sh;
+  return KMG_OK;
+}
+extern "C" int kmg_shard_close(kmg_shard *sh) {
+  if (!sh) return KMG_OK;
+  if (g_ctx.ready && g_ctx.device == sh->device) dfree(sh->ds.buf, g_ctx.stream());
+  else { cudaSetDevice(sh->device); g_arena[sh->device & 63].put(sh->ds.buf, nullptr, false); }
+  delete sh;
+  return KMG_OK;
+}
+extern "C" int kmg_shard_windows(const kmg_shard *sh, int64_t *nstarts) {
+  if (!sh || !nstarts) return fail(KMG_ERR_ARG, "NULL argument");
+  *nstarts = sh->sv.nstarts;
+  return KMG_OK;
+}
+
+extern "C" int kmg_shard_sample_keys(const kmg_shard *sh, int n, uint64_t *d_samples) {
+  if (!sh || n <= 0 || !d_samples) return fail(KMG_ERR_ARG, "bad sample request");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  LAUNCH("sample", s, sample_kernel<<<ceil_div(n, 256), 256, 0, s>>>(sh->sv, n, d_samples));
+  return KMG_OK;
+}
+
+__global__ void widen_counts_kernel(const uint32_t *hist, int n, uint64_t *out) {
+  if ((int)threadIdx.x < n) out[threadIdx.x] = hist[threadIdx.x];
+}
+
+extern "C" int kmg_shard_count(const kmg_shard *sh, const uint64_t *d_splitters, int nparts, uint64_t *d_counts) {
+  if (!sh || !d_counts) return fail(KMG_ERR_ARG, "NULL argument");
+  if (nparts < 1 || nparts > MAX_PEERS) return fail(KMG_ERR_ARG, "nparts must be in [1,%d]", MAX_PEERS);
+  if (nparts > 1 && !d_splitters) return fail(KMG_ERR_ARG, "splitters is NULL");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  uint32_t *hist = nullptr;
+  TRY(dalloc(&hist, (size_t)RADIX, s));
+  CU(cudaMemsetAsync(hist, 0, RADIX * 4, s));
+  if (sh->sv.nstarts > 0) {
+    OwnerBin ob{d_splitters, nparts};
+    const int64_t tiles = ceil_div<int64_t>(sh->sv.nstarts, HIST_TILE);
+    const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
+    LAUNCH("hist_seq_owner", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, OwnerBin><<<hgrid, HIST_THREADS, 0, s>>>(sh->sv, hist, ob));
+    prof_bytes("hist_seq_owner", (double)sh->sv.avail);
+  }
+  LAUNCH("widen_counts", s, widen_counts_kernel<<<1, MAX_PEERS, 0, s>>>(hist, nparts, d_counts));
+  dfree(hist, s);
+  return KMG_OK;
+}
+
+extern "C" int kmg_shard_scatter(const kmg_shard *sh, const uint64_t *d_splitters, int nparts, int rank,
+                                 void *const *peer_keys, void *const *peer_pos, uint64_t capacity,
+                                 const uint64_t *d_matrix, int32_t pos_add, uint64_t *d_info) {
+  if (!sh || !peer_keys || !peer_pos || !d_matrix || !d_info) return fail(KMG_ERR_ARG, "NULL argument");
+  if (nparts < 1 || nparts > MAX_PEERS || rank < 0 || rank >= nparts) return fail(KMG_ERR_ARG, "bad nparts/rank");
+  if (nparts > 1 && !d_splitters) return fail(KMG_ERR_ARG, "splitters is NULL");
+  if (capacity > (uint64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "capacity exceeds int coordinates");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  SortScratch sc;
+  PeerTable *tab = nullptr;
+  auto body = [&]() -> int {
+    TRY(scratch_alloc(sc, sh->sv.nstarts, s));
+    TRY(dalloc(&tab, 1, s));
+    PeerPtrs pp{};
+    for (int i = 0; i < nparts; ++i) { pp.keys[i] = (uint64_t *)peer_keys[i]; pp.pos[i] = (uint32_t *)peer_pos[i]; }
+    LAUNCH("owner_offsets", s, owner_offsets_kernel<<<1, RADIX, 0, s>>>(d_matrix, nparts, rank, capacity, pp, sc.gbase(0), tab, d_info));
+    if (sh->sv.nstarts == 0) return KMG_OK;
+    OwnerBin ob{d_splitters, nparts};
+    PassParams<OwnerBin, NoBin> P{};
+    P.sv = sh->sv;
+    P.gbase = sc.gbase(0); P.hist_next = nullptr;
+    P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
+    P.pos_add = (uint32_t)pos_add;
+    P.peer = tab;
+    P.bin = ob;
+    TRY((launch_pass_cfg<Cfg0, true, OwnerBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
+    prof_bytes("scatter_peer", (double)sh->sv.avail + 12.0 * (double)sh->sv.nstarts);
+    return KMG_OK;
+  };
+  int rc = body();
+  dfree(tab, s);
+  scratch_free(sc, s);
+  return rc;
+}
+
+__global__ void set_n_kernel(const uint64_t *info, uint64_t cap, uint64_t *n) { *n = info[0] < cap ? info[0] : cap; }
+
+// Index from the records peers scattered into (d_keys, d_pos): their number is on the device (d_info[0]).
+// Everything is sized by `capacity`; the one host synchronisation is the read of the finished index's stats.
+extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, const uint64_t *d_info, int k, kmg_index **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (capacity == 0 || capacity > (uint64_t)INT32_MAX || !d_keys || !d_pos || !d_info) return fail(KMG_ERR_ARG, "bad record arrays");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  kmg_index *ix = new (std::nothrow) kmg_index();
+  if (!ix) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  ix->device = g_ctx.device;
+  ix->k = k;
+  const int64_t n = (int64_t)capacity;
+  SortScratch sc;
+  uint64_t *ka = d_keys, *kb = nullptr;
+  uint32_t *pa = d_pos, *pb = nullptr, *pfinal = nullptr;
+  uint64_t h_info[2] = {0, 0};
+  auto body = [&]() -> int {
+    TRY(scratch_alloc(sc, n, s));
+    TRY(dalloc(&kb, (size_t)n, s));
+    TRY(dalloc(&pb, (size_t)n, s));
+    LAUNCH("set_n", s, set_n_kernel<<<1, 1, 0, s>>>(d_info, capacity, &sc.stats()->n));
+    const unsigned hgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 16), (int64_t)g_ctx.sms * 8);
+    LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, &sc.stats()->n, sc.hist(0), DigitBin{0}));
+    LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), nullptr));
+    TRY(dalloc(&pfinal, (size_t)n, s));
+    TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s, pfinal));
+    CU(cudaMemcpyAsync(h_info, d_info, sizeof h_info, cudaMemcpyDeviceToHost, s));
+    TRY(finish_index(ix, sc, ka, pfinal, n, s));            // synchronises
+    pfinal = nullptr;
+    const int R = num_passes(k);
+    prof_bytes("hist_rec", 8.0 * (double)ix->N);
+    if (R > 1) prof_bytes("sort_pass_hist", 24.0 * (double)ix->N * (R - 1));
+    prof_bytes("sort_pass", 24.0 * (double)ix->N);
+    return KMG_OK;
+  };
+  int rc = body();
+  if (ka != d_keys) dfree(ka, s);
+  if (kb != d_keys) dfree(kb, s);
+  if (pa != d_pos) dfree(pa, s);
+  if (pb != d_pos) dfree(pb, s);
+  dfree(pfinal, s);
+  scratch_free(sc, s);
+  if (rc == KMG_OK && h_info[1]) rc = fail(KMG_ERR_RANGE, "an owner received more than the exchange capacity of %llu records", (unsigned long long)capacity);
+  if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_free(ix); return rc; }
+  *out = ix;
+  return KMG_OK;
+}
+
+// ---- exchange buffers that other processes on the node can map (CUDA IPC over NVLink) ---------------------
+extern "C" int kmg_ipc_alloc(size_t bytes, void **dptr, void *handle) {
+  if (!dptr || !handle) return fail(KMG_ERR_ARG, "NULL argument");
+  TRY(ctx_init());
+  void *p = nullptr;
+  CU(cudaMalloc(&p, bytes ? bytes : 1));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(KMG_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle is 64 bytes");
+  memcpy(handle, &h, 64);
+  *dptr = p;
+  return KMG_OK;
+}
+extern "C" int kmg_ipc_free(void *dptr) {
+  if (dptr) { cudaDeviceSynchronize(); cudaFree(dptr); }
+  return KMG_OK;
+}
+extern "C" int kmg_ipc_open(const void *handle, void **dptr) {
+  if (!dptr || !handle) return fail(KMG_ERR_ARG, "NULL argument");
+  TRY(ctx_init());
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return KMG_OK;
+}
+extern "C" int kmg_ipc_close(void *dptr) {
+  if (dptr) cudaIpcCloseMemHandle(dptr);
+  return KMG_OK;
+}
+
+// match the (key, i) records peers scattered into (d_keys, d_i); their number is d_info[0] on the device
+extern "C" int kmg_query_received(const kmg_index *ix, const uint64_t *d_keys, const int32_t *d_i, uint64_t capacity,
+                                  const uint64_t *d_info, kmg_query **st, uint64_t *M) {
+  if (!st) return fail(KMG_ERR_ARG, "st is NULL");
+  *st = nullptr;
+  if (capacity == 0 || capacity > (uint64_t)INT32_MAX || !d_keys || !d_i || !d_info) return fail(KMG_ERR_ARG, "bad record arrays");
+  TRY(use_index(ix));
+  uint64_t h_info[2] = {0, 0};
+  CU(cudaMemcpyAsync(h_info, d_info, sizeof h_info, cudaMemcpyDeviceToHost, g_ctx.stream()));
+  SeqView sv{};
+  int rc = query_common(ix, false, sv, d_keys, d_i, (int64_t)capacity, st, M, d_info);
+  cudaStreamSynchronize(g_ctx.stream());
+  if (rc == KMG_OK && h_info[1]) {
+    kmg_query_free(*st);
+    *st = nullptr;
+    return fail(KMG_ERR_RANGE, "an owner received more than the exchange capacity of %llu records", (unsigned long long)capacity);
+  }
+  return rc;
+}
+
+
+// ---- halo + splitter sample in one exchange ------------------------------------------------------------
+// Pack of one rank (what every other rank may need from it): bytes [0,k-1) = its first k-1 bytes,
+// byte 40 = its last byte, then n ascending sample keys at byte 48.  Ranks all-gather the packs;
+// kmg_shard_open_packed then assembles the shard with its halo and selects the splitters, all on the device.
+constexpr int PACK_HDR = 48;
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+shard_pack_kernel(const uint8_t *__restrict__ own, int64_t n_own, int k, int n, uint8_t *__restrict__ pack) {
+  extern __shared__ uint64_t sk[];                       // n keys (n a power of two)
+  const int tid = threadIdx.x;
+  if (tid < PACK_HDR) {
+    uint8_t v = 0;
+    if (tid < k - 1 && tid < n_own) v = own[tid];
+    if (tid == 40 && n_own > 0) v = own[n_own - 1];
+    pack[tid] = v;
+  }
+  const int64_t nwin = n_own - k + 1 > 0 ? n_own - k + 1 : 1;
+  for (int i = tid; i < n; i += THREADS) {               // evenly spaced windows of the rank's own bytes; breakers are
+    const int64_t q = ((int64_t)i * nwin) / n;           // encoded like any byte (a sample only steers load balance)
+    uint64_t w = 0;
+    for (int j = 0; j < k; ++j) {
+      const int64_t o = q + j;
+      const uint8_t c = o < n_own ? own[o] : 0;
+      w = (w << 2) | ((c >> 1) & 3u);
+    }
+    sk[i] = w & key_mask(k);
+  }
+  __syncthreads();
+  for (int size = 2; size <= n; size <<= 1)              // bitonic sort, ascending
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < n / 2; i += THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));       // element with bit `stride` clear
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const uint64_t a = sk[lo], b = sk[hi];
+        if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+      }
+      __syncthreads();
+    }
+  uint64_t *out = reinterpret_cast<uint64_t *>(pack + PACK_HDR);
+  for (int i = tid; i < n; i += THREADS) out[i] = sk[i];
+}
+
+extern "C" int kmg_shard_pack_bytes(int n_samples) { return PACK_HDR + 8 * n_samples; }
+
+extern "C" int kmg_shard_pack(const void *d_own, int64_t n_own, int k, int n_samples, void *d_pack) {
+  if (!d_pack || (n_own > 0 && !d_own) || n_own < 0) return fail(KMG_ERR_ARG, "bad arguments");
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (n_samples < 2 || n_samples > 4096 || (n_samples & (n_samples - 1))) return fail(KMG_ERR_ARG, "n_samples must be a power of two in [2,4096]");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  LAUNCH("shard_pack", s, shard_pack_kernel<1024><<<1, 1024, (size_t)n_samples * 8, s>>>((const uint8_t *)d_own, n_own, k, n_samples, (uint8_t *)d_pack));
+  return KMG_OK;
+}
+
+// left byte and right halo of the padded shard, from the gathered packs
+__global__ void halo_fill_kernel(uint8_t *base, int64_t n_own, int need_right, bool left, int rank, int world, int64_t per, int64_t L,
+                                 int k, const uint8_t *__restrict__ allpack, int pack_bytes) {
+  const int t = threadIdx.x;
+  if (t == 0 && left) base[-1] = allpack[(size_t)(rank - 1) * pack_bytes + 40];
+  if (t < need_right) {                                  // byte s1 + t lives in the head of the first later rank that has it
+    int64_t off = t;
+    for (int r = rank + 1; r < world; ++r) {
+      const int64_t rs0 = min((int64_t)r * per, L), rs1 = min((int64_t)(r + 1) * per, L);
+      const int64_t have = min(rs1 - rs0, (int64_t)(k - 1));
+      if (off < have) { base[n_own + t] = allpack[(size_t)r * pack_bytes + off]; break; }
+      off -= have;
+    }
+  }
+}
+
+// splitter j = element number (j * total) / world of all samples in ascending order; every rank's list is sorted,
+// so an element's global position is a sum of binary searches (ties broken by (rank, index): a total order)
+__global__ void select_splitters_kernel(const uint8_t *__restrict__ allpack, int pack_bytes, int n, int world, uint64_t *__restrict__ spl) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * world) return;
+  const int r = e / n, i = e - r * n;
+  const uint64_t *mine = reinterpret_cast<const uint64_t *>(allpack + (size_t)r * pack_bytes + PACK_HDR);
+  const uint64_t x = mine[i];
+  int64_t g = i;
+  for (int o = 0; o < world; ++o) {
+    if (o == r) continue;
+    const uint64_t *lst = reinterpret_cast<const uint64_t *>(allpack + (size_t)o * pack_bytes + PACK_HDR);
+    int lo = 0, hi = n;                                  // o < r: elements <= x come first; o > r: elements < x
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const uint64_t v = lst[mid];
+      if (o < r ? v <= x : v < x) lo = mid + 1; else hi = mid;
+    }
+    g += lo;
+  }
+  const int64_t total = (int64_t)n * world;
+  for (int j = 1; j < world; ++j)
+    if (g == (j * total) / world) spl[j - 1] = x;
+}
+
+extern "C" int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L, int world, int rank, int k, int n_samples,
+                                     const void *d_allpack, kmg_shard **out, uint64_t *d_splitters) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || !d_allpack || (world > 1 && !d_splitters))
+    return fail(KMG_ERR_ARG, "bad world/rank/pack arguments");
+  const int64_t per = (L + world - 1) / world;
+  const int64_t s0 = std::min<int64_t>((int64_t)rank * per, L), s1 = std::min<int64_t>((int64_t)(rank + 1) * per, L);
+  if (n_own != s1 - s0 || (n_own > 0 && !d_own)) return fail(KMG_ERR_ARG, "rank %d must hold bytes [%lld,%lld) of the sequence", rank, (long long)s0, (long long)s1);
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  kmg_shard *sh = new (std::nothrow) kmg_shard();
+  if (!sh) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  sh->device = g_ctx.device;
+  const int pack_bytes = PACK_HDR + 8 * n_samples;
+  auto body = [&]() -> int {
+    const int64_t need_hi = std::min<int64_t>(L, s1 + k - 1);
+    const int64_t avail = std::max<int64_t>(0, need_hi - s0);
+    const size_t cap = 16 + (size_t)((avail + 15) / 16) * 16 + 16;
+    TRY(dalloc(&sh->ds.buf, cap, s));
+    sh->ds.base = sh->ds.buf + 16;
+    CU(cudaMemsetAsync(sh->ds.buf, 0, 16, s));
+    CU(cudaMemsetAsync(sh->ds.buf + cap - 32, 0, 32, s));
+    if (n_own > 0) CU(cudaMemcpyAsync(sh->ds.base, d_own, (size_t)n_own, cudaMemcpyDefault, s));
+    const int need_right = (int)(need_hi - s1);
+    if (need_right > 0 || s0 > 0)
+      LAUNCH("halo_fill", s, halo_fill_kernel<<<1, 32, 0, s>>>(sh->ds.base, n_own, need_right, s0 > 0 && n_own > 0, rank, world, per, L, k,
+                                                               (const uint8_t *)d_allpack, pack_bytes));
+    int64_t nstarts = std::min<int64_t>(s1, L - k + 1) - s0;
+    sh->sv.base = sh->ds.base; sh->sv.nstarts = nstarts > 0 ? nstarts : 0; sh->sv.avail = avail; sh->sv.s0 = s0; sh->sv.L = L; sh->sv.k = k;
+    if (s0 + sh->sv.nstarts > (int64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "positions exceed int");
+    if (world > 1)
+      LAUNCH("select_splitters", s, select_splitters_kernel<<<ceil_div(n_samples * world, 256), 256, 0, s>>>(
+                                        (const uint8_t *)d_allpack, pack_bytes, n_samples, world, d_splitters));
+    return KMG_OK;
+  };
+  int rc = body();
+  if (rc != KMG_OK) { kmg_shard_close(sh); return rc; }
+  *out = sh;
   return KMG_OK;
 }

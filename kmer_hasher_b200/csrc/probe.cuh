@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t find_key(const KeyTable &kt, uint64_t key) {
 template <int THREADS, int ITEMS, bool FROM_SEQ>
 __global__ void __launch_bounds__(THREADS)
 probe_match_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, const int32_t *__restrict__ i_in,
-                   int64_t n_in, const KeyTable kt, int32_t *__restrict__ hit_i, uint32_t *__restrict__ hit_u,
+                   int64_t n_in, const uint64_t *__restrict__ n_dev, const KeyTable kt, int32_t *__restrict__ hit_i, uint32_t *__restrict__ hit_u,
                    uint64_t *__restrict__ row_off, QueryStats *qs, Pair64 *status, uint32_t *ticket) {
   constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32;
   __shared__ TileCodes<FROM_SEQ ? TILE : 16> tc;
@@ -71,7 +71,7 @@ probe_match_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, const
   __syncthreads();
   const uint32_t tile = s_tile;
   const int64_t q0 = (int64_t)tile * TILE;
-  const int64_t total = FROM_SEQ ? sv.nstarts : n_in;
+  const int64_t total = FROM_SEQ ? sv.nstarts : (n_dev ? min((int64_t)*n_dev, n_in) : n_in);   // the count may only exist on the device
   if (q0 >= total) return;
 
   uint32_t u[ITEMS], cnt[ITEMS];

@@ -50,6 +50,16 @@ struct NoBin {
   __device__ __forceinline__ uint32_t operator()(uint64_t) const { return 0; }
 };
 
+// PEER mode (sharded build): bin b's records go to arrays of the GPU that owns key range b, which may
+// be peer memory mapped over NVLink; the pass writes them there directly (no staging, no all-to-all).
+constexpr int MAX_PEERS = 16;
+struct PeerTable {
+  uint64_t *keys[MAX_PEERS];
+  uint32_t *pos[MAX_PEERS];
+  int64_t delta[MAX_PEERS];   // (this rank's first slot in owner b's arrays) - (first index of bin b in this rank's stream)
+  uint64_t cap;               // records each destination array can hold
+};
+
 template <class BinFn, class NextFn>
 struct PassParams {
   SeqView sv;                 // FROM_SEQ source
@@ -63,6 +73,8 @@ struct PassParams {
   uint32_t *ticket;           // tile id dispenser (zero before launch)
   const uint64_t *n_records;  // record source: exact number of records (device scalar)
   uint32_t epoch;
+  uint32_t pos_add;           // FROM_SEQ: added to the 1-based start (k-1 turns it into the 1-based end of a query window)
+  const PeerTable *peer;      // PEER: per-bin destination arrays (own or NVLink-mapped peer memory)
   unsigned long long *trace;  // tuning runs only: 8 clock64 stamps per tile, or nullptr
   uint32_t dbg;               // tuning runs only (wrong results): 1 no look-back wait, 2 no global stores
   BinFn bin;
@@ -95,6 +107,7 @@ struct PassSmem {
   uint32_t next[RADIX];
   uint32_t scratch[8];
   uint32_t tile;
+  PeerTable peer;                                      // PEER mode only
   TileCodes<FROM_SEQ ? TILE : 16> tc;
 };
 
@@ -119,7 +132,7 @@ __device__ __forceinline__ uint32_t match_bin(uint32_t d, uint32_t active) {
 }
 
 // One tile.  FULL: every slot of the tile holds a valid record (no predicates on the hot path).
-template <class Cfg, bool FROM_SEQ, bool FULL, class BinFn, class NextFn, bool HAS_NEXT>
+template <class Cfg, bool FROM_SEQ, bool FULL, class BinFn, class NextFn, bool HAS_NEXT, bool PEER>
 __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, PassSmem<Cfg, FROM_SEQ> &sm,
                                           const uint32_t tile, const int64_t q0, const int64_t n_in,
                                           const uint32_t gbase, const bool special) {
@@ -314,7 +327,9 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
       }
       st_relaxed_u64(P.status + (size_t)tile * RADIX + tid, st_pack(ST_INCL, P.epoch, excl + cnt));
     }
-    sm.goff[tid] = (int32_t)((int64_t)gbase + (int64_t)excl - (int64_t)lstart);
+    int64_t go = (int64_t)gbase + (int64_t)excl - (int64_t)lstart;
+    if constexpr (PEER) go += tid < MAX_PEERS ? sm.peer.delta[tid] : 0;
+    sm.goff[tid] = (int32_t)go;
   }
   __syncthreads();
   KMG_STAMP(6);                                          // look-back finished for all bins
@@ -325,11 +340,16 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     const int s = j * THREADS + tid;
     if (FULL || s < (int)tile_count) {
       const uint64_t kk = sm.keys[s];
-      const int dst = sm.goff[P.bin(kk)] + s;
-      if (!(P.dbg & 2u)) {
-        P.keys_out[dst] = kk;
-        if constexpr (FROM_SEQ) P.pos_out[dst] = (uint32_t)(P.sv.s0 + q0 + 1) + sm.pos[s];   // 1-based start
-        else P.pos_out[dst] = sm.pos[s];
+      const uint32_t b = P.bin(kk);
+      const int dst = sm.goff[b] + s;
+      uint64_t *kout = P.keys_out;
+      uint32_t *pout = P.pos_out;
+      bool room = true;
+      if constexpr (PEER) { kout = sm.peer.keys[b]; pout = sm.peer.pos[b]; room = (uint64_t)dst < sm.peer.cap; }
+      if (room && !(P.dbg & 2u)) {
+        kout[dst] = kk;
+        if constexpr (FROM_SEQ) pout[dst] = (uint32_t)(P.sv.s0 + q0 + 1) + P.pos_add + sm.pos[s];   // 1-based start (+ pos_add)
+        else pout[dst] = sm.pos[s];
       }
       if constexpr (HAS_NEXT) atomicAdd(&sm.next[P.next(kk)], 1u);
     }
@@ -338,7 +358,7 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
 #undef KMG_STAMP
 }
 
-template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
+template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS)
 scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   using S = PassSmem<Cfg, FROM_SEQ>;
@@ -362,6 +382,10 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
     }
   }
   if (HAS_NEXT && tid < RADIX) sm.next[tid] = 0;
+  if constexpr (PEER) {
+    static_assert(sizeof(PeerTable) % 8 == 0, "copied as 64-bit words");
+    if (tid < sizeof(PeerTable) / 8) reinterpret_cast<uint64_t *>(&sm.peer)[tid] = reinterpret_cast<const uint64_t *>(P.peer)[tid];
+  }
   const uint32_t gbase = tid < RADIX ? __ldg(P.gbase + tid) : 0;   // 1 KB, L2-resident
   const int64_t n_in = FROM_SEQ ? P.sv.nstarts : (int64_t)*P.n_records;
   __syncthreads();
@@ -374,9 +398,9 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   if constexpr (FROM_SEQ) special = tile_pack<TILE, THREADS>(P.sv, q0, sm.tc);
   const bool touches_end = FROM_SEQ && (P.sv.s0 + q0 + TILE + P.sv.k > P.sv.L);
   if (q0 + TILE <= n_in && !special && !touches_end)
-    pass_tile<Cfg, FROM_SEQ, true, BinFn, NextFn, HAS_NEXT>(P, sm, tile, q0, n_in, gbase, special);
+    pass_tile<Cfg, FROM_SEQ, true, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special);
   else
-    pass_tile<Cfg, FROM_SEQ, false, BinFn, NextFn, HAS_NEXT>(P, sm, tile, q0, n_in, gbase, special);
+    pass_tile<Cfg, FROM_SEQ, false, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special);
 
   if constexpr (HAS_NEXT) {
     __syncthreads();
@@ -406,6 +430,39 @@ scan_hist_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ gbase
   }
   gbase[tid] = incl - v + add;
   if (n && tid == 0) *n = tot;
+}
+
+// ---- sharded build: where this rank's records of every owner go -------------------------------------
+// matrix[src][owner] = records rank `src` holds for `owner` (all-gathered).  One block of RADIX threads.
+//   gbase[b]  = first index of bin b in this rank's partitioned stream (exclusive scan of its own row);
+//   delta[b]  = (records ranks < rank send to b) - gbase[b]: the pass adds it to the stream index;
+//   info[0]   = records this rank receives, info[1] = 1 if some owner receives more than `cap`.
+struct PeerPtrs { uint64_t *keys[MAX_PEERS]; uint32_t *pos[MAX_PEERS]; };
+__global__ void __launch_bounds__(RADIX)
+owner_offsets_kernel(const uint64_t *__restrict__ matrix, int nparts, int rank, uint64_t cap, PeerPtrs ptrs,
+                     uint32_t *gbase, PeerTable *tab, uint64_t *info) {
+  const int b = threadIdx.x;
+  if (b == 0) {
+    info[1] = 0;
+    uint64_t run = 0;
+    for (int o = 0; o < RADIX; ++o) { gbase[o] = (uint32_t)run; if (o < nparts) run += matrix[(size_t)rank * nparts + o]; }
+  }
+  __syncthreads();
+  if (b < MAX_PEERS) {
+    uint64_t before = 0, total = 0;
+    if (b < nparts)
+      for (int src = 0; src < nparts; ++src) {
+        const uint64_t c = matrix[(size_t)src * nparts + b];
+        if (src < rank) before += c;
+        total += c;
+      }
+    tab->keys[b] = b < nparts ? ptrs.keys[b] : nullptr;
+    tab->pos[b] = b < nparts ? ptrs.pos[b] : nullptr;
+    tab->delta[b] = (int64_t)before - (int64_t)gbase[b];
+    if (b == rank) info[0] = total;
+    if (total > cap) info[1] = 1;
+  }
+  if (b == 0) tab->cap = cap;
 }
 
 // ---- all passes' histograms from the sequence, in one sweep -------------------------------------------
@@ -527,8 +584,9 @@ hist_seq_kernel(const SeqView sv, uint32_t *hist, BinFn bin) {
 // Record source.
 template <int THREADS, class BinFn>
 __global__ void __launch_bounds__(THREADS)
-hist_rec_kernel(const uint64_t *keys, int64_t n, uint32_t *hist, BinFn bin) {
+hist_rec_kernel(const uint64_t *keys, int64_t n_host, const uint64_t *n_dev, uint32_t *hist, BinFn bin) {
   __shared__ uint32_t sh[RADIX];
+  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;   // the count may only exist on the device
   for (int b = threadIdx.x; b < RADIX; b += THREADS) sh[b] = 0;
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS)

@@ -20,6 +20,7 @@ gloo (tests/test_dist_cpu.py plugs in a test double); the product engine is Cuda
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 import torch
@@ -62,6 +63,60 @@ class CudaEngine:
         self._lib.check(self.L.kmg_build_records(keys.data_ptr(), pos.data_ptr(), n, k, C.byref(h)))
         return KmerHash(h.value, k)
 
+    # ---- peer-memory path (NVLink P2P, no host synchronisation before the index is read) ----------------
+    def shard_open(self, shard, g0, g1, L, s0, s1, k):
+        h = C.c_void_p()
+        self._lib.check(self.L.kmg_shard_open(shard.data_ptr(), g0, g1, L, s0, s1, k, C.byref(h)))
+        return h
+
+    def shard_pack(self, own, k, n_samples):
+        pack = torch.empty(self.L.kmg_shard_pack_bytes(n_samples), dtype=torch.uint8, device=self.device)
+        self._lib.check(self.L.kmg_shard_pack(own.data_ptr(), own.numel(), k, n_samples, pack.data_ptr()))
+        return pack
+
+    def shard_open_packed(self, own, L, world, rank, k, n_samples, allpack):
+        h = C.c_void_p()
+        spl = torch.empty(max(world - 1, 1), dtype=torch.int64, device=self.device)
+        self._lib.check(self.L.kmg_shard_open_packed(own.data_ptr(), own.numel(), L, world, rank, k, n_samples,
+                                                     allpack.data_ptr(), C.byref(h), spl.data_ptr()))
+        return h, spl[:world - 1]
+
+    def shard_close(self, h):
+        self.L.kmg_shard_close(h)
+
+    def sample_keys(self, h, n):
+        out = torch.empty(n, dtype=torch.int64, device=self.device)
+        self._lib.check(self.L.kmg_shard_sample_keys(h, n, out.data_ptr()))
+        return out
+
+    def shard_count(self, h, splitters_dev, nparts):
+        out = torch.empty(nparts, dtype=torch.int64, device=self.device)
+        self._lib.check(self.L.kmg_shard_count(h, splitters_dev.data_ptr(), nparts, out.data_ptr()))
+        return out
+
+    def shard_scatter(self, h, splitters_dev, nparts, rank, slot, capacity, matrix, pos_add):
+        info = torch.empty(2, dtype=torch.int64, device=self.device)
+        self._lib.check(self.L.kmg_shard_scatter(h, splitters_dev.data_ptr(), nparts, rank, slot.peer_keys, slot.peer_pos,
+                                                 capacity, matrix.data_ptr(), pos_add, info.data_ptr()))
+        return info
+
+    def build_received(self, slot, capacity, info, k):
+        from . import KmerHash
+        h = C.c_void_p()
+        self._lib.check(self.L.kmg_build_received(slot.keys, slot.pos, capacity, info.data_ptr(), k, C.byref(h)))
+        return KmerHash(h.value, k)
+
+    def query_received(self, index, slot, capacity, info):
+        st, M = C.c_void_p(), C.c_uint64()
+        self._lib.check(self.L.kmg_query_received(index._handle(), slot.keys, slot.pos, capacity, info.data_ptr(),
+                                                  C.byref(st), C.byref(M)))
+        rows = torch.empty((M.value, 2), dtype=torch.int32, device=self.device)
+        try:
+            self._lib.check(self.L.kmg_query_emit(st, rows.data_ptr()))
+        finally:
+            self.L.kmg_query_free(st)
+        return rows
+
     def query_records(self, index, keys, coords, n):
         st, M = C.c_void_p(), C.c_uint64()
         self._lib.check(self.L.kmg_query_records(index._handle(), keys.data_ptr(), coords.data_ptr(), n,
@@ -72,6 +127,74 @@ class CudaEngine:
         finally:
             self.L.kmg_query_free(st)
         return rows
+
+
+_MARKS = None     # tuning runs: set to a list to collect (phase, cuda event, host time) marks of sharded_build_p2p
+
+
+class _Slot:
+    """One set of receive arrays: this rank's (keys, pos) and every rank's, as the scatter sees them."""
+    __slots__ = ("keys", "pos", "peer_keys", "peer_pos")
+
+
+class PeerExchange:
+    """Receive arrays for the fused partition + exchange, mapped into every rank of the node (CUDA IPC
+    over NVLink).  Two alternating slots: a peer may already scatter the next build's records while this
+    rank is still sorting the current one."""
+
+    def __init__(self, engine: "CudaEngine", capacity: int, group=None):
+        self.engine, self.capacity, self.group = engine, int(capacity), group
+        L, lib = engine.L, engine._lib
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self._own, self._opened = [], []
+        handles = torch.zeros(4 * 64, dtype=torch.uint8)
+        for i in range(4):                                   # slot0 keys, slot0 pos, slot1 keys, slot1 pos
+            p, hbuf = C.c_void_p(), (C.c_ubyte * 64)()
+            lib.check(L.kmg_ipc_alloc(self.capacity * (8 if i % 2 == 0 else 4), C.byref(p), hbuf))
+            self._own.append(p.value)
+            handles[i * 64:(i + 1) * 64] = torch.frombuffer(bytearray(hbuf), dtype=torch.uint8)
+        mine = handles.to(engine.device)
+        allh = torch.empty(world * 4 * 64, dtype=torch.uint8, device=engine.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy().reshape(world, 4, 64)
+        ptrs = [[0] * 4 for _ in range(world)]
+        for r in range(world):
+            for i in range(4):
+                if r == rank:
+                    ptrs[r][i] = self._own[i]
+                else:
+                    p = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(allh[r, i].tobytes())
+                    lib.check(L.kmg_ipc_open(hb, C.byref(p)))
+                    self._opened.append(p.value)
+                    ptrs[r][i] = p.value
+        self.slots = []
+        for sidx in range(2):
+            sl = _Slot()
+            sl.keys, sl.pos = self._own[2 * sidx], self._own[2 * sidx + 1]
+            sl.peer_keys = (C.c_void_p * world)(*[ptrs[r][2 * sidx] for r in range(world)])
+            sl.peer_pos = (C.c_void_p * world)(*[ptrs[r][2 * sidx + 1] for r in range(world)])
+            self.slots.append(sl)
+        self._turn = 0
+        self._token = torch.zeros(1, dtype=torch.int32, device=engine.device)
+
+    def next_slot(self) -> _Slot:
+        self._turn ^= 1
+        return self.slots[self._turn]
+
+    def barrier(self):
+        """Device-side: every rank's scatter has finished before any rank reads what it received."""
+        dist.all_reduce(self._token, group=self.group)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            self.engine.L.kmg_ipc_close(p)
+        dist.barrier(group=self.group)
+        for p in self._own:
+            self.engine.L.kmg_ipc_free(p)
+        self._opened, self._own = [], []
 
 
 def shard_bounds(L: int, world: int, rank: int, k: int):
@@ -95,17 +218,18 @@ def exchange_halo(own: torch.Tensor, L: int, k: int, rank: int, world: int, grou
     # left context: last byte of the left neighbour; right context: first k-1 bytes to the right.
     # (k-1 <= 31 bytes always come from one neighbour unless shards are shorter than k; handle the
     # general case by all-gathering fixed-size heads/tails, which is tiny.)
-    head = torch.zeros(k, dtype=torch.uint8, device=own.device)
-    tail = torch.zeros(1, dtype=torch.uint8, device=own.device)
+    ht = torch.zeros(k + 1, dtype=torch.uint8, device=own.device)     # [0,k): head, [k]: last byte
     n_head = min(k - 1, own.numel())
     if n_head:
-        head[:n_head] = own[:n_head]
+        ht[:n_head] = own[:n_head]
     if own.numel():
-        tail[0] = own[-1]
-    heads = [torch.empty_like(head) for _ in range(world)]
-    tails = [torch.empty_like(tail) for _ in range(world)]
-    dist.all_gather(heads, head, group=group)
-    dist.all_gather(tails, tail, group=group)
+        ht[k] = own[-1]
+    allht = torch.empty(world * (k + 1), dtype=torch.uint8, device=own.device)
+    dist.all_gather_into_tensor(allht, ht, group=group)
+    allht = allht.view(world, k + 1)
+    heads = [allht[r, :k] for r in range(world)]
+    tails = [allht[r, k:] for r in range(world)]
+    tail = ht[k:]
     parts = []
     if g0 < s0:
         parts.append(tails[rank - 1] if per >= 1 else tail)
@@ -130,14 +254,61 @@ def choose_splitters(samples_all: np.ndarray, world: int) -> np.ndarray:
     return s[idx].astype(np.uint64)
 
 
-class ShardedIndex:
-    """One rank's slice of a sharded index: the k-mers whose key falls in this rank's range."""
+def device_splitters(samples_all: torch.Tensor, world: int) -> torch.Tensor:
+    """choose_splitters on the device (keys are uint64 held in int64 tensors: flip the sign bit to sort)."""
+    flip = torch.tensor(-2**63, dtype=torch.int64, device=samples_all.device)
+    s, _ = torch.sort(samples_all ^ flip)
+    idx = torch.tensor([(i * s.numel()) // world for i in range(1, world)], dtype=torch.int64, device=s.device)
+    return (s[idx] ^ flip).contiguous()
 
-    def __init__(self, local, k, rank, world, U_all, N_all, splitters, engine):
+
+class ShardedIndex:
+    """One rank's slice of a sharded index: the k-mers whose key falls in this rank's range.
+    U_all / N_all (every rank's sizes, for the global 1-based k-mer index) are gathered on first use:
+    a collective, so all ranks must ask together."""
+
+    def __init__(self, local, k, rank, world, U_all, N_all, splitters, engine, splitters_dev=None, group=None):
         self.local, self.k, self.rank, self.world = local, k, rank, world
-        self.U_all, self.N_all, self.splitters, self.engine = U_all, N_all, splitters, engine
-        self.i_offset = int(sum(U_all[:rank]))          # global k-mer index = local + i_offset
-        self.U_total, self.N_total = int(sum(U_all)), int(sum(N_all))
+        self._U_all, self._N_all, self._splitters, self.engine = U_all, N_all, splitters, engine
+        self.splitters_dev, self.group = splitters_dev, group
+
+    def _gather_sizes(self):
+        if self._U_all is None:
+            U, N, _ = self.local.sizes
+            dev = self.engine.device
+            sizes = torch.tensor([U, N], dtype=torch.int64, device=dev)
+            allsz = torch.empty(self.world * 2, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allsz, sizes, group=self.group)
+            allsz = allsz.cpu().numpy().reshape(self.world, 2)
+            self._U_all, self._N_all = allsz[:, 0].tolist(), allsz[:, 1].tolist()
+
+    @property
+    def U_all(self):
+        self._gather_sizes()
+        return self._U_all
+
+    @property
+    def N_all(self):
+        self._gather_sizes()
+        return self._N_all
+
+    @property
+    def i_offset(self):                                   # global k-mer index = local + i_offset
+        return int(sum(self.U_all[:self.rank]))
+
+    @property
+    def U_total(self):
+        return int(sum(self.U_all))
+
+    @property
+    def N_total(self):
+        return int(sum(self.N_all))
+
+    @property
+    def splitters(self) -> np.ndarray:
+        if self._splitters is None:                        # the peer-memory build keeps them on the device
+            self._splitters = self.splitters_dev.cpu().numpy().view(np.uint64)
+        return self._splitters
 
     def free(self):
         self.local.free()
@@ -190,6 +361,74 @@ def sharded_build(own_bytes, L: int, k: int, engine, group=None, n_samples: int 
     return ShardedIndex(local, k, rank, world, all_sizes[:, 0].tolist(), all_sizes[:, 1].tolist(), splitters, engine)
 
 
+def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerExchange, group=None,
+                      n_samples: int = 2048) -> ShardedIndex:
+    """sharded_build with the exchange fused into the partitioning pass: records go straight into the
+    owners' arrays over NVLink (kmg_shard_scatter); the host never waits between the halo and the
+    finished index.  Falls back to sharded_build if an owner's share exceeds the exchange capacity."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def ev(name):
+        if _MARKS is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            _MARKS.append((name, e, time.perf_counter()))
+    ev("start")
+    own = own_bytes if isinstance(own_bytes, torch.Tensor) else engine.upload(np.asarray(own_bytes, np.uint8))
+    pack = engine.shard_pack(own, k, n_samples)              # halo bytes + sorted splitter sample: ONE exchange
+    allpack = torch.empty(world * pack.numel(), dtype=torch.uint8, device=engine.device)
+    dist.all_gather_into_tensor(allpack, pack, group=group)
+    ev("halo")
+    sh, spl = engine.shard_open_packed(own, L, world, rank, k, n_samples, allpack)
+    try:
+        ev("splitters")
+        counts = engine.shard_count(sh, spl, world)
+        matrix = torch.empty(world * world, dtype=torch.int64, device=engine.device)
+        dist.all_gather_into_tensor(matrix, counts, group=group)
+        ev("counts")
+        slot = xchg.next_slot()
+        info = engine.shard_scatter(sh, spl, world, rank, slot, xchg.capacity, matrix, 0)
+        ev("scatter")
+        xchg.barrier()
+        ev("barrier")
+        from ._lib import KmgError
+        try:
+            local = engine.build_received(slot, xchg.capacity, info, k)
+        except KmgError as e:
+            if e.code != -3:
+                raise
+            local = None
+    finally:
+        engine.shard_close(sh)
+    ev("built")
+    if local is None:          # an owner overflowed; every rank saw the same flag (it is computed from the shared
+        return sharded_build(own, L, k, engine, group)       # count matrix), so all take the general path together
+    return ShardedIndex(local, k, rank, world, None, None, None, engine, splitters_dev=spl, group=group)
+
+
+def sharded_query_p2p(index: ShardedIndex, own_query_bytes, Lq: int, k: int, xchg: PeerExchange, group=None) -> torch.Tensor:
+    """sharded_query with query (key, i) records scattered straight to the key's owner over NVLink."""
+    engine = index.engine
+    world, rank = index.world, index.rank
+    s0, s1, _, _ = shard_bounds(Lq, world, rank, k)
+    own = own_query_bytes if isinstance(own_query_bytes, torch.Tensor) else engine.upload(np.asarray(own_query_bytes, np.uint8))
+    shard, g0, g1 = exchange_halo(own, Lq, k, rank, world, group)
+    spl = index.splitters_dev
+    if spl is None:
+        spl = torch.from_numpy(np.ascontiguousarray(index.splitters).view(np.int64)).to(engine.device)
+    sh = engine.shard_open(shard, g0, g1, Lq, s0, s1, k)
+    try:
+        counts = engine.shard_count(sh, spl, world)
+        matrix = torch.empty(world * world, dtype=torch.int64, device=engine.device)
+        dist.all_gather_into_tensor(matrix, counts, group=group)
+        slot = xchg.next_slot()
+        info = engine.shard_scatter(sh, spl, world, rank, slot, xchg.capacity, matrix, k - 1)   # 1-based END (src/kmer_pos.c:127)
+        xchg.barrier()
+        return engine.query_received(index.local, slot, xchg.capacity, info)
+    finally:
+        engine.shard_close(sh)
+
+
 def sharded_query(index: ShardedIndex, own_query_bytes, Lq: int, k: int, group=None) -> torch.Tensor:
     """Collective seq.kmer.pos against a sharded index: every rank passes its slice of the query.
     Query windows are routed to the key's owner exactly like index records; each owner returns its
@@ -236,7 +475,8 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     own_host = torch.from_numpy(own_pin)                   # page-locked by kmg_host_alloc: async DMA source
     own_dev = own_host.to(dev)
 
-    ix = sharded_build(own_dev, Ltot, k, engine)
+    xchg = PeerExchange(engine, int(L * 1.25) + 4096)      # receive arrays mapped into every rank (NVLink P2P)
+    ix = sharded_build_p2p(own_dev, Ltot, k, engine, xchg)
     U, N, _ = ix.local.sizes
     ntot = ix.N_total
     ix.free()
@@ -245,12 +485,12 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     pos_pin, cnt_pin = kh.pinned_empty((max(N, 1), 2), np.int32), kh.pinned_empty(max(U, 1), np.int32)
 
     def step_device():
-        ix = sharded_build(own_dev, Ltot, k, engine)
+        ix = sharded_build_p2p(own_dev, Ltot, k, engine, xchg)
         kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos_dev, "count": cnt_dev})
         ix.free()
 
     def step_e2e():
-        ix = sharded_build(own_host.to(dev, non_blocking=True), Ltot, k, engine)
+        ix = sharded_build_p2p(own_host.to(dev, non_blocking=True), Ltot, k, engine, xchg)
         kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos_pin, "count": cnt_pin})
         ix.free()
 
@@ -284,11 +524,12 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     sizes = torch.tensor([N, U], dtype=torch.int64, device=dev)
     all_sizes = [torch.empty_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
+    xchg.close()
     if rank != 0:
         return None
     all_sizes = torch.stack(all_sizes).cpu().numpy()
     roof = None
-    sp = prof.get("sort_pass")
+    sp = prof.get("sort_pass_hist") or prof.get("sort_pass")
     if sp and sp[0] > 0:
         ach = sp[2] / (sp[0] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "sort_pass (rank 0)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
@@ -300,12 +541,13 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": w["name"] + f" per GPU; {world} shards of one {Ltot}-base sequence, (key,pos) records "
-                       "routed to key-range owners by one NCCL all-to-all", "k": k, "bases": Ltot, "kmers": int(ntot),
+                       "written straight into the key-range owners' arrays over NVLink by the partitioning pass (peer memory, no all-to-all)", "k": k, "bases": Ltot, "kmers": int(ntot),
                        "per_rank_kmers": all_sizes[:, 0].tolist(), "per_rank_distinct": all_sizes[:, 1].tolist(),
                        "l2": "inputs_exceed_l2"},
             "e2e": {"value": ntot / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(L * world),
                     "d2h_bytes_per_step": int((8 * all_sizes[:, 0] + 4 * all_sizes[:, 1]).sum()), "ms_per_step": ms_e2e,
                     "what": "per rank: pinned host shard -> device, sharded build, kmer_pos(2|8) into pinned host arrays"},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": None,
-            "exchange": {"bytes_per_gpu_per_step": exchanged, "what": "12-byte records leaving each GPU (estimate, uniform owners)"},
+            "exchange": {"bytes_per_gpu_per_step": exchanged, "what": "12-byte records leaving each GPU over NVLink (estimate, uniform owners)",
+                         "kernel": "scatter_peer", "ms_per_step": (prof.get("scatter_peer", (0, 0, 0))[0] / steps)},
             "kernels": kernels}

@@ -323,3 +323,102 @@ def test_sharded_engine_single_process(kh, oracle, world, k):
     rows = np.concatenate(rows_all)
     rows = rows[np.argsort(rows[:, 0], kind="stable")]
     assert np.array_equal(rows.ravel(), qo)
+
+
+@pytest.mark.parametrize("world,k,L", [(2, 32, 500_000), (3, 21, 500_000), (8, 12, 500_000), (8, 32, 100), (5, 7, 23)])
+def test_peer_scatter_single_process(kh, oracle, world, k, L):
+    """The fused partition + exchange (kmg_shard_count / kmg_shard_scatter / kmg_build_received /
+    kmg_query_received) with the ranks played one after another on one GPU: every "peer" array lives on
+    this device, so the scatter's addressing (lower ranks first inside each owner's arrays), the
+    device-side counts and the overflow flag are checked without NVLink."""
+    import ctypes as C
+    import torch
+    from kmer_hasher_b200 import dist as kdist, synth, _lib
+    dev = torch.device("cuda", 0)
+    eng = kdist.CudaEngine(dev)
+    seq = synth.config_c3(L, tail_k=k) if L > 1000 else synth.generate(L, 11, n_single=2)
+    per = (L + world - 1) // world
+    if L > 1000:
+        seq[per - 2:per + 1] = np.frombuffer(b"nAC", np.uint8)      # breaker at the first cut
+    whole = oracle.build(seq, k)
+    want = whole.extract(2 | 8)
+    # halo + splitter sample in one exchange (kmg_shard_pack -> "all-gather" -> kmg_shard_open_packed)
+    ns = 512 if L > 1000 else 4
+    owns = [eng.upload(seq[min(r * per, L):min((r + 1) * per, L)]) for r in range(world)]
+    packs = [eng.shard_pack(o, k, ns) for o in owns]
+    allpack = torch.cat(packs)
+    handles, spls = [], []
+    for r in range(world):
+        h, spl_r = eng.shard_open_packed(owns[r], L, world, r, k, ns, allpack)
+        handles.append(h); spls.append(spl_r.cpu().numpy().view(np.uint64))
+    smp = np.concatenate([p.cpu().numpy()[48:].view(np.uint64) for p in packs])
+    for r in range(world):
+        assert np.all(np.diff(packs[r].cpu().numpy()[48:].view(np.uint64).astype(np.float64)) >= 0)
+        assert np.array_equal(spls[r], kdist.choose_splitters(smp, world))
+    spl = torch.from_numpy(spls[0].view(np.int64).copy()).to(dev)
+    assert np.array_equal(kdist.device_splitters(torch.from_numpy(smp.view(np.int64).copy()).to(dev), world).cpu().numpy().view(np.uint64), spls[0])
+    matrix = torch.cat([eng.shard_count(h, spl, world) for h in handles])
+    m = matrix.cpu().numpy().reshape(world, world)
+    assert m.sum() == whole.N
+    cap = int(m.sum(axis=0).max()) + 7
+
+    def scatter_all(cap, pos_add, hs, mat):
+        keys = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(world)]
+        pos = [torch.zeros(cap, dtype=torch.int32, device=dev) for _ in range(world)]
+        infos = []
+        for r in range(world):
+            sl = kdist._Slot()
+            sl.keys, sl.pos = keys[r].data_ptr(), pos[r].data_ptr()
+            sl.peer_keys = (C.c_void_p * world)(*[t.data_ptr() for t in keys])
+            sl.peer_pos = (C.c_void_p * world)(*[t.data_ptr() for t in pos])
+            infos.append((sl, eng.shard_scatter(hs[r], spl, world, r, sl, cap, mat, pos_add)))
+        return keys, pos, infos
+
+    keys, pos, infos = scatter_all(cap, 0, handles, matrix)
+    got_keys, got_cnt, got_pos, offs, owners = [], [], [], 0, []
+    for o, (sl, info) in enumerate(infos):
+        assert info.cpu().tolist() == [int(m[:, o].sum()), 0]
+        ix = eng.build_received(sl, cap, info, k)
+        U, N, _ = ix.sizes
+        assert N == m[:, o].sum()
+        e = kh.kmer_pos(ix, 2 | 8)
+        got_keys.append(kh.kmer_keys(ix)); got_cnt.append(e["count"])
+        p = e["pos"].copy(); p[:, 0] += offs; got_pos.append(p)
+        offs += U
+        owners.append(ix)
+    assert np.array_equal(np.concatenate(got_keys), want["keys"])
+    assert np.array_equal(np.concatenate(got_cnt), want["count"])
+    assert np.array_equal(np.concatenate(got_pos).ravel(), want["pos"])
+
+    if L <= 1000:
+        for ix in owners:
+            ix.free()
+        for h in handles:
+            eng.shard_close(h)
+        return
+    # routed probe through the same scatter (coordinates = 1-based end of the query window)
+    q = synth.config_c4_query(seq, 120_000)
+    qo = whole.query(q, k)
+    Lq = len(q)
+    qh = []
+    for r in range(world):
+        s0, s1, g0, g1 = kdist.shard_bounds(Lq, world, r, k)
+        qh.append(eng.shard_open(eng.upload(q[g0:g1]), g0, g1, Lq, s0, s1, k))
+    qmat = torch.cat([eng.shard_count(h, spl, world) for h in qh])
+    qcap = int(qmat.cpu().numpy().reshape(world, world).sum(axis=0).max()) + 1
+    qkeep_k, qkeep_p, qinfos = scatter_all(qcap, k - 1, qh, qmat)      # keep the receive arrays alive
+    rows = np.concatenate([eng.query_received(owners[o], sl, qcap, info).cpu().numpy() for o, (sl, info) in enumerate(qinfos)])
+    rows = rows[np.argsort(rows[:, 0], kind="stable")]
+    assert np.array_equal(rows.ravel(), qo)
+
+    # an exchange that is too small is reported, not silently truncated
+    small = int(m.sum(axis=0).max()) - 1
+    keep2_k, keep2_p, infos2 = scatter_all(small, 0, handles, matrix)
+    big = int(np.argmax(m.sum(axis=0)))
+    assert infos2[big][1].cpu().tolist()[1] == 1
+    with pytest.raises(_lib.KmgError):
+        eng.build_received(infos2[big][0], small, infos2[big][1], k)
+    for ix in owners:
+        ix.free()
+    for h in handles + qh:
+        eng.shard_close(h)
