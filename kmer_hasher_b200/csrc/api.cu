@@ -326,8 +326,8 @@ struct kmg_index {
   uint32_t *pos = nullptr;      // [N]
   // made on first use
   std::mutex mu;
-  uint32_t *lut = nullptr;
-  int lut_bits = 0, lut_shift = 0;
+  uint4 *hash = nullptr;        // key table of the probe (probe.cuh), made on the first query
+  uint64_t hash_bmask = 0;
   uint32_t *multi_u = nullptr;
   uint64_t *pair_off = nullptr;
 };
@@ -335,7 +335,7 @@ struct kmg_query {
   const kmg_index *idx = nullptr;
   uint64_t H = 0, M = 0;
   int32_t *hit_i = nullptr;
-  uint32_t *hit_u = nullptr;
+  uint32_t *hit_start = nullptr;
   uint64_t *row_off = nullptr;
 };
 
@@ -592,7 +592,7 @@ extern "C" int kmg_free(kmg_index *ix) {
   cudaSetDevice(ix->device);
   const bool mine = g_ctx.ready && g_ctx.device == ix->device;
   if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
-  void *ptrs[6] = {ix->ukeys, ix->ustart, ix->pos, ix->lut, ix->multi_u, ix->pair_off};
+  void *ptrs[6] = {ix->ukeys, ix->ustart, ix->pos, ix->hash, ix->multi_u, ix->pair_off};
   for (void *p : ptrs) g_arena[ix->device & 63].put(p, nullptr, true);
   cudaGetLastError();
   if (prev >= 0) cudaSetDevice(prev);
@@ -772,23 +772,20 @@ extern "C" int kmg_pairs(const kmg_index *ix, int32_t *out) {
 // ------------------------------------------------------------------------------------------------
 // probe
 // ------------------------------------------------------------------------------------------------
-static int ensure_lut(kmg_index *ix) {
+static int ensure_hash(kmg_index *ix) {
   std::lock_guard<std::mutex> g(ix->mu);
-  if (ix->lut || ix->U == 0) return KMG_OK;
+  if (ix->hash || ix->U == 0) return KMG_OK;
   cudaStream_t s = g_ctx.stream();
-  int lg = 0;
-  while ((uint64_t(1) << (lg + 1)) <= ix->U) ++lg;           // floor(log2 U)
-  int bits = lg - 1;                                           // ~2-4 keys per bucket
-  bits = std::max(1, std::min(bits, std::min(2 * ix->k, 27)));
-  const uint64_t nb = uint64_t(1) << bits;
-  uint32_t *lut = nullptr;
-  TRY(dalloc(&lut, nb + 1, s));
-  const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(ix->U, 256), (uint64_t)g_ctx.sms * 16);
-  const int shift = 2 * ix->k - bits;
-  LAUNCH("lut", s, lut_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->U, shift, nb, lut));
+  uint64_t cap = 4 * BUCKET_SLOTS;
+  while (cap < 2 * ix->U) cap <<= 1;                          // load <= 0.5
+  uint4 *slots = nullptr;
+  TRY(dalloc(&slots, cap, s));
+  CU(cudaMemsetAsync(slots, 0, cap * sizeof(uint4), s));
+  const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(ix->U, 256), (uint64_t)g_ctx.sms * 32);
+  LAUNCH("hash_insert", s, hash_insert_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, KeyHash{slots, cap / BUCKET_SLOTS - 1}));
   CU(cudaStreamSynchronize(s));
-  ix->lut = lut; ix->lut_bits = bits; ix->lut_shift = shift;
-  prof_bytes("lut", 8.0 * ix->U + 4.0 * nb);
+  ix->hash = slots; ix->hash_bmask = cap / BUCKET_SLOTS - 1;
+  prof_bytes("hash_insert", 12.0 * ix->U + 16.0 * ix->U);
   return KMG_OK;
 }
 
@@ -801,15 +798,16 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
   q->idx = ix;
   const int64_t total = from_seq ? sv.nstarts : n;
   if (total <= 0 || ix->U == 0) { *out = q; if (M) *M = 0; return KMG_OK; }
-  int rc = ensure_lut(ix);
+  int rc = ensure_hash(ix);
   if (rc != KMG_OK) { delete q; return rc; }
   QueryStats *qs = nullptr;
   Pair64 *status = nullptr;
   uint32_t *ticket = nullptr;
+  uint2 *found = nullptr;
   auto body = [&]() -> int {
     const uint64_t tiles = ceil_div<uint64_t>((uint64_t)total, PROBE_TILE);
     TRY(dalloc(&q->hit_i, (size_t)total, s));
-    TRY(dalloc(&q->hit_u, (size_t)total, s));
+    TRY(dalloc(&q->hit_start, (size_t)total, s));
     TRY(dalloc(&q->row_off, (size_t)total, s));
     TRY(dalloc(&qs, 1, s));
     TRY(dalloc(&status, tiles, s));
@@ -817,13 +815,18 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
     CU(cudaMemsetAsync(qs, 0, sizeof(QueryStats), s));
     CU(cudaMemsetAsync(status, 0, tiles * sizeof(Pair64), s));
     CU(cudaMemsetAsync(ticket, 0, 4, s));
-    KeyTable kt{ix->ukeys, ix->ustart, ix->lut, ix->U, uint64_t(1) << ix->lut_bits, ix->lut_shift};
-    if (from_seq)
-      LAUNCH("probe_match", s, probe_match_kernel<PROBE_THREADS, PROBE_ITEMS, true><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
-                                   sv, nullptr, nullptr, 0, nullptr, kt, q->hit_i, q->hit_u, q->row_off, qs, status, ticket));
-    else
-      LAUNCH("probe_match_rec", s, probe_match_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
-                                       sv, d_keys, d_i, n, d_n, kt, q->hit_i, q->hit_u, q->row_off, qs, status, ticket));
+    KeyHash kt{ix->hash, ix->hash_bmask};
+    TRY(dalloc(&found, (size_t)total, s));
+    const unsigned ltiles = (unsigned)ceil_div<uint64_t>((uint64_t)total, PROBE_TILE);
+    if (from_seq) {
+      LAUNCH("probe_lookup", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, true><<<ltiles, PROBE_THREADS, 0, s>>>(sv, nullptr, 0, nullptr, kt, found));
+      LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, PROBE_ITEMS, true><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+                                     found, sv.s0 + sv.k, nullptr, total, nullptr, q->hit_i, q->hit_start, q->row_off, qs, status, ticket));
+    } else {
+      LAUNCH("probe_lookup_rec", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<ltiles, PROBE_THREADS, 0, s>>>(sv, d_keys, n, d_n, kt, found));
+      LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+                                     found, 0, d_i, n, d_n, q->hit_i, q->hit_start, q->row_off, qs, status, ticket));
+    }
     QueryStats h;
     CU(cudaMemcpyAsync(&h, qs, sizeof h, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -831,9 +834,11 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
     return KMG_OK;
   };
   rc = body();
-  dfree(qs, s); dfree(status, s); dfree(ticket, s);
+  dfree(qs, s); dfree(status, s); dfree(ticket, s); dfree(found, s);
   if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_query_free(q); return rc; }
-  prof_bytes(from_seq ? "probe_match" : "probe_match_rec", (from_seq ? (double)sv.avail : 12.0 * total) + 8.0 * ix->U + 16.0 * q->H);
+  // a lookup moves one 128-byte line of HBM (measured: tools/micro/gups.cu), whatever it uses of it
+  prof_bytes(from_seq ? "probe_lookup" : "probe_lookup_rec", (from_seq ? (double)sv.avail : 8.0 * total) + 128.0 * total + 8.0 * total);
+  prof_bytes("probe_compact", 8.0 * total + 16.0 * q->H);
   *out = q;
   if (M) *M = q->M;
   return KMG_OK;
@@ -873,12 +878,12 @@ extern "C" int kmg_query_emit_chunk(kmg_query *q, uint64_t first, uint64_t n, in
   if (!out) return fail(KMG_ERR_ARG, "out is NULL");
   const kmg_index *ix = q->idx;
   const int32_t *hit_i = q->hit_i;
-  const uint32_t *hit_u = q->hit_u, *ustart = ix->ustart, *pos = ix->pos;
+  const uint32_t *hit_start = q->hit_start, *pos = ix->pos;
   const uint64_t *row_off = q->row_off;
   const uint64_t H = q->H;
   int rc = stream_rows(n, 8, out, CHUNK_BYTES / 8, [=](uint64_t f, uint64_t rows, void *dst, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
-    LAUNCH("probe_emit", s, probe_emit_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(hit_i, hit_u, row_off, H, ustart, pos, first + f, rows, (int2 *)dst));
+    LAUNCH("probe_emit", s, probe_emit_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(hit_i, hit_start, row_off, H, pos, first + f, rows, (int2 *)dst));
     return KMG_OK;
   });
   prof_bytes("probe_emit", 12.0 * n);
@@ -894,7 +899,7 @@ extern "C" int kmg_query_free(kmg_query *q) {
   cudaSetDevice(dev);
   const bool mine = g_ctx.ready && g_ctx.device == dev;
   if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
-  void *ptrs[3] = {q->hit_i, q->hit_u, q->row_off};
+  void *ptrs[3] = {q->hit_i, q->hit_start, q->row_off};
   for (void *p : ptrs) g_arena[dev & 63].put(p, nullptr, true);
   cudaGetLastError();
   delete q;

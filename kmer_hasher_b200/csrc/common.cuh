@@ -36,6 +36,11 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// one 32-byte sector in ONE request (sm_100 256-bit load); p must be 32-byte aligned
+__device__ __forceinline__ void ld_stream_sector(const uint4 *p, uint4 &a, uint4 &b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
 __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
   uint64_t r;
   asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));

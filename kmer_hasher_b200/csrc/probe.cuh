@@ -1,8 +1,11 @@
-// probe.cuh -- seq.kmer.pos: match query windows against the sorted distinct keys.
+// probe.cuh -- seq.kmer.pos: match query windows against the index.
 //
-// Replaces seq_kmer_positions (src/kmer_pos.c:110-136): kmer_pos/kh_get (:55-60) becomes a prefix
-// table + short binary search over ukeys[]; pair_positions_push (:101-108) becomes a count pass, a
-// chained 64-bit scan and a load-balanced emit, so rows come out ordered by query position then
+// Replaces seq_kmer_positions (src/kmer_pos.c:110-136).  kmer_pos/kh_get (:55-60) is one random DRAM
+// probe per query window in the reference and stays one here: the distinct keys are put (once per
+// index, on first use) into an open-addressing table of 16-byte slots {key, first position slot,
+// count}, two slots per 32-byte sector, load <= 0.5, so a lookup is one sector read in the common
+// case and needs no second access for the list length.  pair_positions_push (:101-108) becomes a count
+// pass, a chained 64-bit scan and a load-balanced emit, so rows come out ordered by query position then
 // index position exactly as the reference pushes them.
 #pragma once
 #include "common.cuh"
@@ -17,53 +20,132 @@ struct QueryStats {
   uint64_t M;   // result rows
 };
 
-// Prefix table over the distinct keys: lut[b] = first u whose key >> shift is >= b, b in [0, 2^B].
-__global__ void lut_kernel(const uint64_t *__restrict__ ukeys, uint64_t U, int shift, uint64_t nbuckets,
-                           uint32_t *__restrict__ lut) {
-  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t p = ukeys[u] >> shift;
-    const uint64_t from = u == 0 ? 0 : (ukeys[u - 1] >> shift) + 1;
-    for (uint64_t b = from; b <= p; ++b) lut[b] = (uint32_t)u;
-    if (u == U - 1)
-      for (uint64_t b = p + 1; b <= nbuckets; ++b) lut[b] = (uint32_t)U;
-  }
-}
-
-struct KeyTable {
-  const uint64_t *ukeys;
-  const uint32_t *ustart;
-  const uint32_t *lut;
-  uint64_t U;
-  uint64_t nbuckets;   // 2^B
-  int shift;
+// ---- key table -------------------------------------------------------------------------------------------
+// slot = uint4 {key lo, key hi, start, count}; count == 0 marks an empty slot (a stored k-mer has >= 1
+// position).  Two slots form a 32-byte bucket = one memory request; a key lives in the first bucket at or
+// after its home bucket that had room, so a bucket with an empty slot ends the search.  Measured on B200
+// (tools/micro/gups.cu, profiles/): a random read costs a whole 128-byte line of DRAM traffic whatever its
+// size and the rate is bound by requests, 46 G/s for 32-byte requests = HBM peak in lines; an overflow
+// bucket is in the same line three times out of four and then comes from L2.
+constexpr int BUCKET_SLOTS = 2;
+struct KeyHash {
+  uint4 *slots;
+  uint64_t bmask;   // buckets - 1 (a power of two; 2 * buckets >= 2 U)
 };
 
-// index of `key` among the distinct keys, or 0xFFFFFFFF
-__device__ __forceinline__ uint32_t find_key(const KeyTable &kt, uint64_t key) {
-  const uint64_t b = kt.shift >= 64 ? 0 : (key >> kt.shift);
-  if (b >= kt.nbuckets) return 0xFFFFFFFFu;
-  uint32_t lo = __ldg(kt.lut + b), hi = __ldg(kt.lut + b + 1);
-  const uint32_t end = hi;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    const uint64_t v = __ldg(kt.ukeys + mid);
-    if (v < key) lo = mid + 1; else hi = mid;
-  }
-  if (lo < end && __ldg(kt.ukeys + lo) == key) return lo;
-  return 0xFFFFFFFFu;
+__device__ __forceinline__ uint64_t hash64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
 }
 
-// Count pass + ordered compaction of the hits + chained scan of their row counts.
-//   FROM_SEQ: windows of the query sequence, coordinate i = 1-based END of the window
-//             (src/kmer_pos.c:127,132: `i` is one past the window);
-//   else    : pre-encoded (key, i) records.
+// Distinct keys only; a slot is claimed by a CAS on its count word.  Nobody reads the table before this
+// kernel has finished, so key/start can be written after the claim.
+__global__ void hash_insert_kernel(const uint64_t *__restrict__ ukeys, const uint32_t *__restrict__ ustart, uint64_t U, KeyHash kh) {
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = ukeys[u];
+    const uint32_t start = ustart[u], count = ustart[u + 1] - start;
+    uint64_t b = hash64(key) & kh.bmask;
+    bool placed = false;
+    while (!placed) {
+#pragma unroll
+      for (int j = 0; j < BUCKET_SLOTS; ++j) {
+        if (placed) break;
+        uint32_t *slot = reinterpret_cast<uint32_t *>(kh.slots + b * BUCKET_SLOTS + j);
+        if (atomicCAS(slot + 3, 0u, count) == 0u) {
+          slot[0] = (uint32_t)key; slot[1] = (uint32_t)(key >> 32); slot[2] = start;
+          placed = true;
+        }
+      }
+      b = (b + 1) & kh.bmask;
+    }
+  }
+}
+
+// (start, count) of `key`, or count 0.  s0, s1: the key's home bucket `b`, already loaded.
+__device__ __forceinline__ uint2 resolve_key(const KeyHash &kh, uint64_t key, uint64_t b, uint4 s0, uint4 s1) {
+  const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+  while (true) {
+    if (s0.w != 0 && s0.x == klo && s0.y == khi) return make_uint2(s0.z, s0.w);
+    if (s1.w != 0 && s1.x == klo && s1.y == khi) return make_uint2(s1.z, s1.w);
+    if (s0.w == 0 || s1.w == 0) return make_uint2(0u, 0u);
+    b = (b + 1) & kh.bmask;
+    ld_stream_sector(kh.slots + b * BUCKET_SLOTS, s0, s1);
+  }
+}
+
+// ---- pass 1: look every query window up; write (first position slot, count) per window, count 0 = no hit ----
+//   FROM_SEQ: windows of the query sequence;  else: pre-encoded keys.
+// A thread owns ITEMS consecutive windows (keys roll from one to the next) and has BATCH table requests in
+// flight at a time; there is no block-wide step after the tile is packed, so the kernel runs at the
+// random-access rate of HBM.
+template <int THREADS, int ITEMS, bool FROM_SEQ>
+__global__ void __launch_bounds__(THREADS, 3)
+probe_lookup_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, int64_t n_in, const uint64_t *__restrict__ n_dev,
+                    const KeyHash kh, uint2 *__restrict__ found) {
+  constexpr int TILE = THREADS * ITEMS;
+  __shared__ TileCodes<FROM_SEQ ? TILE : 16> tc;
+  const unsigned tid = threadIdx.x;
+  const int64_t q0 = (int64_t)blockIdx.x * TILE;
+  const int64_t total = FROM_SEQ ? sv.nstarts : (n_dev ? min((int64_t)*n_dev, n_in) : n_in);   // the count may only exist on the device
+  if (q0 >= total) return;
+  const int t0 = tid * ITEMS;
+  bool special = false;
+  if constexpr (FROM_SEQ) special = tile_pack<TILE, THREADS>(sv, q0, tc);
+  constexpr int BATCH = 4;
+  static_assert(ITEMS % BATCH == 0, "items in batches");
+  uint64_t key = 0;
+  const uint64_t kmask = key_mask(FROM_SEQ ? sv.k : 32);
+#pragma unroll
+  for (int i0 = 0; i0 < ITEMS; i0 += BATCH) {
+    uint4 s0[BATCH], s1[BATCH];
+    uint64_t kk[BATCH], home[BATCH];
+    bool ok[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const int i = i0 + j;
+      if constexpr (FROM_SEQ) {
+        if (i == 0) key = tile_key<TILE>(tc, t0, sv.k);
+        else {                                            // roll in the base at tile position t0 + i + k - 1
+          const int p = t0 + i + sv.k - 1;
+          const uint32_t code = (tc.codes[p >> 4] >> (30 - 2 * (p & 15))) & 3u;
+          key = ((key << 2) | code) & kmask;
+        }
+        ok[j] = tile_valid<TILE>(sv, tc, q0, t0 + i, special);
+      } else {
+        ok[j] = q0 + t0 + i < total;
+        key = ok[j] ? ld_stream_u64(keys_in + q0 + t0 + i) : 0;
+      }
+      kk[j] = key;
+      home[j] = hash64(key) & kh.bmask;
+      if (ok[j]) ld_stream_sector(kh.slots + home[j] * BUCKET_SLOTS, s0[j], s1[j]);
+    }
+    uint2 r[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) r[j] = ok[j] ? resolve_key(kh, kk[j], home[j], s0[j], s1[j]) : make_uint2(0u, 0u);
+    if (q0 + t0 + i0 + BATCH <= total) {                  // 32 contiguous bytes per thread
+      uint4 *dst = reinterpret_cast<uint4 *>(found + q0 + t0 + i0);
+      dst[0] = make_uint4(r[0].x, r[0].y, r[1].x, r[1].y);
+      dst[1] = make_uint4(r[2].x, r[2].y, r[3].x, r[3].y);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j)
+        if (q0 + t0 + i0 + j < total) found[q0 + t0 + i0 + j] = r[j];
+    }
+  }
+}
+
+// ---- pass 2: ordered compaction of the hits + chained 64-bit scan of their row counts --------------------
+//   coordinate i of a hit: FROM_SEQ: 1-based END of the window (src/kmer_pos.c:127,132: `i` is one past the
+//   window); else the record's own i.
 template <int THREADS, int ITEMS, bool FROM_SEQ>
 __global__ void __launch_bounds__(THREADS)
-probe_match_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, const int32_t *__restrict__ i_in,
-                   int64_t n_in, const uint64_t *__restrict__ n_dev, const KeyTable kt, int32_t *__restrict__ hit_i, uint32_t *__restrict__ hit_u,
-                   uint64_t *__restrict__ row_off, QueryStats *qs, Pair64 *status, uint32_t *ticket) {
+probe_compact_kernel(const uint2 *__restrict__ found, int64_t coord0, const int32_t *__restrict__ i_in, int64_t n_in,
+                     const uint64_t *__restrict__ n_dev, int32_t *__restrict__ hit_i, uint32_t *__restrict__ hit_start,
+                     uint64_t *__restrict__ row_off, QueryStats *qs, Pair64 *status, uint32_t *ticket) {
   constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32;
-  __shared__ TileCodes<FROM_SEQ ? TILE : 16> tc;
+  static_assert(ITEMS % 2 == 0, "pairs of windows are read as one 16-byte word");
   __shared__ uint32_t s_tile, s_wh[WARPS];
   __shared__ uint64_t s_wr[WARPS], s_bh, s_br;
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -71,42 +153,27 @@ probe_match_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, const
   __syncthreads();
   const uint32_t tile = s_tile;
   const int64_t q0 = (int64_t)tile * TILE;
-  const int64_t total = FROM_SEQ ? sv.nstarts : (n_dev ? min((int64_t)*n_dev, n_in) : n_in);   // the count may only exist on the device
+  const int64_t total = n_dev ? min((int64_t)*n_dev, n_in) : n_in;
   if (q0 >= total) return;
-
-  uint32_t u[ITEMS], cnt[ITEMS];
-  int32_t coord[ITEMS];
-  const int t0 = warp * (32 * ITEMS) + lane;
-  bool special = false;
-  if constexpr (FROM_SEQ) special = tile_pack<TILE, THREADS>(sv, q0, tc);
+  const int64_t t0 = q0 + (int64_t)tid * ITEMS;
+  uint2 f[ITEMS];
+  if (t0 + ITEMS <= total) {
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int t = t0 + i * 32;
-    u[i] = 0xFFFFFFFFu;
-    if constexpr (FROM_SEQ) {
-      coord[i] = (int32_t)(sv.s0 + q0 + t + sv.k);
-      if (tile_valid<TILE>(sv, tc, q0, t, special)) u[i] = find_key(kt, tile_key<TILE>(tc, t, sv.k));
-    } else {
-      coord[i] = 0;
-      if (q0 + t < total) { coord[i] = i_in[q0 + t]; u[i] = find_key(kt, ld_stream_u64(keys_in + q0 + t)); }
+    for (int i = 0; i < ITEMS; i += 2) {
+      const uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(found + t0 + i));
+      f[i] = make_uint2(v.x, v.y); f[i + 1] = make_uint2(v.z, v.w);
     }
-  }
+  } else {
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i)
-    cnt[i] = u[i] != 0xFFFFFFFFu ? __ldg(kt.ustart + u[i] + 1) - __ldg(kt.ustart + u[i]) : 0;
-
-  uint32_t hb[ITEMS], hrun = 0;
-  uint64_t rb[ITEMS], rrun = 0;
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const unsigned bal = __ballot_sync(FULL, cnt[i] != 0);
-    hb[i] = hrun + __popc(bal & lanemask_lt());
-    hrun += __popc(bal);
-    const uint64_t inc = warp_incl_scan64(cnt[i]);
-    rb[i] = rrun + inc - cnt[i];
-    rrun += __shfl_sync(FULL, inc, 31);
+    for (int i = 0; i < ITEMS; ++i) f[i] = t0 + i < total ? found[t0 + i] : make_uint2(0u, 0u);
   }
-  if (lane == 0) { s_wh[warp] = hrun; s_wr[warp] = rrun; }
+  uint32_t hmine = 0;
+  uint64_t rmine = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) { hmine += f[i].y != 0; rmine += f[i].y; }
+  const uint32_t hincl = warp_incl_scan(hmine);
+  const uint64_t rincl = warp_incl_scan64(rmine);
+  if (lane == 31) { s_wh[warp] = hincl; s_wr[warp] = rincl; }
   __syncthreads();
   uint64_t bh = 0, br = 0, th = 0, tr = 0;
 #pragma unroll
@@ -120,14 +187,16 @@ probe_match_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, const
     if (lane == 0) { s_bh = ea; s_br = eb; }
   }
   __syncthreads();
-  bh += s_bh; br += s_br;
+  uint64_t h = s_bh + bh + (hincl - hmine);
+  uint64_t r = s_br + br + (rincl - rmine);
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    if (cnt[i]) {
-      const uint64_t h = bh + hb[i];
-      hit_i[h] = coord[i];
-      hit_u[h] = u[i];
-      row_off[h] = br + rb[i];
+    if (f[i].y) {
+      hit_i[h] = FROM_SEQ ? (int32_t)(coord0 + t0 + i) : i_in[t0 + i];
+      hit_start[h] = f[i].x;
+      row_off[h] = r;
+      ++h;
+      r += f[i].y;
     }
   }
   if (q0 + TILE >= total && tid == 0) { qs->H = s_bh + th; qs->M = s_br + tr; }
@@ -137,9 +206,9 @@ probe_match_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, const
 // the hit's query coordinate with the (r - row_off[h])-th position of its k-mer.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-probe_emit_kernel(const int32_t *__restrict__ hit_i, const uint32_t *__restrict__ hit_u,
-                  const uint64_t *__restrict__ row_off, uint64_t H, const uint32_t *__restrict__ ustart,
-                  const uint32_t *__restrict__ pos, uint64_t first, uint64_t nrows, int2 *__restrict__ out) {
+probe_emit_kernel(const int32_t *__restrict__ hit_i, const uint32_t *__restrict__ hit_start,
+                  const uint64_t *__restrict__ row_off, uint64_t H, const uint32_t *__restrict__ pos, uint64_t first,
+                  uint64_t nrows, int2 *__restrict__ out) {
   constexpr int PER = 8, T = THREADS * PER;
   __shared__ __align__(16) uint8_t s_flag[T];
   __shared__ __align__(16) uint32_t s_seg[T];
@@ -154,9 +223,8 @@ probe_emit_kernel(const int32_t *__restrict__ hit_i, const uint32_t *__restrict_
     const uint32_t s = j * THREADS + threadIdx.x;
     if (b0 + s >= nrows) continue;
     const uint64_t h = h0 + s_seg[s];
-    const uint32_t u = hit_u[h];
     const uint64_t within = r0 + s - row_off[h];
-    out[b0 + s] = make_int2(hit_i[h], (int)pos[ustart[u] + within]);
+    out[b0 + s] = make_int2(hit_i[h], (int)pos[hit_start[h] + within]);
   }
 }
 
