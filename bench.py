@@ -41,6 +41,15 @@ def gen_sequence(workload: str, L: int, out=None):
     return synth.config_c2(L, out=out) if workload == "c2" else synth.config_c3(L, out=out)
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_sort_pass_ncu.json")
+    if kernel.startswith("sort_pass") and os.path.exists(path):
+        d = json.load(open(path))
+        return d["traffic_bytes_per_launch"], d["source"]
+    return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -275,9 +284,10 @@ def bench_single(args, kh, torch, w, k, L, steps, warm, hbm_peak, peak_src, dev)
     if dom:
         name, (tms, nl, bytes_) = dom
         ach = bytes_ / (tms * 1e-3) / 1e9 if tms > 0 else 0.0
+        traffic, traffic_src = ncu_traffic(name)
         roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "launches": int(nl), "avg_launch_ms": tms / max(nl, 1),
-                "algo_bytes_per_launch": bytes_ / max(nl, 1)}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches": int(nl),
+                "avg_launch_ms": tms / max(nl, 1), "algo_bytes_per_launch": bytes_ / max(nl, 1)}
     kernels = {n: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps,
                    "GBps": (v[2] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None)} for n, v in sorted(prof.items())}
 

@@ -444,7 +444,7 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
   CU(cudaMemsetAsync(status2, 0, (size_t)tiles * sizeof(Pair64), s));
   LAUNCH("rle", s, rle_kernel<RLE_THREADS, RLE_ITEMS><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(
                        keys_sorted, st, ukeys, ustart, status2, sc.ticket(MAX_PASSES + 1)));
-  const unsigned sgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, 256 * 8), g_ctx.sms * 8);
+  const unsigned sgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, 256 * 16), g_ctx.sms * 8);
   LAUNCH("stats", s, stats_kernel<256><<<sgrid, 256, 0, s>>>(ustart, st));
   IndexStats h;
   CU(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));

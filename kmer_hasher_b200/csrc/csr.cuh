@@ -104,7 +104,21 @@ stats_kernel(const uint32_t *__restrict__ ustart, IndexStats *st) {
   const uint64_t U = st->U;
   uint64_t P = 0, multi = 0;
   uint32_t maxc = 0;
-  for (uint64_t u = (uint64_t)blockIdx.x * THREADS + threadIdx.x; u < U; u += (uint64_t)gridDim.x * THREADS) {
+  // four list starts per 16-byte load; the count of the last needs the next group's first start
+  const uint64_t groups = U / 4;
+  for (uint64_t g = (uint64_t)blockIdx.x * THREADS + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * THREADS) {
+    const uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(ustart) + g);
+    const uint32_t nx = __ldg(ustart + 4 * g + 4);
+    const uint32_t c[4] = {v.y - v.x, v.z - v.y, v.w - v.z, nx - v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      P += (uint64_t)c[j] * (c[j] - 1) / 2;
+      multi += c[j] > 1;
+      maxc = max(maxc, c[j]);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < U - 4 * groups) {
+    const uint64_t u = 4 * groups + threadIdx.x;
     const uint64_t c = ustart[u + 1] - ustart[u];
     P += c * (c - 1) / 2;
     multi += c > 1;
@@ -131,13 +145,35 @@ __device__ __forceinline__ uint64_t block_segments(const OffT *__restrict__ off,
   static_assert(PER == 8, "flags are read as one 64-bit word per thread");
   constexpr int T = THREADS * PER, WARPS = THREADS / 32;
   const unsigned tid = threadIdx.x;
-  if (tid == 0) {                                        // largest m with off[m] <= r0
-    uint64_t lo = 0, hi = cnt;                           // invariant: off[lo] <= r0 < off[hi]
+  {                                                      // largest m with off[m] <= r0: THREADS-ary search by the whole block
+    uint64_t lo = 0, hi = cnt;                           // invariant: off[lo] <= r0 < off[hi] (off[cnt] = +inf)
     while (hi - lo > 1) {
-      uint64_t mid = (lo + hi) >> 1;
-      if ((uint64_t)off[mid] <= r0) lo = mid; else hi = mid;
+      const uint64_t span = hi - lo;
+      // thread t probes lo + ceil(span * (t+1) / (THREADS+1)) clipped to (lo, hi)
+      uint64_t m = lo + (span * (tid + 1) + THREADS) / (THREADS + 1);
+      if (m >= hi) m = hi - 1;
+      const bool le = m > lo && (uint64_t)off[m] <= r0;
+      if (tid == 0) *s_first = lo;
+      __syncthreads();
+      if (le) atomicMax(reinterpret_cast<unsigned long long *>(s_first), (unsigned long long)m);
+      __syncthreads();
+      const uint64_t nlo = *s_first;
+      // the new upper bound is the smallest probe above nlo that failed (probes are non-decreasing in t)
+      uint64_t nhi = hi;
+      {
+        const uint64_t mt = m;
+        const bool gt = mt > nlo && !le;
+        __syncthreads();
+        if (tid == 0) s_warp[0] = 0xFFFFFFFFu;
+        __syncthreads();
+        if (gt) atomicMin(&s_warp[0], (uint32_t)(mt - lo));
+        __syncthreads();
+        if (s_warp[0] != 0xFFFFFFFFu) nhi = lo + s_warp[0];
+      }
+      __syncthreads();
+      lo = nlo; hi = nhi;
     }
-    *s_first = lo;
+    if (tid == 0) *s_first = lo;
   }
   reinterpret_cast<uint64_t *>(s_flag)[tid] = 0;
   __syncthreads();
@@ -168,7 +204,15 @@ __device__ __forceinline__ uint64_t block_segments(const OffT *__restrict__ off,
 
 // ---- flag 8: counts ---------------------------------------------------------------------------------------
 __global__ void counts_kernel(const uint32_t *__restrict__ ustart, uint64_t U, int32_t *__restrict__ out) {
-  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x)
+  // ustart may be offset by a chunk start (any 4-byte alignment): peel to 16-byte alignment of both arrays if possible
+  const bool vec = ((reinterpret_cast<uintptr_t>(ustart) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  const uint64_t groups = vec ? U / 4 : 0;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(ustart) + g);
+    const uint32_t nx = __ldg(ustart + 4 * g + 4);
+    reinterpret_cast<int4 *>(out)[g] = make_int4((int)(v.y - v.x), (int)(v.z - v.y), (int)(v.w - v.z), (int)(nx - v.w));
+  }
+  for (uint64_t u = 4 * groups + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x)
     out[u] = (int32_t)(ustart[u + 1] - ustart[u]);
 }
 
