@@ -42,6 +42,7 @@ typedef enum {
 
 typedef struct kmg_index kmg_index; /* replaces khash_ptr            (src/kmer_pos.h:43-48)  */
 typedef struct kmg_query kmg_query; /* replaces the kmer_ppos result (src/kmer_pos.h:41)     */
+typedef struct kmg_join kmg_join;   /* the result of kmer.pairs      (src/kmer_hash.c:1177)   */
 
 /* ---- library / device -------------------------------------------------------------------- */
 const char *kmg_last_error(void);
@@ -101,6 +102,18 @@ int kmg_query_begin(const kmg_index *idx, const char *q, int64_t qlen, int k, km
 int kmg_query_emit(kmg_query *st, int32_t *out /* 2M */);
 int kmg_query_emit_chunk(kmg_query *st, uint64_t first, uint64_t n, int32_t *out /* 2n */);
 int kmg_query_free(kmg_query *st);
+
+/* ---- kmer.pairs ----------------------------------------------------------------------------------
+ * kmg_join_begin + kmg_join_emit replace kmer_pair_pos, src/kmer_hash.c:1174-1203 (kmer_hash.R:30-34):
+ * for every k-mer of index `a` that index `b` also holds, the rows (a_pos, b_pos), a position outer,
+ * b position inner (:1190-1195).  The reference walks a's hash buckets without kh_exist and crashes
+ * (test.R:330-331); this is its evident intent, with a's k-mers taken in ascending key order.  Keys
+ * are compared as raw 2-bit codes, whatever k each index was built with, as kh_get does (:1185).
+ * Both indexes must be on the same device.  M = number of rows. */
+int kmg_join_begin(const kmg_index *a, const kmg_index *b, kmg_join **st, uint64_t *M);
+int kmg_join_emit(kmg_join *st, int32_t *out /* 2M */);
+int kmg_join_emit_chunk(kmg_join *st, uint64_t first, uint64_t n, int32_t *out /* 2n */);
+int kmg_join_free(kmg_join *st);
 
 /* ---- sharded build (one process per GPU; the exchange itself is the host's NCCL all-to-all) ----
  * A rank holds bytes [g0,g1) of a global sequence of length L in device memory at d_seq (d_seq[0]

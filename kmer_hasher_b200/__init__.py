@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib
 from ._lib import KmgError, check
 
-__all__ = ["KmerHash", "make_kmer_hash", "kmer_pos", "seq_kmer_pos", "pinned_empty", "KmgError",
+__all__ = ["KmerHash", "make_kmer_hash", "kmer_pos", "seq_kmer_pos", "kmer_pairs", "pinned_empty", "KmgError",
            "OPT_KMER", "OPT_POS", "OPT_PAIRS", "OPT_COUNT"]
 
 # opt.flag bits, src/kmer_hash.c:17 (pos_opt_flags) in the reference
@@ -225,6 +225,27 @@ def seq_kmer_pos(ex_ptr, seq, k, *, allow_k32: bool = False, out: np.ndarray | N
         _L.kmg_query_free(st)
     del keep
     return a[:M.value]
+
+
+def kmer_pairs(ptr_a, ptr_b, *, out: np.ndarray | None = None) -> np.ndarray:
+    """kmer.pairs (kmer_hash.R:30-34 -> kmer_pair_pos, src/kmer_hash.c:1174-1203).
+
+    M x 2 int32 array, columns (a, b): for every k-mer that both indexes hold, each of its 1-based
+    positions in `ptr_a` paired with each of its positions in `ptr_b` (a position outer, b position
+    inner), k-mers of `ptr_a` in ascending key order.  (The reference's own routine crashes on its
+    bucket walk, test.R:330-331; this is its evident intent.)
+    """
+    a, b = _extract(ptr_a), _extract(ptr_b)
+    st, M = C.c_void_p(), C.c_uint64()
+    check(_L.kmg_join_begin(a._handle(), b._handle(), C.byref(st), C.byref(M)))
+    try:
+        if M.value > INT_MAX:
+            raise OverflowError(f"{M.value} result rows exceed an R matrix extent")
+        r = out if out is not None else np.empty((M.value, 2), np.int32)
+        check(_L.kmg_join_emit(st, _out_ptr(r)))
+    finally:
+        _L.kmg_join_free(st)
+    return r[:M.value]
 
 
 def profile(enable: bool | None = None, reset: bool = False) -> dict:

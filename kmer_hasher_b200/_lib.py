@@ -38,6 +38,10 @@ SIGNATURES = {
     "kmg_query_emit": (C.c_int, [vp, vp]),
     "kmg_query_emit_chunk": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp]),
     "kmg_query_free": (C.c_int, [vp]),
+    "kmg_join_begin": (C.c_int, [vp, vp, C.POINTER(vp), u64p]),
+    "kmg_join_emit": (C.c_int, [vp, vp]),
+    "kmg_join_emit_chunk": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp]),
+    "kmg_join_free": (C.c_int, [vp]),
     "kmg_shard_sample": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, vp]),
     "kmg_shard_partition": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                       u64p, C.c_int, vp, vp, u64p]),

@@ -907,6 +907,105 @@ extern "C" int kmg_query_free(kmg_query *q) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// kmer.pairs
+// ------------------------------------------------------------------------------------------------
+struct kmg_join {
+  const kmg_index *a = nullptr, *b = nullptr;
+  uint64_t H = 0, M = 0;
+  uint32_t *hit_astart = nullptr, *hit_bstart = nullptr, *hit_cb = nullptr;
+  uint64_t *row_off = nullptr;
+};
+
+extern "C" int kmg_join_free(kmg_join *j) {
+  if (!j) return KMG_OK;
+  const int dev = j->a ? j->a->device : g_ctx.device;
+  cudaSetDevice(dev);
+  const bool mine = g_ctx.ready && g_ctx.device == dev;
+  if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
+  void *ptrs[4] = {j->hit_astart, j->hit_bstart, j->hit_cb, j->row_off};
+  for (void *p : ptrs) g_arena[dev & 63].put(p, nullptr, true);
+  cudaGetLastError();
+  delete j;
+  return KMG_OK;
+}
+
+extern "C" int kmg_join_begin(const kmg_index *a, const kmg_index *cb, kmg_join **out, uint64_t *M) {
+  if (!out) return fail(KMG_ERR_ARG, "st is NULL");
+  *out = nullptr;
+  if (!a || !cb) return fail(KMG_ERR_ARG, "index is NULL");
+  if (a->device != cb->device) return fail(KMG_ERR_ARG, "the two indexes live on different devices (%d, %d)", a->device, cb->device);
+  TRY(use_index(a));
+  kmg_index *b = const_cast<kmg_index *>(cb);
+  cudaStream_t s = g_ctx.stream();
+  kmg_join *j = new (std::nothrow) kmg_join();
+  if (!j) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  j->a = a; j->b = b;
+  if (a->U == 0 || b->U == 0) { *out = j; if (M) *M = 0; return KMG_OK; }
+  int rc = ensure_hash(b);
+  if (rc != KMG_OK) { delete j; return rc; }
+  QueryStats *qs = nullptr;
+  Pair64 *status = nullptr;
+  uint32_t *ticket = nullptr;
+  uint2 *found = nullptr;
+  const uint64_t U = a->U;
+  auto body = [&]() -> int {
+    const uint64_t tiles = ceil_div<uint64_t>(U, PROBE_TILE);
+    TRY(dalloc(&j->hit_astart, (size_t)U, s));
+    TRY(dalloc(&j->hit_bstart, (size_t)U, s));
+    TRY(dalloc(&j->hit_cb, (size_t)U, s));
+    TRY(dalloc(&j->row_off, (size_t)U, s));
+    TRY(dalloc(&found, (size_t)U, s));
+    TRY(dalloc(&qs, 1, s));
+    TRY(dalloc(&status, tiles, s));
+    TRY(dalloc(&ticket, 1, s));
+    CU(cudaMemsetAsync(qs, 0, sizeof(QueryStats), s));
+    CU(cudaMemsetAsync(status, 0, tiles * sizeof(Pair64), s));
+    CU(cudaMemsetAsync(ticket, 0, 4, s));
+    KeyHash kt{b->hash, b->hash_bmask};
+    SeqView sv{};
+    LAUNCH("probe_lookup_rec", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+                                      sv, a->ukeys, (int64_t)U, nullptr, kt, found));
+    LAUNCH("join_compact", s, join_compact_kernel<PROBE_THREADS, PROBE_ITEMS><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+                                  found, a->ustart, U, j->hit_astart, j->hit_bstart, j->hit_cb, j->row_off, qs, status, ticket));
+    QueryStats h;
+    CU(cudaMemcpyAsync(&h, qs, sizeof h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    j->H = h.H; j->M = h.M;
+    return KMG_OK;
+  };
+  rc = body();
+  dfree(qs, s); dfree(status, s); dfree(ticket, s); dfree(found, s);
+  if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_join_free(j); return rc; }
+  prof_bytes("probe_lookup_rec", 8.0 * U + 128.0 * U + 8.0 * U);
+  prof_bytes("join_compact", 12.0 * U + 20.0 * j->H);
+  *out = j;
+  if (M) *M = j->M;
+  return KMG_OK;
+}
+
+extern "C" int kmg_join_emit_chunk(kmg_join *j, uint64_t first, uint64_t n, int32_t *out) {
+  if (!j) return fail(KMG_ERR_ARG, "join is NULL");
+  TRY(use_index(j->a));
+  if (first > j->M || n > j->M - first) return fail(KMG_ERR_ARG, "rows outside the result");
+  if (n == 0) return KMG_OK;
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  const uint32_t *ha = j->hit_astart, *hb = j->hit_bstart, *hc = j->hit_cb, *pa = j->a->pos, *pb = j->b->pos;
+  const uint64_t *row_off = j->row_off;
+  const uint64_t H = j->H;
+  int rc = stream_rows(n, 8, out, CHUNK_BYTES / 8, [=](uint64_t f, uint64_t rows, void *dst, cudaStream_t s) -> int {
+    const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
+    LAUNCH("join_emit", s, join_emit_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ha, hb, hc, row_off, H, pa, pb, first + f, rows, (int2 *)dst));
+    return KMG_OK;
+  });
+  prof_bytes("join_emit", 16.0 * n);
+  return rc;
+}
+extern "C" int kmg_join_emit(kmg_join *j, int32_t *out) {
+  if (!j) return fail(KMG_ERR_ARG, "join is NULL");
+  return kmg_join_emit_chunk(j, 0, j->M, out);
+}
+
+// ------------------------------------------------------------------------------------------------
 // sharded build
 // ------------------------------------------------------------------------------------------------
 // The caller's shard [g0,g1) is copied into an aligned, padded buffer whose byte 16 is window start s0.

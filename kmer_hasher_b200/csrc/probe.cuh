@@ -228,4 +228,95 @@ probe_emit_kernel(const int32_t *__restrict__ hit_i, const uint32_t *__restrict_
   }
 }
 
+// ---- kmer.pairs(a, b): positions of the k-mers two indexes share ----------------------------------------------
+// kmer_pair_pos (src/kmer_hash.c:1174-1203): for every k-mer of `a` that `b` also holds, rows (a_pos, b_pos),
+// a position outer, b position inner.  a's distinct keys are looked up in b's key table (probe_lookup_kernel,
+// record source); this kernel compacts the shared ones in a's order and scans their row counts ca * cb.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+join_compact_kernel(const uint2 *__restrict__ found, const uint32_t *__restrict__ ustart_a, uint64_t U,
+                    uint32_t *__restrict__ hit_astart, uint32_t *__restrict__ hit_bstart, uint32_t *__restrict__ hit_cb,
+                    uint64_t *__restrict__ row_off, QueryStats *qs, Pair64 *status, uint32_t *ticket) {
+  constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32;
+  __shared__ uint32_t s_tile, s_wh[WARPS];
+  __shared__ uint64_t s_wr[WARPS], s_bh, s_br;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t q0 = (uint64_t)tile * TILE;
+  if (q0 >= U) return;
+  const uint64_t t0 = q0 + (uint64_t)tid * ITEMS;
+  uint2 f[ITEMS];
+  uint32_t as[ITEMS + 1];
+#pragma unroll
+  for (int i = 0; i <= ITEMS; ++i) as[i] = t0 + i <= U ? ustart_a[t0 + i] : 0;
+  uint32_t hmine = 0;
+  uint64_t rmine = 0, rows[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    f[i] = t0 + i < U ? found[t0 + i] : make_uint2(0u, 0u);
+    rows[i] = f[i].y ? (uint64_t)(as[i + 1] - as[i]) * f[i].y : 0;
+    hmine += f[i].y != 0;
+    rmine += rows[i];
+  }
+  const uint32_t hincl = warp_incl_scan(hmine);
+  const uint64_t rincl = warp_incl_scan64(rmine);
+  if (lane == 31) { s_wh[warp] = hincl; s_wr[warp] = rincl; }
+  __syncthreads();
+  uint64_t bh = 0, br = 0, th = 0, tr = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    if (w < (int)warp) { bh += s_wh[w]; br += s_wr[w]; }
+    th += s_wh[w]; tr += s_wr[w];
+  }
+  if (warp == 0) {
+    uint64_t ea, eb;
+    pair_lookback(status, tile, th, tr, ea, eb);
+    if (lane == 0) { s_bh = ea; s_br = eb; }
+  }
+  __syncthreads();
+  uint64_t h = s_bh + bh + (hincl - hmine);
+  uint64_t r = s_br + br + (rincl - rmine);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    if (f[i].y) {
+      hit_astart[h] = as[i];
+      hit_bstart[h] = f[i].x;
+      hit_cb[h] = f[i].y;
+      row_off[h] = r;
+      ++h;
+      r += rows[i];
+    }
+  }
+  if (q0 + TILE >= U && tid == 0) { qs->H = s_bh + th; qs->M = s_br + tr; }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+join_emit_kernel(const uint32_t *__restrict__ hit_astart, const uint32_t *__restrict__ hit_bstart,
+                 const uint32_t *__restrict__ hit_cb, const uint64_t *__restrict__ row_off, uint64_t H,
+                 const uint32_t *__restrict__ pos_a, const uint32_t *__restrict__ pos_b, uint64_t first, uint64_t nrows,
+                 int2 *__restrict__ out) {
+  constexpr int PER = 8, T = THREADS * PER;
+  __shared__ __align__(16) uint8_t s_flag[T];
+  __shared__ __align__(16) uint32_t s_seg[T];
+  __shared__ uint32_t s_warp[THREADS / 32];
+  __shared__ uint64_t s_first;
+  const uint64_t b0 = (uint64_t)blockIdx.x * T;
+  if (b0 >= nrows) return;
+  const uint64_t r0 = first + b0;
+  const uint64_t h0 = block_segments<THREADS, PER, uint64_t>(row_off, H, r0, s_flag, s_seg, s_warp, &s_first);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const uint32_t s = j * THREADS + threadIdx.x;
+    if (b0 + s >= nrows) continue;
+    const uint64_t h = h0 + s_seg[s];
+    const uint64_t within = r0 + s - row_off[h];
+    const uint32_t cb = hit_cb[h];
+    const uint64_t ia = within / cb;                       // a position outer, b position inner (src/kmer_hash.c:1190-1195)
+    out[b0 + s] = make_int2((int)pos_a[hit_astart[h] + ia], (int)pos_b[hit_bstart[h] + (within - ia * cb)]);
+  }
+}
+
 }  // namespace kmg

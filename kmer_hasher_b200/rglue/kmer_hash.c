@@ -9,6 +9,7 @@
  *   make_kmer_h_index(seq, k, do.sort)      replaces src/kmer_hash.c:506-540
  *   kmer_positions(ptr, opt.flag)           replaces src/kmer_hash.c:1054-1147
  *   sequence_kmer_positions(ptr, seq, k)    replaces src/kmer_hash.c:1151-1172
+ *   kmer_pair_pos(ptr.a, ptr.b)             replaces src/kmer_hash.c:1174-1203 (which crashes: test.R:330-331)
  *   R_init_kmer_hash                        replaces src/kmer_hash.c:1221-1224
  *
  * Differences a user can observe: k-mers come out ordered by 2-bit key instead of khash bucket order
@@ -174,10 +175,31 @@ SEXP sequence_kmer_positions(SEXP ptr_r, SEXP seq_r, SEXP k_r) {
   return m;
 }
 
+/* kmer.pairs(ptr.a, ptr.b) -> .Call("kmer_pair_pos", ...), kmer_hash.R:30-34; replaces src/kmer_hash.c:1174-1203:
+ * rows (a, b) for every k-mer the two indexes share; kmer.pairs() names and transposes. */
+SEXP kmer_pair_pos(SEXP ptr_a, SEXP ptr_b) {
+  kmer_handle *a = handle_or_error(ptr_a);
+  kmer_handle *b = handle_or_error(ptr_b);
+  kmg_join *j = NULL;
+  uint64_t M = 0;
+  if (kmg_join_begin(a->index, b->index, &j, &M) != KMG_OK) error("kmer.pairs failed: %s", kmg_last_error());
+  if (M > (uint64_t)INT_MAX) {
+    kmg_join_free(j);
+    error("kmer.pairs would return %llu rows, more than an R matrix can hold (2^31-1)", (unsigned long long)M);
+  }
+  SEXP m = PROTECT(allocMatrix(INTSXP, 2, (int)M));
+  const int rc = kmg_join_emit(j, INTEGER(m));
+  kmg_join_free(j);
+  UNPROTECT(1);
+  if (rc != KMG_OK) error("kmer.pairs failed: %s", kmg_last_error());
+  return m;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"make_kmer_h_index", (DL_FUNC)&make_kmer_h_index, 3},
     {"kmer_positions", (DL_FUNC)&kmer_positions, 2},
     {"sequence_kmer_positions", (DL_FUNC)&sequence_kmer_positions, 3},
+    {"kmer_pair_pos", (DL_FUNC)&kmer_pair_pos, 2},
     {NULL, NULL, 0}};
 
 void R_init_kmer_hash(DllInfo *info) { R_registerRoutines(info, NULL, call_methods, NULL, NULL); }

@@ -89,6 +89,24 @@ class OracleIndex:
         self.close()
 
 
+def pairs_join(a: dict, b: dict) -> np.ndarray:
+    """kmer.pairs restated (kmer_pair_pos, src/kmer_hash.c:1174-1203) from two canonical extractions
+    (`extract(2 | 8)` with keys): for every k-mer of `a` that `b` also holds, rows (a_pos, b_pos), a
+    position outer, b position inner (:1190-1195), a's k-mers in ascending key order.  Flattened."""
+    pa, pb = a["pos"].reshape(-1, 2)[:, 1], b["pos"].reshape(-1, 2)[:, 1]
+    sa = np.concatenate([[0], np.cumsum(a["count"], dtype=np.int64)])
+    sb = np.concatenate([[0], np.cumsum(b["count"], dtype=np.int64)])
+    idx = np.searchsorted(b["keys"], a["keys"])
+    idx[idx >= len(b["keys"])] = 0
+    shared = np.nonzero(b["keys"][idx] == a["keys"])[0] if len(b["keys"]) else np.empty(0, np.int64)
+    out = []
+    for u in shared:
+        v = idx[u]
+        la, lb = pa[sa[u]:sa[u + 1]], pb[sb[v]:sb[v + 1]]
+        out.append(np.stack([np.repeat(la, len(lb)), np.tile(lb, len(la))], axis=1))
+    return (np.concatenate(out) if out else np.empty((0, 2), np.int32)).astype(np.int32).ravel()
+
+
 class Oracle:
     def __init__(self):
         if not os.path.exists(ORACLE_SO):
@@ -179,6 +197,14 @@ class ReferenceIndex:
             self._lib.ref_query_free(rows)
         return out if want_rows else n
 
+    def pairs_join(self, other: "ReferenceIndex") -> np.ndarray:
+        """kmer.pairs(self, other) on the reference's own hash tables (ref_pairs_join): rows (a, b) flattened."""
+        rows = _i32p()
+        n = self._lib.ref_pairs_join(self._h, other._h, C.byref(rows))
+        out = np.ctypeslib.as_array(rows, shape=(2 * n,)).copy() if n else np.empty(0, np.int32)
+        self._lib.ref_free_buf(rows)
+        return out
+
     def close(self):
         if self._h:
             self._lib.ref_free(self._h)
@@ -210,6 +236,8 @@ class Reference:
         lib.ref_window_stream.restype = C.c_int64
         lib.ref_window_stream.argtypes = [C.c_char_p, C.c_int, C.POINTER(_u64p), C.POINTER(_i32p)]
         lib.ref_free_buf.argtypes = [C.c_void_p]
+        lib.ref_pairs_join.restype = C.c_int64
+        lib.ref_pairs_join.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_i32p)]
         self.lib = lib
 
     @staticmethod

@@ -188,6 +188,39 @@ int64_t ref_query(const ref_index *ri, const char *seq, int k, int **rows, doubl
 }
 void ref_query_free(int *rows) { free(rows); }
 
+/* kmer_pair_pos restated from the R glue (kmer_hash.c:1174-1203) on the reference's own tables: for
+ * every k-mer of a that b holds (kh_get, :1185), rows (a_pos, b_pos), a position outer, b position
+ * inner (:1190-1195).  Two repairs, both stated in SURVEY.md 8f: buckets of a that hold nothing are
+ * skipped (the original omits kh_exist on it_a and crashes, test.R:330-331) and kh_get's "not found"
+ * is tested against kh_end.  Canonical form: a's k-mers in ascending key order. */
+int64_t ref_pairs_join(const ref_index *ra, const ref_index *rb, int **rows_out) {
+  khash_t(kmer_h) *ha = ra->hp.hash, *hb = rb->hp.hash;
+  const size_t U = kh_size(ha);
+  key_slot *ord = malloc((U ? U : 1) * sizeof(key_slot));
+  size_t w = 0;
+  for (khiter_t it = kh_begin(ha); it != kh_end(ha); ++it)
+    if (kh_exist(ha, it)) { ord[w].key = kh_key(ha, it); ord[w].slot = (uint32_t)it; ++w; }
+  qsort(ord, U, sizeof(key_slot), cmp_key_slot);
+  int64_t n = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int *rows = pass ? malloc((size_t)(n ? n : 1) * 2 * sizeof(int)) : NULL;
+    int64_t r = 0;
+    for (size_t u = 0; u < U; ++u) {
+      khiter_t ib = kh_get(kmer_h, hb, ord[u].key);
+      if (ib == kh_end(hb)) continue;
+      const kmer_pos_t *av = &kh_val(ha, ord[u].slot), *bv = &kh_val(hb, ib);
+      if (rows)
+        for (size_t i = 0; i < av->v.n; ++i)
+          for (size_t j = 0; j < bv->v.n; ++j) { rows[2 * r] = av->v.a[i]; rows[2 * r + 1] = bv->v.a[j]; ++r; }
+      else
+        r += (int64_t)(av->v.n * bv->v.n);
+    }
+    if (!pass) n = r; else *rows_out = rows;
+  }
+  free(ord);
+  return n;
+}
+
 /* The insertion stream of seq_to_hash, observed without touching the reference:
  * build an index of the sequence, then read every (key,pos) back and order by
  * position.  Gives the exact multiset of windows the reference emits. */

@@ -100,6 +100,14 @@ class RSession:
         self.stub.rstub_release(r)
         return out
 
+    def kmer_pairs(self, ptr_a, ptr_b):
+        """kmer.pairs (kmer_hash.R:30-34): t() of the 2 x M matrix .Call("kmer_pair_pos") returns."""
+        r = self.call("kmer_pair_pos", ptr_a, ptr_b)
+        nr, nc = self.dims(r)
+        v = self.ints(r).reshape(nc, nr)
+        self.stub.rstub_release(r)
+        return v
+
     def seq_kmer_pos(self, ptr, seq, k):
         r = self.call("sequence_kmer_positions", ptr, self.character(seq), self.integer(k))
         nr, nc = self.dims(r)

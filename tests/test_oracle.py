@@ -95,3 +95,30 @@ def test_query_k_independent_of_index_k(oracle, reference):
     a, b = reference.build(s, 8), oracle.build(s, 8)
     for kq in (4, 8, 12):
         assert np.array_equal(a.query(s[:2000], kq), b.query(s[:2000], kq))
+
+
+def test_pairs_join_restatement_matches_reference_tables(oracle, reference):
+    """kmer.pairs: the numpy restatement (oracle.pairs_join) against ref_pairs_join, which walks the
+    reference's own khash tables (kmer_pair_pos with its missing kh_exist added)."""
+    import oracle as oracle_mod
+    from kmer_hasher_b200 import synth
+    a_seq = synth.config_c3(60_000)
+    b_seq = synth.config_c4_query(a_seq, 30_000)
+    for ka, kb in ((12, 12), (16, 16), (9, 7)):
+        ra, rb = reference.build(a_seq, ka), reference.build(b_seq, kb)
+        want = ra.pairs_join(rb)
+        got = oracle_mod.pairs_join(ra.extract(2 | 8), rb.extract(2 | 8))
+        assert np.array_equal(got, want)
+        if ka == kb:
+            assert len(want) > 0
+        # symmetry: swapping the indexes swaps the columns (as a multiset of rows)
+        back = rb.pairs_join(ra).reshape(-1, 2)[:, ::-1]
+        w2 = want.reshape(-1, 2)
+        assert np.array_equal(back[np.lexsort((back[:, 1], back[:, 0]))], w2[np.lexsort((w2[:, 1], w2[:, 0]))])
+        ra.close(); rb.close()
+    # known answer: a = ACGTACGT (k=4): ACGT@{1,5}, CGTA@2, GTAC@3, TACG@4 ; b = TTACGTT: TTAC@1, TACG@2, ACGT@3, CGTT@4
+    ra, rb = reference.build("ACGTACGTA"[:8] + "A", 4), reference.build("TTACGTT", 4)
+    rows = ra.pairs_join(rb).reshape(-1, 2)
+    # shared: ACGT (a@1,5 ; b@3), TACG (a@4 ; b@2); keys ascending: ACGT = 0b00011011 = 27... order by key
+    assert sorted(map(tuple, rows.tolist())) == [(1, 3), (4, 2), (5, 3)]
+    ra.close(); rb.close()

@@ -422,3 +422,41 @@ def test_peer_scatter_single_process(kh, oracle, world, k, L):
         ix.free()
     for h in handles + qh:
         eng.shard_close(h)
+
+
+@pytest.mark.parametrize("ka,kb", [(16, 16), (32, 32), (12, 12), (9, 7)])
+def test_kmer_pairs(kh, oracle, ka, kb):
+    """kmer.pairs (kmg_join_*) against the restated kmer_pair_pos: shared k-mers' position pairs, a outer / b inner."""
+    import oracle as oracle_mod
+    from kmer_hasher_b200 import synth
+    a_seq = synth.config_c3(300_000, tail_k=ka)
+    b_seq = synth.config_c4_query(a_seq, 150_000)
+    ia, ib = kh.make_kmer_hash(a_seq, ka), kh.make_kmer_hash(b_seq, kb)
+    oa, ob = oracle.build(a_seq, ka), oracle.build(b_seq, kb)
+    want = oracle_mod.pairs_join(oa.extract(2 | 8), ob.extract(2 | 8))
+    got = kh.kmer_pairs(ia, ib)
+    assert got.shape == (len(want) // 2, 2)
+    assert np.array_equal(got.ravel(), want)
+    # chunked emission == whole, pinned output, and an index joined with itself = sum of squares of the counts
+    import ctypes as C
+    from kmer_hasher_b200 import _lib
+    L = _lib.load()
+    st, M = C.c_void_p(), C.c_uint64()
+    _lib.check(L.kmg_join_begin(ia._handle(), ib._handle(), C.byref(st), C.byref(M)))
+    assert M.value == len(got)
+    if M.value > 10:
+        cut = M.value // 3
+        p1, p2 = np.empty((cut, 2), np.int32), kh.pinned_empty((M.value - cut, 2), np.int32)
+        _lib.check(L.kmg_join_emit_chunk(st, 0, cut, p1.ctypes.data))
+        _lib.check(L.kmg_join_emit_chunk(st, cut, M.value - cut, p2.ctypes.data))
+        assert np.array_equal(np.concatenate([p1, np.asarray(p2)]), got)
+    L.kmg_join_free(st)
+    if ka == kb:
+        self_rows = kh.kmer_pairs(ia, ia)
+        cnt = kh.kmer_pos(ia, 8)["count"].astype(np.int64)
+        assert len(self_rows) == int((cnt * cnt).sum())
+    empty = kh.make_kmer_hash("A" * 40, 16)
+    other = kh.make_kmer_hash("C" * 40, 16)
+    assert kh.kmer_pairs(empty, other).shape == (0, 2)
+    for ix in (ia, ib, empty, other):
+        ix.free()

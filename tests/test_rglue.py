@@ -14,7 +14,9 @@ def R():
 
 
 def test_registered_routines(R):
-    # the three index entry points, same names and arity as the reference's callMethods table
+    # the index entry points, same names and arity as the reference's callMethods table
+    with pytest.raises(RError, match="Incorrect number of arguments"):
+        R.call("kmer_pair_pos", R.integer(1))
     with pytest.raises(RError, match="not in load table"):
         R.call("count_kmers", R.integer(1), R.integer(1), R.integer(1))
     with pytest.raises(RError, match="Incorrect number of arguments"):
@@ -68,6 +70,15 @@ def test_call_surface_matches_oracle(R, oracle, test_fa):
     assert only["kmer"] is None and only["pos"] is None and only["pair.pos"] is None and len(only["count"]) == o.U
     rows = R.seq_kmer_pos(ptr, test_fa[:20000], k)
     assert np.array_equal(rows.ravel(), o.query(test_fa[:20000], k))
+    # kmer.pairs through its .Call entry (kmer_pair_pos): shared k-mers of two indexes
+    import oracle as oracle_mod
+    other = R.make_kmer_hash(test_fa[10000:30000], k)
+    o2 = oracle.build(test_fa[10000:30000], k)
+    pr = R.kmer_pairs(ptr, other)
+    assert pr.shape[1] == 2 and np.array_equal(pr.ravel(), oracle_mod.pairs_join(want, o2.extract(2 | 8)))
+    with pytest.raises(RError, match="ptr_r should be an external pointer"):
+        R.call("kmer_pair_pos", ptr, R.integer(1))
+    R.stub.rstub_finalize(other)
     assert R.stub.rstub_protect_depth() == 0 and R.stub.rstub_transient_bytes() == 0
     # lifetime: GC finalises once, tolerates a second run, later use is a clean error
     R.stub.rstub_finalize(ptr)
