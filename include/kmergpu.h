@@ -99,6 +99,11 @@ int kmg_pairs_chunk(const kmg_index *idx, uint64_t first, uint64_t n, int32_t *o
  * the reference's R-level limit k <= 31 (src/kmer_hash.c:1163) is the glue's business. */
 int kmg_query_begin(const kmg_index *idx, const char *q, int64_t qlen, int k, kmg_query **st,
                     uint64_t *M);
+/* the same probe with reverseComplement(q) taken on the device (every dot plot of test.R:43-52,73 probes
+ * both strands; the reference's users make the reverse complement on the host): IUPAC complement, case
+ * kept, N and every other byte unchanged; i is a coordinate of the reverse-complemented string. */
+int kmg_query_begin_rc(const kmg_index *idx, const char *q, int64_t qlen, int k, kmg_query **st,
+                       uint64_t *M);
 int kmg_query_emit(kmg_query *st, int32_t *out /* 2M */);
 int kmg_query_emit_chunk(kmg_query *st, uint64_t first, uint64_t n, int32_t *out /* 2n */);
 int kmg_query_free(kmg_query *st);

@@ -198,12 +198,15 @@ def kmer_keys(ex_ptr) -> np.ndarray:
     return a
 
 
-def seq_kmer_pos(ex_ptr, seq, k, *, allow_k32: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+def seq_kmer_pos(ex_ptr, seq, k, *, allow_k32: bool = False, out: np.ndarray | None = None,
+                 reverse_complement: bool = False) -> np.ndarray:
     """seq.kmer.pos (kmer_hash.R:23-28 -> sequence_kmer_positions, src/kmer_hash.c:1151-1172).
 
     M x 2 int32 array, columns (i, j): i = 1-based END of the query k-mer, j = 1-based start in the
     index; rows ordered by i then j.  The reference's R entry rejects k > 31
     (src/kmer_hash.c:1163) although its C core handles k = 32; `allow_k32=True` lifts that guard.
+    `reverse_complement=True` probes reverseComplement(seq) instead, made on the device: the second half
+    of every dot plot in the reference's notebook (test.R:43-52,73); i then refers to that string.
     """
     ix = _extract(ex_ptr)
     if isinstance(seq, (list, tuple)):
@@ -215,7 +218,8 @@ def seq_kmer_pos(ex_ptr, seq, k, *, allow_k32: bool = False, out: np.ndarray | N
     if n <= k or k > (32 if allow_k32 else 31):
         raise ValueError("the sequence should be longer than k and k should not be longer than 31")
     st, M = C.c_void_p(), C.c_uint64()
-    check(_L.kmg_query_begin(ix._handle(), ptr, n, k, C.byref(st), C.byref(M)))
+    begin = _L.kmg_query_begin_rc if reverse_complement else _L.kmg_query_begin
+    check(begin(ix._handle(), ptr, n, k, C.byref(st), C.byref(M)))
     try:
         if M.value > INT_MAX:
             raise OverflowError(f"{M.value} result rows exceed an R matrix extent")

@@ -35,6 +35,7 @@ SIGNATURES = {
     "kmg_pairs": (C.c_int, [vp, vp]),
     "kmg_pairs_chunk": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp]),
     "kmg_query_begin": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(vp), u64p]),
+    "kmg_query_begin_rc": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(vp), u64p]),
     "kmg_query_emit": (C.c_int, [vp, vp]),
     "kmg_query_emit_chunk": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp]),
     "kmg_query_free": (C.c_int, [vp]),

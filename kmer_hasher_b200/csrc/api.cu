@@ -861,6 +861,35 @@ extern "C" int kmg_query_begin(const kmg_index *ix, const char *qseq, int64_t ql
   return rc;
 }
 
+// seq.kmer.pos(idx, reverseComplement(q), k) with the reverse complement taken on the device
+extern "C" int kmg_query_begin_rc(const kmg_index *ix, const char *qseq, int64_t qlen, int k, kmg_query **st, uint64_t *M) {
+  if (!st) return fail(KMG_ERR_ARG, "st is NULL");
+  *st = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (qlen < 0 || (qlen > 0 && !qseq)) return fail(KMG_ERR_ARG, "bad query pointer/length");
+  if (qlen + 1 > (int64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "query longer than int coordinates");
+  TRY(use_index(ix));
+  cudaStream_t s = g_ctx.stream();
+  DevSeq fwd, rc;
+  TRY(upload_seq(qseq, qlen, s, &fwd));
+  const size_t cap = 16 + (size_t)((qlen + 15) / 16) * 16 + 16;
+  int rcode = dalloc(&rc.buf, cap, s);
+  if (rcode != KMG_OK) { dfree(fwd.buf, s); return rcode; }
+  rc.base = rc.buf + 16; rc.len = qlen;
+  cudaMemsetAsync(rc.buf, 0, 16, s);
+  cudaMemsetAsync(rc.buf + cap - 32, 0, 32, s);
+  if (qlen > 0) {
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(qlen, 256), (int64_t)g_ctx.sms * 16);
+    LAUNCH("revcomp", s, revcomp_kernel<<<grid, 256, 0, s>>>(fwd.base, qlen, rc.base));
+    prof_bytes("revcomp", 2.0 * qlen);
+  }
+  SeqView sv;
+  sv.base = rc.base; sv.nstarts = qlen - k + 1 > 0 ? qlen - k + 1 : 0; sv.avail = qlen; sv.s0 = 0; sv.L = qlen; sv.k = k;
+  int rv = query_common(ix, true, sv, nullptr, nullptr, 0, st, M);
+  dfree(fwd.buf, s); dfree(rc.buf, s);
+  return rv;
+}
+
 extern "C" int kmg_query_records(const kmg_index *ix, const uint64_t *d_keys, const int32_t *d_i, int64_t n, kmg_query **st, uint64_t *M) {
   if (!st) return fail(KMG_ERR_ARG, "st is NULL");
   *st = nullptr;

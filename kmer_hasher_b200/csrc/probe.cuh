@@ -228,6 +228,27 @@ probe_emit_kernel(const int32_t *__restrict__ hit_i, const uint32_t *__restrict_
   }
 }
 
+// ---- reverse complement of a query on the device ---------------------------------------
+// Every dot plot in the reference's notebook probes the index twice, with the query and with
+// reverseComplement(query) made on the host (test.R:43-52,73).  out[i] = comp(in[L-1-i]) with the IUPAC
+// complement (A<->T, C<->G, R<->Y, K<->M, B<->V, D<->H; S, W, N and every other byte unchanged; case kept),
+// so probing `out` equals seq.kmer.pos on the host-made reverse complement, byte for byte.
+__device__ __forceinline__ uint8_t dna_complement(uint8_t c) {
+  const uint8_t up = c & 0xDFu, lower = c & 0x20u;
+  uint8_t r;
+  switch (up) {
+    case 'A': r = 'T'; break;  case 'T': r = 'A'; break;  case 'C': r = 'G'; break;  case 'G': r = 'C'; break;
+    case 'R': r = 'Y'; break;  case 'Y': r = 'R'; break;  case 'K': r = 'M'; break;  case 'M': r = 'K'; break;
+    case 'B': r = 'V'; break;  case 'V': r = 'B'; break;  case 'D': r = 'H'; break;  case 'H': r = 'D'; break;
+    default: return c;
+  }
+  return (uint8_t)(r | lower);       // c & 0xDF matched a letter, so c is that letter in either case
+}
+__global__ void revcomp_kernel(const uint8_t *__restrict__ in, int64_t L, uint8_t *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = dna_complement(in[L - 1 - i]);
+}
+
 // ---- kmer.pairs(a, b): positions of the k-mers two indexes share ----------------------------------------------
 // kmer_pair_pos (src/kmer_hash.c:1174-1203): for every k-mer of `a` that `b` also holds, rows (a_pos, b_pos),
 // a position outer, b position inner.  a's distinct keys are looked up in b's key table (probe_lookup_kernel,

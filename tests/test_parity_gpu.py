@@ -460,3 +460,33 @@ def test_kmer_pairs(kh, oracle, ka, kb):
     assert kh.kmer_pairs(empty, other).shape == (0, 2)
     for ix in (ia, ib, empty, other):
         ix.free()
+
+
+def _revcomp_host(seq: np.ndarray) -> np.ndarray:
+    """reverseComplement as Biostrings defines it for DNA: IUPAC complement, case kept, anything else unchanged."""
+    tab = np.arange(256, dtype=np.uint8)
+    for a, b in ("AT", "CG", "RY", "KM", "BV", "DH"):
+        for x, y in ((a, b), (b, a)):
+            tab[ord(x)] = ord(y)
+            tab[ord(x.lower())] = ord(y.lower())
+    return tab[seq[::-1]].copy()
+
+
+@pytest.mark.parametrize("k", [4, 16, 31])
+def test_reverse_complement_probe(kh, oracle, k):
+    """seq.kmer.pos on the reverse strand with the reverse complement taken on the device == the reference's
+    probe of the host-made reverse complement (what test.R:43-52 does with Biostrings)."""
+    from kmer_hasher_b200 import synth
+    seq = synth.config_c3(200_000, tail_k=k)
+    q = synth.config_c4_query(seq, 60_000)
+    q[100:110] = np.frombuffer(b"RYKMBVDHSW", np.uint8)          # IUPAC codes
+    q[200:204] = np.frombuffer(b"rykm", np.uint8)
+    q[300] = ord("-")
+    rc = _revcomp_host(q)
+    index_of_rc = kh.make_kmer_hash(_revcomp_host(seq), k)        # so that the reverse strand of q has hits
+    o = oracle.build(_revcomp_host(seq), k)
+    want = o.query(rc, k)
+    got = kh.seq_kmer_pos(index_of_rc, q, k, reverse_complement=True)
+    assert len(want) > 0 and np.array_equal(got.ravel(), want)
+    assert np.array_equal(kh.seq_kmer_pos(index_of_rc, rc, k).ravel(), want)
+    index_of_rc.free()
