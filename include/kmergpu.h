@@ -193,6 +193,7 @@ int kmg_profile_count(void);             /* number of distinct kernels seen     
 int kmg_profile_get(int i, const char **name, double *total_ms, uint64_t *launches,
                     double *algo_bytes);
 uint64_t kmg_launch_count(void);         /* kernels launched by this library since load         */
+int kmg_selftest_lane_order(uint32_t *failures); /* precondition of the one-atomic rank variant (sort.cuh) */
 int kmg_tune(const char *key, int value); /* tuning runs only: "sort_cfg" selects a pass variant  */
 
 #ifdef __cplusplus

@@ -68,6 +68,7 @@ SIGNATURES = {
     "kmg_profile_count": (C.c_int, []),
     "kmg_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p, C.POINTER(C.c_double)]),
     "kmg_launch_count": (C.c_uint64, []),
+    "kmg_selftest_lane_order": (C.c_int, [C.POINTER(C.c_uint32)]),
     "kmg_tune": (C.c_int, [C.c_char_p, C.c_int]),
 }
 

@@ -347,20 +347,32 @@ constexpr int PIDX_THREADS = 256, PIDX_ITEMS = 8, PIDX_TILE = PIDX_THREADS * PID
 
 // Pass configurations selectable at run time (KMG_SORT_CFG=<index>, for tuning runs):
 // <threads, records per thread, CTAs per SM, rank variant (1 ballots, 0 bitmap), look-back width>.
-using Cfg0 = PassCfg<256, 24, 2, 0, 8>;   // default (profiles/r01_sort_pass_tuning.md)
-using Cfg1 = PassCfg<256, 24, 2, 1, 8>;
-using Cfg2 = PassCfg<256, 24, 2, 2, 8>;
-using Cfg3 = PassCfg<256, 16, 3, 0, 8>;
-using Cfg4 = PassCfg<256, 16, 3, 1, 8>;
-using Cfg5 = PassCfg<256, 20, 2, 0, 8>;
-constexpr int N_SORT_CFG = 6;
+using Cfg0 = PassCfg<256, 24, 2, 0, 8>;   // bitmap match: the default where the lane-order check fails
+using Cfg1 = PassCfg<256, 24, 2, 1, 8>;   // ballot match
+using Cfg2 = PassCfg<256, 24, 2, 2, 8>;   // half ballots, half bitmaps
+using Cfg3 = PassCfg<256, 24, 2, 3, 4>;   // one atomic per record: the default where the lane-order check passes
+using Cfg4 = PassCfg<256, 24, 2, 3, 8>;
+using Cfg5 = PassCfg<256, 16, 3, 3, 8>;
+using Cfg6 = PassCfg<512, 12, 2, 3, 8>;
+using Cfg7 = PassCfg<256, 24, 2, 3, 16>;
+constexpr int N_SORT_CFG = 8;
 static int g_sort_cfg = -1;
 static uint32_t g_sort_dbg = 0;
+static int lane_order_failures(uint32_t *failures);
+static bool log_on();
+// The pass variant: KMG_SORT_CFG / kmg_tune if given; else the one-atomic variant (3) when this device applies
+// colliding shared-memory atomics of one instruction in lane order (checked once), the bitmap variant (0) if not.
 static int sort_cfg() {
   if (g_sort_cfg < 0) {
     const char *e = getenv("KMG_SORT_CFG");
-    int v = e ? atoi(e) : 0;
-    g_sort_cfg = (v >= 0 && v < N_SORT_CFG) ? v : 0;
+    if (e) {
+      const int v = atoi(e);
+      g_sort_cfg = (v >= 0 && v < N_SORT_CFG) ? v : 0;
+    } else {
+      uint32_t f = 1;
+      g_sort_cfg = (lane_order_failures(&f) == KMG_OK && f == 0) ? 3 : 0;
+      if (log_on()) fprintf(stderr, "[kmergpu] lane-order self-test: %u failures -> sort pass variant %d\n", f, g_sort_cfg);
+    }
   }
   return g_sort_cfg;
 }
@@ -385,6 +397,24 @@ extern "C" int kmg_tune(const char *key, int value) {
   }
   return fail(KMG_ERR_ARG, "unknown tuning key");
 }
+// RANK 3's precondition, checked on the current device: failures = 0 means the lanes of one shared-memory
+// atomic instruction that collide on an address are applied in ascending lane order.
+static int lane_order_failures(uint32_t *failures) {
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  uint32_t *bad = nullptr;
+  TRY(dalloc(&bad, 1, s));
+  CU(cudaMemsetAsync(bad, 0, 4, s));
+  LAUNCH("lane_order_selftest", s, lane_order_selftest_kernel<<<g_ctx.sms * 4, 256, 0, s>>>(bad));
+  CU(cudaMemcpyAsync(failures, bad, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  dfree(bad, s);
+  return KMG_OK;
+}
+extern "C" int kmg_selftest_lane_order(uint32_t *failures) {
+  if (!failures) return fail(KMG_ERR_ARG, "failures is NULL");
+  return lane_order_failures(failures);
+}
 constexpr int SORT_TILE_MIN = 2048;   // status/scratch sizing: smallest tile of any configuration
 
 template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false>
@@ -401,7 +431,7 @@ template <bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
 static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
   switch (sort_cfg()) {
 #define KMG_CASE(i) case i: return launch_pass_cfg<Cfg##i, FROM_SEQ, BinFn, NextFn, HAS_NEXT>(name, P, n_upper, s);
-    KMG_CASE(0) KMG_CASE(1) KMG_CASE(2) KMG_CASE(3) KMG_CASE(4) KMG_CASE(5)
+    KMG_CASE(0) KMG_CASE(1) KMG_CASE(2) KMG_CASE(3) KMG_CASE(4) KMG_CASE(5) KMG_CASE(6) KMG_CASE(7)
 #undef KMG_CASE
   }
   return fail(KMG_ERR_ARG, "bad sort configuration");
@@ -1278,6 +1308,7 @@ extern "C" int kmg_shard_scatter(const kmg_shard *sh, const uint64_t *d_splitter
     P.pos_add = (uint32_t)pos_add;
     P.peer = tab;
     P.bin = ob;
+    // few bins, many lanes per bin: the bitmap variant measured best here (0.51 ms at N=2; ballots 0.54 ms)
     TRY((launch_pass_cfg<Cfg0, true, OwnerBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
     prof_bytes("scatter_peer", (double)sh->sv.avail + 12.0 * (double)sh->sv.nstarts);
     return KMG_OK;

@@ -82,12 +82,16 @@ struct PassParams {
 };
 
 // Tuning knobs of one pass (chosen per launch by the host, see api.cu).
-//   RANK 1: peers of a record (same bin, same warp step) from 8 ballots, no shared memory;
-//   RANK 0: peers through a per-warp bitmap table (atomicOr the lane bit, read back, leader clears).
+//   RANK 3: ONE shared-memory atomicAdd per record on the warp's bin counter; its return value is the rank.
+//           Needs colliding lanes of one instruction to be applied in ascending lane order, which the library
+//           verifies per device before using it (lane_order_selftest_kernel); the default when that holds;
+//   RANK 0: peers through a per-warp bitmap table (atomicOr the lane bit, read back, leader clears): the
+//           default otherwise;
+//   RANK 1: peers of a record (same bin, same warp step) from 8 ballots, no shared memory; RANK 2: half/half.
 //   LB    : status words fetched per look-back round trip.
 // Measured and dropped on B200 (profiles/r01_sort_pass_tuning.md): __match_any_sync (20 % slower
 // than ballots), several items per bitmap round trip, two interleaved rank chains, cp.async of the
-// positions.
+// positions, persistent CTAs that claim the next ticket early and prefetch its records into L2 (13 % slower).
 template <int THREADS_, int ITEMS_, int MINBLOCKS_, int RANK_ = 1, int LB_ = 8>
 struct PassCfg {
   static constexpr int THREADS = THREADS_, ITEMS = ITEMS_, MINBLOCKS = MINBLOCKS_, RANK = RANK_, LB = LB_;
@@ -102,7 +106,7 @@ struct PassSmem {
   uint64_t keys[TILE];
   PosT pos[TILE];
   uint32_t whist[WARPS][RADIX];                        // per-warp bin counts, later the warp's first slot of the bin
-  uint32_t match[Cfg::RANK != 1 ? WARPS * RADIX : 1];  // RANK 0: lane bitmaps of the item being matched (self-clearing)
+  uint32_t match[(Cfg::RANK == 0 || Cfg::RANK == 2) ? WARPS * RADIX : 1];  // RANK 0: lane bitmaps of the item being matched (self-clearing)
   int32_t goff[RADIX];                                 // global index of the bin's first record of this tile - its tile slot
   uint32_t next[RADIX];
   uint32_t scratch[8];
@@ -129,6 +133,42 @@ __device__ __forceinline__ uint32_t match_bin(uint32_t d, uint32_t active) {
   KMG_MATCH_BIT(16); KMG_MATCH_BIT(32); KMG_MATCH_BIT(64); KMG_MATCH_BIT(128);
 #undef KMG_MATCH_BIT
   return peers;
+}
+
+// Do the lanes of one shared-memory atomic instruction that hit the same address get their old values in
+// ascending lane order?  (RANK 3 needs it.)  Several collision patterns, many repetitions; *bad counts failures.
+__global__ void lane_order_selftest_kernel(uint32_t *bad) {
+  __shared__ uint32_t tab[8][RADIX];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t fails = 0;
+  for (int rep = 0; rep < 64; ++rep) {
+    for (int b = lane; b < RADIX; b += 32) tab[warp][b] = 0;
+    __syncwarp();
+    for (int pattern = 0; pattern < 6; ++pattern) {
+      uint32_t d;
+      switch (pattern) {
+        case 0: d = 7; break;                                   // all lanes one address
+        case 1: d = lane & 1; break;                            // two addresses, interleaved
+        case 2: d = lane >> 3; break;                           // four runs
+        case 3: d = (lane * 2654435761u + rep * 40503u) >> 29; break;   // 8 addresses, scattered
+        case 4: d = (lane * 2246822519u + rep * 97u) & 255u; break;     // mostly distinct
+        default: d = (lane % 3 == 0) ? 200 : lane; break;
+      }
+      const uint32_t before = tab[warp][d];
+      __syncwarp();
+      const uint32_t got = atomicAdd(&tab[warp][d], 1u);
+      uint32_t peers = FULL_MASK_;
+#pragma unroll
+      for (int b = 0; b < RADIX_BITS; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(FULL_MASK_, bit);
+        peers &= bit ? bal : ~bal;
+      }
+      if (got != before + __popc(peers & lanemask_lt())) ++fails;
+      __syncwarp();
+    }
+  }
+  if (fails) atomicAdd(bad, fails);
 }
 
 // One tile.  FULL: every slot of the tile holds a valid record (no predicates on the hot path).
@@ -178,7 +218,21 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     for (int i = 0; i < ITEMS; ++i) dpk[i >> 2] |= P.bin(key[i]) << (8 * (i & 3));
   }
 #define KMG_BIN(i) (BinFn::CHEAP ? P.bin(key[i]) : ((dpk[(i) >> 2] >> (8 * ((i) & 3))) & 0xFFu))
-  if constexpr (Cfg::RANK >= 1) {
+  if constexpr (Cfg::RANK == 3) {
+    // One shared-memory atomic per record: the value it returns is the record's rank among the warp's
+    // earlier records of the bin, PROVIDED the hardware applies the lanes of one instruction that hit the
+    // same address in ascending lane order.  PTX does not promise that; the library checks it once per
+    // device (lane_order_selftest_kernel) and never selects this variant unless the check passed.
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const uint32_t d = KMG_BIN(i);
+      const bool ok = FULL || ((valid >> i) & 1u);
+      uint32_t r = 0;
+      if (ok) r = atomicAdd(&sm.whist[warp][d], 1u);
+      rk[i] = (d << 16) | r;
+      if constexpr (!FULL) __syncwarp();                 // keep the steps in order when the guard diverges
+    }
+  } else if constexpr (Cfg::RANK >= 1) {
     // RANK 2: odd items go through the bitmap table instead, so the ALU (ballots) and the
     // shared-memory pipe (bitmaps) share the ranking work.
     // phase A: peers of the ballot items (no memory: all steps overlap)
@@ -375,7 +429,7 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
     uint4 *zw = reinterpret_cast<uint4 *>(sm.whist[warp]);
 #pragma unroll
     for (int j = 0; j < RADIX / 4 / 32; ++j) zw[j * 32 + lane] = make_uint4(0, 0, 0, 0);
-    if constexpr (Cfg::RANK != 1) {
+    if constexpr (Cfg::RANK == 0 || Cfg::RANK == 2) {
       uint4 *zm = reinterpret_cast<uint4 *>(sm.match + warp * RADIX);
 #pragma unroll
       for (int j = 0; j < RADIX / 4 / 32; ++j) zm[j * 32 + lane] = make_uint4(0, 0, 0, 0);
