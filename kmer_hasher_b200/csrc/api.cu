@@ -340,8 +340,9 @@ struct kmg_query {
 };
 
 constexpr int HIST_THREADS = 512, HIST_ITEMS = 16, HIST_TILE = HIST_THREADS * HIST_ITEMS;
-constexpr int RLE_THREADS = 256, RLE_ITEMS = 16, RLE_TILE = RLE_THREADS * RLE_ITEMS;
+constexpr int RLE_THREADS = 256, RLE_ITEMS = 32, RLE_TILE = RLE_THREADS * RLE_ITEMS;
 constexpr int PROBE_THREADS = 256, PROBE_ITEMS = 8, PROBE_TILE = PROBE_THREADS * PROBE_ITEMS;
+constexpr int COMPACT_ITEMS = 8, COMPACT_TILE = PROBE_THREADS * COMPACT_ITEMS;
 constexpr int EMIT_THREADS = 256, EMIT_TILE = EMIT_THREADS * 8;
 constexpr int PIDX_THREADS = 256, PIDX_ITEMS = 8, PIDX_TILE = PIDX_THREADS * PIDX_ITEMS;
 
@@ -835,7 +836,7 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
   uint32_t *ticket = nullptr;
   uint2 *found = nullptr;
   auto body = [&]() -> int {
-    const uint64_t tiles = ceil_div<uint64_t>((uint64_t)total, PROBE_TILE);
+    const uint64_t tiles = ceil_div<uint64_t>((uint64_t)total, COMPACT_TILE);
     TRY(dalloc(&q->hit_i, (size_t)total, s));
     TRY(dalloc(&q->hit_start, (size_t)total, s));
     TRY(dalloc(&q->row_off, (size_t)total, s));
@@ -850,11 +851,11 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
     const unsigned ltiles = (unsigned)ceil_div<uint64_t>((uint64_t)total, PROBE_TILE);
     if (from_seq) {
       LAUNCH("probe_lookup", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, true><<<ltiles, PROBE_THREADS, 0, s>>>(sv, nullptr, 0, nullptr, kt, found));
-      LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, PROBE_ITEMS, true><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+      LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, COMPACT_ITEMS, true><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
                                      found, sv.s0 + sv.k, nullptr, total, nullptr, q->hit_i, q->hit_start, q->row_off, qs, status, ticket));
     } else {
       LAUNCH("probe_lookup_rec", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<ltiles, PROBE_THREADS, 0, s>>>(sv, d_keys, n, d_n, kt, found));
-      LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+      LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, COMPACT_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
                                      found, 0, d_i, n, d_n, q->hit_i, q->hit_start, q->row_off, qs, status, ticket));
     }
     QueryStats h;
