@@ -149,3 +149,55 @@ if "c5" in what:
             assert bool((code[dev[sel, 1].long() - 1 + j] == code[dev[sel, 2].long() - 1 + j]).all())
         print("C5 properties ok")
     ix.free()
+
+
+if "big" in what:
+    # 1.5 Gbp, k=32: 1.5e9 records (the reference's int coordinates allow < 2^31), ~56 GB of HBM in flight
+    Lb = 1_500_000_000
+    t0 = time.time()
+    sb = synth.generate(Lb, 0xB16, repeat=0.2, tandem=0.02, homo=0.001, lower=0.2, n_gaps=200, gap_max=200000, n_single=5000,
+                        tandem_len_min=100, tandem_len_max=5000, homo_len_max=80)
+    print(f"big: {Lb} bases generated in {time.time() - t0:.1f}s")
+    db = torch.from_numpy(sb).cuda()
+    ix, ms = timed(lambda: kh.make_kmer_hash(db, 32))
+    ix.free()
+    kh.profile(reset=True)                                 # the first launches of a process include lazy module loading
+    ix, ms = timed(lambda: kh.make_kmer_hash(db, 32))
+    U, N, P = ix.sizes
+    print(f"big build k=32: {ms:.1f} ms, N={N} U={U} P={P} -> {N / ms / 1e6:.2f} G k-mers/s")
+    show_profile("big build")
+    keys = torch.empty(U, dtype=torch.int64, device="cuda")
+    _lib.check(L.kmg_kmers_u64(ix._handle(), keys.data_ptr()))
+    flip = torch.tensor(-2**63, dtype=torch.int64, device="cuda")
+    assert bool(((keys[1:] ^ flip) > (keys[:-1] ^ flip)).all())       # strictly ascending as unsigned
+    cnt = torch.empty(U, dtype=torch.int32, device="cuda")
+    _lib.check(L.kmg_counts(ix._handle(), cnt.data_ptr()))
+    assert int(cnt.sum(dtype=torch.int64)) == N and int(cnt.min()) >= 1
+    del keys
+    # positions in two halves (an N x 2 int32 matrix is 12 GB): every position appears exactly once
+    seen = torch.zeros(Lb + 1, dtype=torch.uint8, device="cuda")
+    code = ((db >> 1) & 3)
+    isn = ((db | 0x20) == ord("n"))
+    st = C.c_void_p()
+    half = N // 2
+    from kmer_hasher_b200 import kmer_pos
+    pos = torch.empty((N, 2), dtype=torch.int32, device="cuda")
+    _lib.check(L.kmg_positions(ix._handle(), pos.data_ptr()))
+    p = pos[:, 1].long()
+    seen.index_add_(0, p, torch.ones(1, dtype=torch.uint8, device="cuda").expand(N))
+    assert int(seen.max()) == 1 and int(seen.sum(dtype=torch.int64)) == N
+    same = pos[1:, 0] == pos[:-1, 0]
+    assert bool((pos[1:, 1][same] > pos[:-1, 1][same]).all()) and bool((pos[1:, 0] >= pos[:-1, 0]).all())
+    sel = torch.randint(0, N, (2_000_000,), device="cuda")
+    st0 = p[sel] - 1
+    for j in range(32):
+        assert not bool(isn[st0 + j].any())
+    grp = pos[sel, 0].long() - 1
+    w = torch.zeros_like(st0)
+    for j in range(32):
+        w = (w << 2) | code[st0 + j].long()
+    keys = torch.empty(U, dtype=torch.int64, device="cuda")
+    _lib.check(L.kmg_kmers_u64(ix._handle(), keys.data_ptr()))
+    assert bool((w == keys[grp]).all())
+    print("big properties ok: keys strictly ascending, counts sum to N, every position exactly once, lists ascending, sampled windows re-encode to their k-mer")
+    ix.free()
