@@ -40,24 +40,32 @@ __device__ __forceinline__ uint64_t hash64(uint64_t x) {
   return x;
 }
 
-// Distinct keys only; a slot is claimed by a CAS on its count word.  Nobody reads the table before this
-// kernel has finished, so key/start can be written after the claim.
+// compare a 16-byte slot with all-zero and swap `desired` in (one 128-bit CAS, sm_90+); true if it was empty
+__device__ __forceinline__ bool claim_slot(uint4 *slot, uint4 desired) {
+  uint64_t olo, ohi;
+  const uint64_t dlo = (uint64_t)desired.x | ((uint64_t)desired.y << 32), dhi = (uint64_t)desired.z | ((uint64_t)desired.w << 32);
+  asm volatile(
+      "{\n\t.reg .b128 cmp, val, old;\n\t"
+      "mov.b128 cmp, {%3, %3};\n\t"
+      "mov.b128 val, {%4, %5};\n\t"
+      "atom.relaxed.gpu.global.cas.b128 old, [%2], cmp, val;\n\t"
+      "mov.b128 {%0, %1}, old;\n\t}"
+      : "=l"(olo), "=l"(ohi) : "l"(slot), "l"((uint64_t)0), "l"(dlo), "l"(dhi) : "memory");
+  return olo == 0 && ohi == 0;
+}
+
+// Distinct keys only: one 128-bit CAS claims a slot and fills it (a stored slot is never all-zero: count >= 1).
 __global__ void hash_insert_kernel(const uint64_t *__restrict__ ukeys, const uint32_t *__restrict__ ustart, uint64_t U, KeyHash kh) {
   for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t key = ukeys[u];
     const uint32_t start = ustart[u], count = ustart[u + 1] - start;
+    const uint4 rec = make_uint4((uint32_t)key, (uint32_t)(key >> 32), start, count);
     uint64_t b = hash64(key) & kh.bmask;
     bool placed = false;
     while (!placed) {
 #pragma unroll
-      for (int j = 0; j < BUCKET_SLOTS; ++j) {
-        if (placed) break;
-        uint32_t *slot = reinterpret_cast<uint32_t *>(kh.slots + b * BUCKET_SLOTS + j);
-        if (atomicCAS(slot + 3, 0u, count) == 0u) {
-          slot[0] = (uint32_t)key; slot[1] = (uint32_t)(key >> 32); slot[2] = start;
-          placed = true;
-        }
-      }
+      for (int j = 0; j < BUCKET_SLOTS; ++j)
+        if (!placed) placed = claim_slot(kh.slots + b * BUCKET_SLOTS + j, rec);
       b = (b + 1) & kh.bmask;
     }
   }
