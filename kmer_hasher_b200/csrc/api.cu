@@ -663,24 +663,28 @@ template <class Emit>
 static int stream_rows(uint64_t total, size_t row_bytes, void *out, uint64_t chunk_rows, Emit emit) {
   if (total == 0) return KMG_OK;
   cudaStream_t s = g_ctx.stream();
-  if (ptr_kind(out) == PK_DEVICE) {
-    TRY(emit((uint64_t)0, total, out, s));
-    CU(cudaStreamSynchronize(s));
-    return KMG_OK;
+  const bool to_device = ptr_kind(out) == PK_DEVICE;
+  if (!to_device) chunk_rows = std::min<uint64_t>(chunk_rows, total);
+  uint64_t *blk = nullptr;                             // first segment of every EMIT_TILE-row block of the chunk being emitted
+  TRY(dalloc(&blk, (size_t)ceil_div<uint64_t>(to_device ? total : chunk_rows, EMIT_TILE), s));
+  if (to_device) {
+    int rc = emit((uint64_t)0, total, out, blk, s);
+    if (rc == KMG_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(KMG_ERR_CUDA, "extraction failed: %s", cudaGetErrorString(cudaGetLastError()));
+    dfree(blk, s);
+    return rc;
   }
-  chunk_rows = std::min<uint64_t>(chunk_rows, total);
   char *buf[2] = {nullptr, nullptr};
-  TRY(dalloc(&buf[0], chunk_rows * row_bytes, s));
-  if (total > chunk_rows) TRY(dalloc(&buf[1], chunk_rows * row_bytes, s));
+  int rc = dalloc(&buf[0], chunk_rows * row_bytes, s);
+  if (rc == KMG_OK && total > chunk_rows) rc = dalloc(&buf[1], chunk_rows * row_bytes, s);
+  if (rc != KMG_OK) { dfree(buf[0], s); dfree(blk, s); return rc; }
   cudaStream_t cs = g_ctx.copy;
   cudaEvent_t *ev = g_ctx.ev;                        // ev[0..1] kernel done, ev[2..3] copy done
-  int rc = KMG_OK;
   uint64_t done = 0;
   for (int c = 0; done < total && rc == KMG_OK; ++c, done += chunk_rows) {
     const int b = c & 1;
     const uint64_t rows = std::min<uint64_t>(chunk_rows, total - done);
     if (c >= 2) cudaStreamWaitEvent(s, ev[2 + b], 0);          // buffer b free again
-    rc = emit(done, rows, (void *)buf[b], s);
+    rc = emit(done, rows, (void *)buf[b], blk, s);
     if (rc != KMG_OK) break;
     cudaEventRecord(ev[b], s);
     cudaStreamWaitEvent(cs, ev[b], 0);
@@ -690,7 +694,7 @@ static int stream_rows(uint64_t total, size_t row_bytes, void *out, uint64_t chu
   }
   cudaStreamSynchronize(cs);
   cudaStreamSynchronize(s);
-  dfree(buf[0], s); dfree(buf[1], s);
+  dfree(buf[0], s); dfree(buf[1], s); dfree(blk, s);
   if (rc == KMG_OK) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = fail(KMG_ERR_CUDA, "extraction failed: %s", cudaGetErrorString(e));
@@ -698,6 +702,14 @@ static int stream_rows(uint64_t total, size_t row_bytes, void *out, uint64_t chu
   return rc;
 }
 constexpr uint64_t CHUNK_BYTES = uint64_t(256) << 20;
+
+// first segment of every EMIT_TILE-row block of a chunk (see segment_starts_kernel) into stream_rows' scratch
+template <typename OffT>
+static int block_starts(const OffT *off, uint64_t cnt, uint64_t first, uint64_t rows, cudaStream_t s, uint64_t *blk) {
+  const uint64_t nb = ceil_div<uint64_t>(rows, EMIT_TILE);
+  LAUNCH("segment_starts", s, segment_starts_kernel<OffT><<<(unsigned)ceil_div<uint64_t>(nb, 128), 128, 0, s>>>(off, cnt, first, EMIT_TILE, nb, blk));
+  return KMG_OK;
+}
 
 extern "C" int kmg_kmers_u64(const kmg_index *ix, uint64_t *keys) {
   TRY(use_index(ix));
@@ -716,7 +728,7 @@ extern "C" int kmg_kmers_ascii(const kmg_index *ix, char *out) {
   const int k = ix->k;
   const uint64_t *ukeys = ix->ukeys;
   const int sms = g_ctx.sms;
-  int rc = stream_rows(ix->U, stride, out, CHUNK_BYTES / stride, [=](uint64_t first, uint64_t rows, void *dst, cudaStream_t s) -> int {
+  int rc = stream_rows(ix->U, stride, out, CHUNK_BYTES / stride, [=](uint64_t first, uint64_t rows, void *dst, uint64_t *, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(rows * stride, 256), (uint64_t)sms * 16);
     LAUNCH("kmers_ascii", s, kmers_ascii_kernel<<<grid, 256, 0, s>>>(ukeys + first, rows, k, (char *)dst));
     return KMG_OK;
@@ -731,7 +743,7 @@ extern "C" int kmg_counts(const kmg_index *ix, int32_t *out) {
   if (ix->maxc > (uint32_t)INT32_MAX) return fail(KMG_ERR_RANGE, "a count exceeds int");
   const uint32_t *ustart = ix->ustart;
   const int sms = g_ctx.sms;
-  int rc = stream_rows(ix->U, 4, out, CHUNK_BYTES / 4, [=](uint64_t first, uint64_t rows, void *dst, cudaStream_t s) -> int {
+  int rc = stream_rows(ix->U, 4, out, CHUNK_BYTES / 4, [=](uint64_t first, uint64_t rows, void *dst, uint64_t *, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(rows, 256), (uint64_t)sms * 16);
     LAUNCH("counts", s, counts_kernel<<<grid, 256, 0, s>>>(ustart + first, rows, (int32_t *)dst));
     return KMG_OK;
@@ -745,9 +757,10 @@ extern "C" int kmg_positions(const kmg_index *ix, int32_t *out) {
   if (!out && ix->N) return fail(KMG_ERR_ARG, "out is NULL");
   const uint32_t *ustart = ix->ustart, *pos = ix->pos;
   const uint64_t U = ix->U, N = ix->N;
-  int rc = stream_rows(N, 8, out, CHUNK_BYTES / 8, [=](uint64_t first, uint64_t rows, void *dst, cudaStream_t s) -> int {
+  int rc = stream_rows(N, 8, out, CHUNK_BYTES / 8, [=](uint64_t first, uint64_t rows, void *dst, uint64_t *blk, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
-    LAUNCH("positions", s, positions_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, U, pos, first, rows, (int2 *)dst));
+    TRY(block_starts(ustart, U, first, rows, s, blk));
+    LAUNCH("positions", s, positions_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, U, pos, first, rows, blk, (int2 *)dst));
     return KMG_OK;
   });
   prof_bytes("positions", 4.0 * U + 12.0 * N);
@@ -787,9 +800,10 @@ extern "C" int kmg_pairs_chunk(const kmg_index *cix, uint64_t first, uint64_t n,
   const uint32_t *ustart = ix->ustart, *pos = ix->pos, *multi_u = ix->multi_u;
   const uint64_t *pair_off = ix->pair_off;
   const uint64_t n_multi = ix->multi;
-  int rc = stream_rows(n, 12, out, CHUNK_BYTES / 12, [=](uint64_t f, uint64_t rows, void *dst, cudaStream_t s) -> int {
+  int rc = stream_rows(n, 12, out, CHUNK_BYTES / 12, [=](uint64_t f, uint64_t rows, void *dst, uint64_t *blk, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
-    LAUNCH("pairs", s, pairs_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, pos, multi_u, pair_off, n_multi, first + f, rows, (int32_t *)dst));
+    TRY(block_starts(pair_off, n_multi, first + f, rows, s, blk));
+    LAUNCH("pairs", s, pairs_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, pos, multi_u, pair_off, n_multi, first + f, rows, blk, (int32_t *)dst));
     return KMG_OK;
   });
   prof_bytes("pairs", 12.0 * n);
@@ -941,9 +955,10 @@ extern "C" int kmg_query_emit_chunk(kmg_query *q, uint64_t first, uint64_t n, in
   const uint32_t *hit_start = q->hit_start, *pos = ix->pos;
   const uint64_t *row_off = q->row_off;
   const uint64_t H = q->H;
-  int rc = stream_rows(n, 8, out, CHUNK_BYTES / 8, [=](uint64_t f, uint64_t rows, void *dst, cudaStream_t s) -> int {
+  int rc = stream_rows(n, 8, out, CHUNK_BYTES / 8, [=](uint64_t f, uint64_t rows, void *dst, uint64_t *blk, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
-    LAUNCH("probe_emit", s, probe_emit_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(hit_i, hit_start, row_off, H, pos, first + f, rows, (int2 *)dst));
+    TRY(block_starts(row_off, H, first + f, rows, s, blk));
+    LAUNCH("probe_emit", s, probe_emit_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(hit_i, hit_start, row_off, H, pos, first + f, rows, blk, (int2 *)dst));
     return KMG_OK;
   });
   prof_bytes("probe_emit", 12.0 * n);
@@ -1052,9 +1067,10 @@ extern "C" int kmg_join_emit_chunk(kmg_join *j, uint64_t first, uint64_t n, int3
   const uint32_t *ha = j->hit_astart, *hb = j->hit_bstart, *hc = j->hit_cb, *pa = j->a->pos, *pb = j->b->pos;
   const uint64_t *row_off = j->row_off;
   const uint64_t H = j->H;
-  int rc = stream_rows(n, 8, out, CHUNK_BYTES / 8, [=](uint64_t f, uint64_t rows, void *dst, cudaStream_t s) -> int {
+  int rc = stream_rows(n, 8, out, CHUNK_BYTES / 8, [=](uint64_t f, uint64_t rows, void *dst, uint64_t *blk, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
-    LAUNCH("join_emit", s, join_emit_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ha, hb, hc, row_off, H, pa, pb, first + f, rows, (int2 *)dst));
+    TRY(block_starts(row_off, H, first + f, rows, s, blk));
+    LAUNCH("join_emit", s, join_emit_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ha, hb, hc, row_off, H, pa, pb, first + f, rows, blk, (int2 *)dst));
     return KMG_OK;
   });
   prof_bytes("join_emit", 16.0 * n);

@@ -138,43 +138,30 @@ stats_kernel(const uint32_t *__restrict__ ustart, IndexStats *st) {
 // ---- shared helper: which segment does each of a block's rows fall in? -----------------------------------
 // off[0..cnt) strictly increasing, off[0] <= r0.  For rows r0 .. r0+T the block computes
 // seg[s] = (largest m with off[m] <= r0+s) - m_first, and returns m_first.
+// For every block of T consecutive rows starting at first + b*T: the largest m with off[m] <= that row
+// (off[0..cnt) strictly increasing, off[0] <= first).  One thread per block; a few microseconds per chunk.
+template <typename OffT>
+__global__ void segment_starts_kernel(const OffT *__restrict__ off, uint64_t cnt, uint64_t first, uint64_t T, uint64_t nblocks,
+                                      uint64_t *__restrict__ out) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const uint64_t r0 = first + b * T;
+  uint64_t lo = 0, hi = cnt;                             // invariant: off[lo] <= r0 < off[hi] (off[cnt] = +inf)
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if ((uint64_t)off[mid] <= r0) lo = mid; else hi = mid;
+  }
+  out[b] = lo;
+}
+
 template <int THREADS, int PER, typename OffT>
-__device__ __forceinline__ uint64_t block_segments(const OffT *__restrict__ off, uint64_t cnt, uint64_t r0,
+__device__ __forceinline__ uint64_t block_segments(const OffT *__restrict__ off, uint64_t cnt, uint64_t r0, uint64_t m_first_in,
                                                    uint8_t *s_flag /* THREADS*PER */, uint32_t *s_seg /* THREADS*PER */,
                                                    uint32_t *s_warp /* THREADS/32 */, uint64_t *s_first) {
   static_assert(PER == 8, "flags are read as one 64-bit word per thread");
   constexpr int T = THREADS * PER, WARPS = THREADS / 32;
   const unsigned tid = threadIdx.x;
-  {                                                      // largest m with off[m] <= r0: THREADS-ary search by the whole block
-    uint64_t lo = 0, hi = cnt;                           // invariant: off[lo] <= r0 < off[hi] (off[cnt] = +inf)
-    while (hi - lo > 1) {
-      const uint64_t span = hi - lo;
-      // thread t probes lo + ceil(span * (t+1) / (THREADS+1)) clipped to (lo, hi)
-      uint64_t m = lo + (span * (tid + 1) + THREADS) / (THREADS + 1);
-      if (m >= hi) m = hi - 1;
-      const bool le = m > lo && (uint64_t)off[m] <= r0;
-      if (tid == 0) *s_first = lo;
-      __syncthreads();
-      if (le) atomicMax(reinterpret_cast<unsigned long long *>(s_first), (unsigned long long)m);
-      __syncthreads();
-      const uint64_t nlo = *s_first;
-      // the new upper bound is the smallest probe above nlo that failed (probes are non-decreasing in t)
-      uint64_t nhi = hi;
-      {
-        const uint64_t mt = m;
-        const bool gt = mt > nlo && !le;
-        __syncthreads();
-        if (tid == 0) s_warp[0] = 0xFFFFFFFFu;
-        __syncthreads();
-        if (gt) atomicMin(&s_warp[0], (uint32_t)(mt - lo));
-        __syncthreads();
-        if (s_warp[0] != 0xFFFFFFFFu) nhi = lo + s_warp[0];
-      }
-      __syncthreads();
-      lo = nlo; hi = nhi;
-    }
-    if (tid == 0) *s_first = lo;
-  }
+  if (tid == 0) *s_first = m_first_in;                   // from segment_starts_kernel: largest m with off[m] <= r0
   reinterpret_cast<uint64_t *>(s_flag)[tid] = 0;
   __syncthreads();
   const uint64_t m_first = *s_first;
@@ -220,7 +207,7 @@ __global__ void counts_kernel(const uint32_t *__restrict__ ustart, uint64_t U, i
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 positions_kernel(const uint32_t *__restrict__ ustart, uint64_t U, const uint32_t *__restrict__ pos, uint64_t first,
-                 uint64_t nrows, int2 *__restrict__ out) {
+                 uint64_t nrows, const uint64_t *__restrict__ blk_first, int2 *__restrict__ out) {
   constexpr int PER = 8, T = THREADS * PER;
   __shared__ __align__(16) uint8_t s_flag[T];
   __shared__ __align__(16) uint32_t s_seg[T];
@@ -229,7 +216,7 @@ positions_kernel(const uint32_t *__restrict__ ustart, uint64_t U, const uint32_t
   const uint64_t b0 = (uint64_t)blockIdx.x * T;
   if (b0 >= nrows) return;
   const uint64_t r0 = first + b0;
-  const uint64_t u0 = block_segments<THREADS, PER, uint32_t>(ustart, U, r0, s_flag, s_seg, s_warp, &s_first);
+  const uint64_t u0 = block_segments<THREADS, PER, uint32_t>(ustart, U, r0, blk_first[blockIdx.x], s_flag, s_seg, s_warp, &s_first);
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const uint32_t s = j * THREADS + threadIdx.x;
@@ -312,7 +299,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 pairs_kernel(const uint32_t *__restrict__ ustart, const uint32_t *__restrict__ pos,
              const uint32_t *__restrict__ multi_u, const uint64_t *__restrict__ pair_off, uint64_t n_multi,
-             uint64_t first, uint64_t nrows, int32_t *__restrict__ out) {
+             uint64_t first, uint64_t nrows, const uint64_t *__restrict__ blk_first, int32_t *__restrict__ out) {
   constexpr int PER = 8, T = THREADS * PER;
   __shared__ __align__(16) uint8_t s_flag[T];
   __shared__ __align__(16) uint32_t s_seg[T];
@@ -321,7 +308,7 @@ pairs_kernel(const uint32_t *__restrict__ ustart, const uint32_t *__restrict__ p
   const uint64_t b0 = (uint64_t)blockIdx.x * T;
   if (b0 >= nrows) return;
   const uint64_t r0 = first + b0;
-  const uint64_t m0 = block_segments<THREADS, PER, uint64_t>(pair_off, n_multi, r0, s_flag, s_seg, s_warp, &s_first);
+  const uint64_t m0 = block_segments<THREADS, PER, uint64_t>(pair_off, n_multi, r0, blk_first[blockIdx.x], s_flag, s_seg, s_warp, &s_first);
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const uint32_t s = j * THREADS + threadIdx.x;

@@ -216,7 +216,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 probe_emit_kernel(const int32_t *__restrict__ hit_i, const uint32_t *__restrict__ hit_start,
                   const uint64_t *__restrict__ row_off, uint64_t H, const uint32_t *__restrict__ pos, uint64_t first,
-                  uint64_t nrows, int2 *__restrict__ out) {
+                  uint64_t nrows, const uint64_t *__restrict__ blk_first, int2 *__restrict__ out) {
   constexpr int PER = 8, T = THREADS * PER;
   __shared__ __align__(16) uint8_t s_flag[T];
   __shared__ __align__(16) uint32_t s_seg[T];
@@ -225,7 +225,7 @@ probe_emit_kernel(const int32_t *__restrict__ hit_i, const uint32_t *__restrict_
   const uint64_t b0 = (uint64_t)blockIdx.x * T;
   if (b0 >= nrows) return;
   const uint64_t r0 = first + b0;
-  const uint64_t h0 = block_segments<THREADS, PER, uint64_t>(row_off, H, r0, s_flag, s_seg, s_warp, &s_first);
+  const uint64_t h0 = block_segments<THREADS, PER, uint64_t>(row_off, H, r0, blk_first[blockIdx.x], s_flag, s_seg, s_warp, &s_first);
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const uint32_t s = j * THREADS + threadIdx.x;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(THREADS)
 join_emit_kernel(const uint32_t *__restrict__ hit_astart, const uint32_t *__restrict__ hit_bstart,
                  const uint32_t *__restrict__ hit_cb, const uint64_t *__restrict__ row_off, uint64_t H,
                  const uint32_t *__restrict__ pos_a, const uint32_t *__restrict__ pos_b, uint64_t first, uint64_t nrows,
-                 int2 *__restrict__ out) {
+                 const uint64_t *__restrict__ blk_first, int2 *__restrict__ out) {
   constexpr int PER = 8, T = THREADS * PER;
   __shared__ __align__(16) uint8_t s_flag[T];
   __shared__ __align__(16) uint32_t s_seg[T];
@@ -335,7 +335,7 @@ join_emit_kernel(const uint32_t *__restrict__ hit_astart, const uint32_t *__rest
   const uint64_t b0 = (uint64_t)blockIdx.x * T;
   if (b0 >= nrows) return;
   const uint64_t r0 = first + b0;
-  const uint64_t h0 = block_segments<THREADS, PER, uint64_t>(row_off, H, r0, s_flag, s_seg, s_warp, &s_first);
+  const uint64_t h0 = block_segments<THREADS, PER, uint64_t>(row_off, H, r0, blk_first[blockIdx.x], s_flag, s_seg, s_warp, &s_first);
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const uint32_t s = j * THREADS + threadIdx.x;
