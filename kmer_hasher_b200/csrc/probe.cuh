@@ -154,8 +154,12 @@ probe_compact_kernel(const uint2 *__restrict__ found, int64_t coord0, const int3
                      uint64_t *__restrict__ row_off, QueryStats *qs, Pair64 *status, uint32_t *ticket) {
   constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32;
   static_assert(ITEMS % 2 == 0, "pairs of windows are read as one 16-byte word");
+  static_assert(TILE <= 4096, "rows inside a tile: at most TILE * (2^32 - 1) < 2^48");
   __shared__ uint32_t s_tile, s_wh[WARPS];
   __shared__ uint64_t s_wr[WARPS], s_bh, s_br;
+  __shared__ int32_t st_i[TILE];
+  __shared__ uint32_t st_start[TILE], st_row[TILE];
+  __shared__ uint16_t st_row_hi[TILE];
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
@@ -195,17 +199,28 @@ probe_compact_kernel(const uint2 *__restrict__ found, int64_t coord0, const int3
     if (lane == 0) { s_bh = ea; s_br = eb; }
   }
   __syncthreads();
-  uint64_t h = s_bh + bh + (hincl - hmine);
-  uint64_t r = s_br + br + (rincl - rmine);
+  // stage the tile's hits in shared memory in order, then write them out coalesced
+  {
+    uint32_t hl = (uint32_t)bh + (hincl - hmine);        // index among the tile's hits
+    uint64_t rl = br + (rincl - rmine);                  // rows before it inside the tile
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    if (f[i].y) {
-      hit_i[h] = FROM_SEQ ? (int32_t)(coord0 + t0 + i) : i_in[t0 + i];
-      hit_start[h] = f[i].x;
-      row_off[h] = r;
-      ++h;
-      r += f[i].y;
+    for (int i = 0; i < ITEMS; ++i) {
+      if (f[i].y) {
+        st_i[hl] = FROM_SEQ ? (int32_t)(coord0 + t0 + i) : i_in[t0 + i];
+        st_start[hl] = f[i].x;
+        st_row[hl] = (uint32_t)rl;                       // < TILE * 2^32 / ... : rows inside a tile fit 44 bits; low 32 here, high below
+        st_row_hi[hl] = (uint16_t)(rl >> 32);
+        ++hl;
+        rl += f[i].y;
+      }
     }
+  }
+  __syncthreads();
+  const uint64_t gh = s_bh, gr = s_br;
+  for (uint32_t idx = tid; idx < (uint32_t)th; idx += THREADS) {
+    hit_i[gh + idx] = st_i[idx];
+    hit_start[gh + idx] = st_start[idx];
+    row_off[gh + idx] = gr + (((uint64_t)st_row_hi[idx] << 32) | st_row[idx]);
   }
   if (q0 + TILE >= total && tid == 0) { qs->H = s_bh + th; qs->M = s_br + tr; }
 }
