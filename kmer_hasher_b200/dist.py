@@ -14,6 +14,14 @@ The path shards with ONE exchange step:
   5. each owner sorts its records and builds its CSR slice (kmg_build_records); the global 1-based
      k-mer index is local rank + the exclusive prefix of U over ranks.
 
+That is the general path (sharded_build / sharded_query).  The product path on an NVLink node is
+sharded_build_p2p / sharded_query_p2p: steps 1-2 collapse into ONE small all-gather (halo bytes + a sorted
+key sample per rank, splitters chosen on the device), and steps 3-4 into ONE kernel: the partitioning
+pass writes every record straight into its owner's arrays, mapped from the peer GPUs with CUDA IPC
+(PeerExchange), so there is no staging buffer and no all-to-all; the host never waits for the device
+before the finished index is read.  If peer memory cannot be mapped on every rank, or an owner's share
+exceeds the exchange capacity, all ranks take the general path together.
+
 The device work sits behind a small engine object so the host logic can be exercised on CPU with
 gloo (tests/test_dist_cpu.py plugs in a test double); the product engine is CudaEngine.
 """
@@ -132,6 +140,10 @@ class CudaEngine:
 _MARKS = None     # tuning runs: set to a list to collect (phase, cuda event, host time) marks of sharded_build_p2p
 
 
+class PeerUnavailable(RuntimeError):
+    """Raised by PeerExchange on every rank when peer memory cannot be used; take the all-to-all path."""
+
+
 class _Slot:
     """One set of receive arrays: this rank's (keys, pos) and every rank's, as the scatter sees them."""
     __slots__ = ("keys", "pos", "peer_keys", "peer_pos")
@@ -143,31 +155,51 @@ class PeerExchange:
     rank is still sorting the current one."""
 
     def __init__(self, engine: "CudaEngine", capacity: int, group=None):
+        """Collective.  Raises PeerUnavailable on EVERY rank if any rank cannot allocate or map the arrays
+        (e.g. devices hidden from one another), so callers can fall back to the all-to-all path together."""
         self.engine, self.capacity, self.group = engine, int(capacity), group
         L, lib = engine.L, engine._lib
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         self._own, self._opened = [], []
         handles = torch.zeros(4 * 64, dtype=torch.uint8)
-        for i in range(4):                                   # slot0 keys, slot0 pos, slot1 keys, slot1 pos
-            p, hbuf = C.c_void_p(), (C.c_ubyte * 64)()
-            lib.check(L.kmg_ipc_alloc(self.capacity * (8 if i % 2 == 0 else 4), C.byref(p), hbuf))
-            self._own.append(p.value)
-            handles[i * 64:(i + 1) * 64] = torch.frombuffer(bytearray(hbuf), dtype=torch.uint8)
+        ok = True
+        try:
+            for i in range(4):                               # slot0 keys, slot0 pos, slot1 keys, slot1 pos
+                p, hbuf = C.c_void_p(), (C.c_ubyte * 64)()
+                lib.check(L.kmg_ipc_alloc(self.capacity * (8 if i % 2 == 0 else 4), C.byref(p), hbuf))
+                self._own.append(p.value)
+                handles[i * 64:(i + 1) * 64] = torch.frombuffer(bytearray(hbuf), dtype=torch.uint8)
+        except lib.KmgError:
+            ok = False
         mine = handles.to(engine.device)
         allh = torch.empty(world * 4 * 64, dtype=torch.uint8, device=engine.device)
         dist.all_gather_into_tensor(allh, mine, group=group)
         allh = allh.cpu().numpy().reshape(world, 4, 64)
         ptrs = [[0] * 4 for _ in range(world)]
-        for r in range(world):
-            for i in range(4):
-                if r == rank:
-                    ptrs[r][i] = self._own[i]
-                else:
-                    p = C.c_void_p()
-                    hb = (C.c_ubyte * 64).from_buffer_copy(allh[r, i].tobytes())
-                    lib.check(L.kmg_ipc_open(hb, C.byref(p)))
-                    self._opened.append(p.value)
-                    ptrs[r][i] = p.value
+        if ok:
+            try:
+                for r in range(world):
+                    for i in range(4):
+                        if r == rank:
+                            ptrs[r][i] = self._own[i]
+                        else:
+                            p = C.c_void_p()
+                            hb = (C.c_ubyte * 64).from_buffer_copy(allh[r, i].tobytes())
+                            lib.check(L.kmg_ipc_open(hb, C.byref(p)))
+                            self._opened.append(p.value)
+                            ptrs[r][i] = p.value
+            except lib.KmgError:
+                ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=engine.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            for p in self._opened:
+                L.kmg_ipc_close(p)
+            dist.barrier(group=group)
+            for p in self._own:
+                L.kmg_ipc_free(p)
+            self._opened, self._own = [], []
+            raise PeerUnavailable("peer memory could not be mapped on every rank")
         self.slots = []
         for sidx in range(2):
             sl = _Slot()
@@ -475,8 +507,14 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     own_host = torch.from_numpy(own_pin)                   # page-locked by kmg_host_alloc: async DMA source
     own_dev = own_host.to(dev)
 
-    xchg = PeerExchange(engine, int(L * 1.25) + 4096)      # receive arrays mapped into every rank (NVLink P2P)
-    ix = sharded_build_p2p(own_dev, Ltot, k, engine, xchg)
+    try:
+        xchg = PeerExchange(engine, int(L * 1.25) + 4096)  # receive arrays mapped into every rank (NVLink P2P)
+    except PeerUnavailable:
+        xchg = None                                        # every rank lands here together: NCCL all-to-all path
+
+    def build(own):
+        return sharded_build_p2p(own, Ltot, k, engine, xchg) if xchg is not None else sharded_build(own, Ltot, k, engine)
+    ix = build(own_dev)
     U, N, _ = ix.local.sizes
     ntot = ix.N_total
     ix.free()
@@ -485,12 +523,12 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     pos_pin, cnt_pin = kh.pinned_empty((max(N, 1), 2), np.int32), kh.pinned_empty(max(U, 1), np.int32)
 
     def step_device():
-        ix = sharded_build_p2p(own_dev, Ltot, k, engine, xchg)
+        ix = build(own_dev)
         kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos_dev, "count": cnt_dev})
         ix.free()
 
     def step_e2e():
-        ix = sharded_build_p2p(own_host.to(dev, non_blocking=True), Ltot, k, engine, xchg)
+        ix = build(own_host.to(dev, non_blocking=True))
         kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos_pin, "count": cnt_pin})
         ix.free()
 
@@ -524,7 +562,8 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     sizes = torch.tensor([N, U], dtype=torch.int64, device=dev)
     all_sizes = [torch.empty_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
-    xchg.close()
+    if xchg is not None:
+        xchg.close()
     if rank != 0:
         return None
     all_sizes = torch.stack(all_sizes).cpu().numpy()
@@ -541,7 +580,8 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": w["name"] + f" per GPU; {world} shards of one {Ltot}-base sequence, (key,pos) records "
-                       "written straight into the key-range owners' arrays over NVLink by the partitioning pass (peer memory, no all-to-all)", "k": k, "bases": Ltot, "kmers": int(ntot),
+                       + ("written straight into the key-range owners' arrays over NVLink by the partitioning pass (peer memory, no all-to-all)"
+                        if xchg is not None else "routed to key-range owners by one NCCL all-to-all (peer memory unavailable)"), "k": k, "bases": Ltot, "kmers": int(ntot),
                        "per_rank_kmers": all_sizes[:, 0].tolist(), "per_rank_distinct": all_sizes[:, 1].tolist(),
                        "l2": "inputs_exceed_l2"},
             "e2e": {"value": ntot / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(L * world),
