@@ -490,3 +490,32 @@ def test_reverse_complement_probe(kh, oracle, k):
     assert len(want) > 0 and np.array_equal(got.ravel(), want)
     assert np.array_equal(kh.seq_kmer_pos(index_of_rc, rc, k).ravel(), want)
     index_of_rc.free()
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 5, 6])
+def test_every_sort_pass_variant_is_exact(kh, oracle, cfg):
+    """The pass variants selectable with KMG_SORT_CFG / kmg_tune (bitmap, ballot, mixed, one-atomic rank, other
+    tile shapes) all give the reference's index; the one-atomic variant is only the default where the
+    lane-order self-test passes, which is asserted here for this GPU."""
+    import ctypes as C
+    from kmer_hasher_b200 import synth, _lib
+    L = _lib.load()
+    f = C.c_uint32(1)
+    _lib.check(L.kmg_selftest_lane_order(C.byref(f)))
+    assert f.value == 0
+    seq = synth.config_c2(400_000)
+    seq[1000:3000] = ord("A")                               # a homopolymer: every lane of a warp on one bin
+    seq[5000:9000] = np.frombuffer(b"CA" * 2000, np.uint8)
+    seq[20000:20040] = ord("N")
+    try:
+        _lib.check(L.kmg_tune(b"sort_cfg", cfg))
+        for k in (32, 21, 9):
+            ix = kh.make_kmer_hash(seq, k)
+            got = kh.kmer_pos(ix, 2 | 8)
+            want = oracle.build(seq, k).extract(2 | 8)
+            assert np.array_equal(kh.kmer_keys(ix), want["keys"])
+            assert np.array_equal(got["count"], want["count"])
+            assert np.array_equal(got["pos"].ravel(), want["pos"])
+            ix.free()
+    finally:
+        _lib.check(L.kmg_tune(b"sort_cfg", 3))
