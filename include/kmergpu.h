@@ -15,8 +15,9 @@
  *   - sequences are byte strings with an explicit length (the reference scans for the NUL of an
  *     R CHARSXP, which cannot contain one).
  *   - all coordinates are 1-based 32-bit ints exactly as the reference returns them.
- *   - k-mers are ordered by ascending 2-bit key (A<C<T<G, first base most significant); the
- *     reference orders them by khash bucket, which is not semantic.
+ *   - the reference orders k-mers by khash bucket, which is not semantic; here they are ordered by
+ *     ascending 2-bit key (KMG_ORDER_SORTED) or by a mix of the key (KMG_ORDER_GROUPED, the faster
+ *     build), see kmg_build_ordered.
  */
 #ifndef KMERGPU_H
 #define KMERGPU_H
@@ -63,7 +64,19 @@ void kmg_host_free(void *p);
  * glue, as in the reference: like the C core, kmg_build accepts any len >= 0.
  * sort_kmer_pos (src/kmer_pos.c:21-33, do.sort) has no counterpart: lists are always ascending.
  */
-int kmg_build(const char *seq, int64_t len, int k, kmg_index **out);
+int kmg_build(const char *seq, int64_t len, int k, kmg_index **out);   /* = kmg_build_ordered(..., KMG_ORDER_GROUPED, ...) */
+
+/* The order of the k-mers in an index (and so the meaning of the k-mer number i) is not semantic: the
+ * reference's is its hash table's bucket order.  KMG_ORDER_SORTED: ascending 2-bit key (A<C<T<G, first base
+ * most significant), ceil(2k/8) radix passes.  KMG_ORDER_GROUPED: the records are sorted on 40 bits of a
+ * bijective mix of the key, which tells almost all k-mers of a genome apart in 5 passes; the few groups in
+ * which two k-mers share those bits are partitioned afterwards.  k-mers then come in the order of the mixed
+ * key; used when it saves at least two passes (k >= 25), otherwise the build is sorted.  Everything else
+ * (positions ascending per k-mer, counts, pairs, probes) is identical; kmg_index_order tells which. */
+#define KMG_ORDER_GROUPED 0
+#define KMG_ORDER_SORTED 1
+int kmg_build_ordered(const char *seq, int64_t len, int k, int order, kmg_index **out);
+int kmg_index_order(const kmg_index *idx);
 
 /* replaces clear_kmer_h (src/kmer_pos.c:10-19) + the finaliser body (src/kmer_hash.c:56-66).
  * NULL is accepted. */
@@ -155,6 +168,10 @@ int kmg_query_records(const kmg_index *idx, const uint64_t *d_keys, const int32_
  *                     (k-1 gives the reference's query coordinate).  d_info[0] = records this rank
  *                     receives, d_info[1] = 1 if an owner would overflow (its surplus is dropped and
  *                     kmg_build_received / kmg_query_received then fail with KMG_ERR_RANGE).
+ * `order` (kmg_shard_pack, kmg_shard_open_packed, kmg_build_received; the same value on every rank):
+ * with KMG_ORDER_GROUPED and k >= 25 the sample, the owner ranges and the exchanged records are those of
+ * the mixed key (see kmg_build_ordered) and every owner builds a grouped index; query records scattered
+ * from a shard opened that way carry the mix too (kmg_query_received: mixed = 1).
  */
 typedef struct kmg_shard kmg_shard;
 int kmg_shard_open(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t s0, int64_t s1,
@@ -165,11 +182,12 @@ int kmg_shard_open(const void *d_seq, int64_t g0, int64_t g1, int64_t L, int64_t
  * (its own bytes [rank*per, (rank+1)*per) of L, per = ceil(L/world), plus halo) and writes the
  * world-1 splitters (element j*total/world of all samples in ascending order) to d_splitters. */
 int kmg_shard_pack_bytes(int n_samples);
-int kmg_shard_pack(const void *d_own, int64_t n_own, int k, int n_samples, void *d_pack);
+int kmg_shard_pack(const void *d_own, int64_t n_own, int k, int n_samples, int order, void *d_pack);
 int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L, int world, int rank, int k,
-                          int n_samples, const void *d_allpack, kmg_shard **out,
+                          int n_samples, int order, const void *d_allpack, kmg_shard **out,
                           uint64_t *d_splitters);
 int kmg_shard_close(kmg_shard *sh);
+int kmg_shard_set_mixed(kmg_shard *sh, int mixed);   /* route by mix64(key): queries against a grouped sharded index */
 int kmg_shard_windows(const kmg_shard *sh, int64_t *nstarts);
 int kmg_shard_sample_keys(const kmg_shard *sh, int n, uint64_t *d_samples);
 int kmg_shard_count(const kmg_shard *sh, const uint64_t *d_splitters, int nparts, uint64_t *d_counts);
@@ -177,9 +195,10 @@ int kmg_shard_scatter(const kmg_shard *sh, const uint64_t *d_splitters, int npar
                       void *const *peer_keys, void *const *peer_pos, uint64_t capacity,
                       const uint64_t *d_matrix, int32_t pos_add, uint64_t *d_info);
 int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, const uint64_t *d_info,
-                       int k, kmg_index **out);
+                       int k, int order, kmg_index **out);
 int kmg_query_received(const kmg_index *idx, const uint64_t *d_keys, const int32_t *d_i,
-                       uint64_t capacity, const uint64_t *d_info, kmg_query **st, uint64_t *M);
+                       uint64_t capacity, const uint64_t *d_info, int mixed, kmg_query **st,
+                       uint64_t *M);
 /* device buffers other processes of the node can map (CUDA IPC); handle is 64 bytes */
 int kmg_ipc_alloc(size_t bytes, void **dptr, void *handle);
 int kmg_ipc_free(void *dptr);

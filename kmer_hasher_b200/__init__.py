@@ -25,6 +25,7 @@ __all__ = ["KmerHash", "make_kmer_hash", "kmer_pos", "seq_kmer_pos", "kmer_pairs
 
 # opt.flag bits, src/kmer_hash.c:17 (pos_opt_flags) in the reference
 OPT_KMER, OPT_POS, OPT_PAIRS, OPT_COUNT = 1, 2, 4, 8
+ORDER_GROUPED, ORDER_SORTED = 0, 1      # include/kmergpu.h
 KMER_HASH_TAG = "kmer_hash_250930"      # src/kmer_hash.c:22
 MAX_K = 32                              # src/kmer_util.h:12
 INT_MAX = 2**31 - 1
@@ -124,31 +125,58 @@ def make_kmer_hash(seq, k, do_sort=False) -> KmerHash:
     """make.kmer.hash (kmer_hash.R:5-8 -> make_kmer_h_index, src/kmer_hash.c:506-540).
 
     `seq` may be a character vector: like the reference, only its first element is used.
-    `do_sort` is accepted and has no effect: position lists are always ascending.
+    Position lists are always ascending, so the reference's `do.sort` has nothing to sort; here it selects
+    the order of the K-MERS, which is not semantic (the reference's is hash-bucket order): do_sort=True gives
+    ascending 2-bit key (KMG_ORDER_SORTED), the default the faster grouped build (KMG_ORDER_GROUPED: order of
+    a mix of the key, used for k >= 25).  `kmer_pos(..., canonical=True)` re-orders any index by key.
     """
     if isinstance(seq, (list, tuple)):
         if len(seq) < 1:
             raise ValueError("seq_r should be a character vector of length at least one")
         seq = seq[0]
     k = int(k)
-    int(do_sort)
+    order = ORDER_SORTED if int(do_sort) else ORDER_GROUPED
     if k < 1 or k > MAX_K:
         raise ValueError("k must be a positive integer less than 1+MAX_K")
     ptr, n, keep = _seq_buffer(seq)
     if n <= k:
         raise ValueError("the length of the sequence must be at least k")
     h = C.c_void_p()
-    check(_L.kmg_build(ptr, n, k, C.byref(h)))
+    check(_L.kmg_build_ordered(ptr, n, k, order, C.byref(h)))
     del keep
     return KmerHash(h.value, k)
 
 
-def kmer_pos(ex_ptr, opt_flag, out: dict | None = None) -> dict:
+def _by_key(ix: "KmerHash"):
+    """(order, rank): order[j] = index (0-based) of the k-mer with the j-th smallest key, rank = its inverse."""
+    U = ix.sizes[0]
+    keys = np.empty(U, np.uint64)
+    check(_L.kmg_kmers_u64(ix._handle(), _out_ptr(keys)))
+    order = np.argsort(keys, kind="stable")
+    rank = np.empty(U, np.int64)
+    rank[order] = np.arange(U)
+    return keys, order, rank
+
+
+def _renumber(rows: np.ndarray, rank: np.ndarray) -> np.ndarray:
+    """Rows whose first column is a 1-based k-mer number: renumber by `rank` and group by the new number (stable)."""
+    if len(rows) == 0:
+        return rows
+    new_i = rank[rows[:, 0].astype(np.int64) - 1] + 1
+    o = np.argsort(new_i, kind="stable")
+    out = rows[o].copy()
+    out[:, 0] = new_i[o].astype(np.int32)
+    return out
+
+
+def kmer_pos(ex_ptr, opt_flag, out: dict | None = None, canonical: bool = False) -> dict:
     """kmer.pos (kmer_hash.R:10-21 -> kmer_positions, src/kmer_hash.c:1054-1147).
 
     Returns {"kmer", "pos", "pair.pos", "count"}; fields whose opt.flag bit is off are None.
     "pos" is an N x 2 int32 array with columns (i, pos) and "pair.pos" a P x 3 array with columns
-    (i, x, y) -- the matrices R holds after kmer.pos's t().  k-mers are ordered by ascending key.
+    (i, x, y) -- the matrices R holds after kmer.pos's t().  k-mers come in the index's own order (see
+    make_kmer_hash); `canonical=True` re-orders them by ascending key with i renumbered, the form in which
+    results are compared with the reference (whose own order is its hash table's).
     `out` may supply preallocated (e.g. pinned) arrays under the same names.
     """
     ix = _extract(ex_ptr)
@@ -186,16 +214,27 @@ def kmer_pos(ex_ptr, opt_flag, out: dict | None = None) -> dict:
             a = np.empty(U, np.int32)
         check(_L.kmg_counts(h, _out_ptr(a)))
         res["count"] = a[:U]
+    if canonical and _L.kmg_index_order(h) != ORDER_SORTED:
+        _, order, rank = _by_key(ix)
+        if res["kmer"] is not None:
+            res["kmer"] = res["kmer"][order]
+        if res["count"] is not None:
+            res["count"] = np.asarray(res["count"])[order]
+        if res["pos"] is not None:
+            res["pos"] = _renumber(np.asarray(res["pos"]), rank)
+        if res["pair.pos"] is not None:
+            res["pair.pos"] = _renumber(np.asarray(res["pair.pos"]), rank)
     return res
 
 
-def kmer_keys(ex_ptr) -> np.ndarray:
-    """The distinct k-mers as uint64 keys, ascending (not part of the R API; used by tests)."""
+def kmer_keys(ex_ptr, canonical: bool = False) -> np.ndarray:
+    """The distinct k-mers as uint64 keys in the index's order, or ascending with canonical=True (not part of
+    the R API; used by tests)."""
     ix = _extract(ex_ptr)
     U, _, _ = ix.sizes
     a = np.empty(U, np.uint64)
     check(_L.kmg_kmers_u64(ix._handle(), _out_ptr(a)))
-    return a
+    return np.sort(a) if canonical else a
 
 
 def seq_kmer_pos(ex_ptr, seq, k, *, allow_k32: bool = False, out: np.ndarray | None = None,

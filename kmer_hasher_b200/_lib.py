@@ -25,6 +25,8 @@ SIGNATURES = {
     "kmg_host_alloc": (vp, [C.c_size_t]),
     "kmg_host_free": (None, [vp]),
     "kmg_build": (C.c_int, [vp, C.c_int64, C.c_int, C.POINTER(vp)]),
+    "kmg_build_ordered": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, C.POINTER(vp)]),
+    "kmg_index_order": (C.c_int, [vp]),
     "kmg_free": (C.c_int, [vp]),
     "kmg_sizes": (C.c_int, [vp, u64p, u64p, u64p]),
     "kmg_index_k": (C.c_int, [vp]),
@@ -51,14 +53,15 @@ SIGNATURES = {
     "kmg_shard_open": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(vp)]),
     "kmg_shard_close": (C.c_int, [vp]),
     "kmg_shard_pack_bytes": (C.c_int, [C.c_int]),
-    "kmg_shard_pack": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, vp]),
-    "kmg_shard_open_packed": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp), vp]),
+    "kmg_shard_pack": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp]),
+    "kmg_shard_open_packed": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp), vp]),
+    "kmg_shard_set_mixed": (C.c_int, [vp, C.c_int]),
     "kmg_shard_windows": (C.c_int, [vp, C.POINTER(C.c_int64)]),
     "kmg_shard_sample_keys": (C.c_int, [vp, C.c_int, vp]),
     "kmg_shard_count": (C.c_int, [vp, vp, C.c_int, vp]),
     "kmg_shard_scatter": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_uint64, vp, C.c_int32, vp]),
-    "kmg_build_received": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_int, C.POINTER(vp)]),
-    "kmg_query_received": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.POINTER(vp), u64p]),
+    "kmg_build_received": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "kmg_query_received": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_int, C.POINTER(vp), u64p]),
     "kmg_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), vp]),
     "kmg_ipc_free": (C.c_int, [vp]),
     "kmg_ipc_open": (C.c_int, [vp, C.POINTER(vp)]),

@@ -321,6 +321,7 @@ struct kmg_index {
   int k = 0;
   uint64_t U = 0, N = 0, P = 0, multi = 0;
   uint32_t maxc = 0;
+  bool grouped = false;         // k-mers in the order of the grouped build instead of ascending key
   uint64_t *ukeys = nullptr;    // [U]
   uint32_t *ustart = nullptr;   // [U+1]
   uint32_t *pos = nullptr;      // [N]
@@ -357,6 +358,9 @@ using Cfg5 = PassCfg<256, 16, 3, 3, 8>;
 using Cfg6 = PassCfg<512, 12, 2, 3, 8>;
 using Cfg7 = PassCfg<256, 24, 2, 3, 16>;
 constexpr int N_SORT_CFG = 8;
+// Bits of mix64(key) the grouped build sorts on (kmg_tune "hash_bits", a multiple of 8; tests lower it to
+// force collisions).  40 bits: ~N^2 / 2^41 colliding pairs (730 at 40 M k-mers, 1 M at 1.5 G).
+static int g_hash_bits = 40;
 static int g_sort_cfg = -1;
 static uint32_t g_sort_dbg = 0;
 static int lane_order_failures(uint32_t *failures);
@@ -390,6 +394,11 @@ extern "C" int kmg_tune(const char *key, int value) {
     return KMG_OK;
   }
   if (key && !strcmp(key, "sort_dbg")) { g_sort_dbg = (uint32_t)value; return KMG_OK; }
+  if (key && !strcmp(key, "hash_bits")) {
+    if (value < 8 || value > 56 || value % RADIX_BITS) return fail(KMG_ERR_ARG, "hash_bits must be a multiple of 8 in [8,56]");
+    g_hash_bits = value;
+    return KMG_OK;
+  }
   if (key && !strcmp(key, "sort_trace")) {          // value = tiles to trace (0 = off); buffer read by kmg_trace_read
     if (g_trace) { cudaFree(g_trace); g_trace = nullptr; }
     g_trace_tiles = value;
@@ -463,7 +472,7 @@ static void scratch_free(SortScratch &sc, cudaStream_t s) { dfree(sc.small, s); 
 
 // Sorted records -> CSR; reads the stats back (one synchronisation) and fills the handle.
 static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, uint32_t *pos_sorted,
-                        int64_t n_upper, cudaStream_t s) {
+                        int64_t n_upper, cudaStream_t s, bool hashed = false) {
   IndexStats *st = sc.stats();
   uint64_t *ukeys = nullptr;
   uint32_t *ustart = nullptr;
@@ -474,7 +483,7 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
   TRY(dalloc(&status2, (size_t)tiles, s));
   CU(cudaMemsetAsync(status2, 0, (size_t)tiles * sizeof(Pair64), s));
   LAUNCH("rle", s, rle_kernel<RLE_THREADS, RLE_ITEMS><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(
-                       keys_sorted, st, ukeys, ustart, status2, sc.ticket(MAX_PASSES + 1)));
+                       keys_sorted, st, ukeys, ustart, status2, sc.ticket(MAX_PASSES + 1), hashed));
   const unsigned sgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, 256 * 16), g_ctx.sms * 8);
   LAUNCH("stats", s, stats_kernel<256><<<sgrid, 256, 0, s>>>(ustart, st));
   IndexStats h;
@@ -505,8 +514,8 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
 // final_pos (optional): the last pass writes its positions there instead of into the ping-pong buffer
 // (the array the index keeps), so `pa` is meaningless afterwards.
 static int sort_tail(SortScratch &sc, int k, int first_pass, bool has_next, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
-                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr) {
-  const int R = num_passes(k);
+                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr, int passes = 0) {
+  const int R = passes > 0 ? passes : num_passes(k);
   for (int r = first_pass; r < R; ++r) {
     PassParams<DigitBin, DigitBin> P{};
     P.keys_in = ka; P.pos_in = pa; P.keys_out = kb; P.pos_out = (final_pos && r == R - 1) ? final_pos : pb;
@@ -528,7 +537,72 @@ static int sort_tail(SortScratch &sc, int k, int first_pass, bool has_next, uint
   return KMG_OK;
 }
 
-static int build_from_view(const SeqView &sv, int k, kmg_index **out) {
+
+// is the grouped build used for this k and requested order?  (it has to save at least two passes)
+static bool grouped_for(int k, int order) { return order == KMG_ORDER_GROUPED && num_passes(k) > g_hash_bits / RADIX_BITS + 1; }
+
+// Collisions of the low bits of the mix: partition those groups by the whole mix (sk, sp: scratch of the
+// same size).  Returns the detect counters through h_cnt after the caller's next synchronisation.
+static int fix_groups(SortScratch &sc, uint64_t *keys, uint32_t *pos, uint64_t *sk, uint32_t *sp, int64_t n_upper, cudaStream_t s,
+                      uint32_t *h_cnt /* [4], pinned or stack read after a sync */, uint32_t **fixmem_out) {
+  FixLists fl{};
+  uint32_t *fixmem = nullptr;
+  fl.small_cap = (uint32_t)std::max<int64_t>(1 << 20, n_upper / 8);
+  fl.big_cap = 1 << 16;
+  const size_t words = 4 + CLAIM_SLOTS + 2 * (size_t)fl.small_cap + 2 * (size_t)fl.big_cap;
+  TRY(dalloc(&fixmem, words, s));
+  *fixmem_out = fixmem;
+  CU(cudaMemsetAsync(fixmem, 0, (4 + CLAIM_SLOTS) * sizeof(uint32_t), s));
+  fl.counters = fixmem; fl.claim = fixmem + 4;
+  fl.small_tasks = reinterpret_cast<uint2 *>(fixmem + 4 + CLAIM_SLOTS);
+  fl.big_tasks = fl.small_tasks + fl.small_cap;
+  const unsigned dgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper, 256 * 8), (int64_t)g_ctx.sms * 16);
+  LAUNCH("group_detect", s, group_detect_kernel<<<dgrid, 256, 0, s>>>(keys, sc.stats(), g_hash_bits, fl));
+  LAUNCH("small_fix", s, small_fix_kernel<<<g_ctx.sms * 4, 128, 0, s>>>(keys, pos, fl));
+  LAUNCH("big_fix", s, big_fix_kernel<256><<<g_ctx.sms, 256, 0, s>>>(keys, pos, sk, sp, fl));
+  CU(cudaMemcpyAsync(h_cnt, fl.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  return KMG_OK;
+}
+
+// Grouped build: equal k-mers contiguous, k-mers in the order of (low bits of mix64(key), mix64(key)).
+static int build_grouped(const SeqView &sv, int k, kmg_index *ix, SortScratch &sc, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
+                         uint32_t *&pb, int64_t n_upper, cudaStream_t s, bool *overflow) {
+  const int bits = g_hash_bits, R = bits / RADIX_BITS;
+  const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
+  const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
+  LAUNCH("hist_seq", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, HashDigitBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), HashDigitBin{0}));
+  LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), &sc.stats()->n));
+  {
+    PassParams<DigitBin, DigitBin> P{};
+    P.sv = sv; P.keys_out = ka; P.pos_out = pa;
+    P.gbase = sc.gbase(0); P.hist_next = sc.hist(1);
+    P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
+    P.hashed = 1;
+    P.bin = DigitBin{0}; P.next = DigitBin{RADIX_BITS};
+    if (R > 1) {
+      TRY((launch_pass<true, DigitBin, DigitBin, true>("sort_pass_seq", P, n_upper, s)));
+      LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(1), sc.gbase(1), nullptr));
+    } else {
+      TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq", P, n_upper, s)));
+    }
+  }
+  TRY(sort_tail(sc, k, 1, true, ka, pa, kb, pb, n_upper, s, nullptr, R));   // records ordered by the low bits of the mix, in (ka, pa)
+  uint32_t h_cnt[4] = {0, 0, 0, 0};
+  uint32_t *fixmem = nullptr;
+  int rc = fix_groups(sc, ka, pa, kb, pb, n_upper, s, h_cnt, &fixmem);       // kb, pb are free: scratch
+  if (rc == KMG_OK) rc = finish_index(ix, sc, ka, pa, n_upper, s, true);      // synchronises
+  dfree(fixmem, s);
+  *overflow = h_cnt[2] != 0;
+  const double N = (double)ix->N, L = (double)sv.avail;
+  prof_bytes("hist_seq", L);
+  prof_bytes("sort_pass_seq", L + 12 * N);
+  if (R > 2) prof_bytes("sort_pass_hist", 24 * N * (R - 2));
+  if (R > 1) prof_bytes("sort_pass", 24 * N);
+  prof_bytes("group_detect", 8 * N);
+  return rc;
+}
+
+static int build_from_view(const SeqView &sv, int k, kmg_index **out, int order = KMG_ORDER_SORTED) {
   cudaStream_t s = g_ctx.stream();
   kmg_index *ix = new (std::nothrow) kmg_index();
   if (!ix) return fail(KMG_ERR_NOMEM, "host allocation failed");
@@ -554,7 +628,19 @@ static int build_from_view(const SeqView &sv, int k, kmg_index **out) {
     TRY(dalloc(&ka, (size_t)n_upper, s));
     TRY(dalloc(&pa, (size_t)n_upper, s));
     const int R = num_passes(k);
+    const bool grouped = order == KMG_ORDER_GROUPED && R > g_hash_bits / RADIX_BITS + 1;   // worth it from two saved passes on
     if (R > 1) { TRY(dalloc(&kb, (size_t)n_upper, s)); TRY(dalloc(&pb, (size_t)n_upper, s)); }
+    if (grouped) {
+      bool overflow = false;
+      TRY(build_grouped(sv, k, ix, sc, ka, pa, kb, pb, n_upper, s, &overflow));
+      if (!overflow) { pa = nullptr; ix->grouped = true; return KMG_OK; }
+      // more colliding groups than the task lists hold (not seen in practice): rebuild sorted by key
+      void *old[3] = {ix->ukeys, ix->ustart, nullptr};
+      for (void *p : old) g_arena[ix->device & 63].put(p, s, false);
+      ix->ukeys = nullptr; ix->ustart = nullptr; ix->pos = nullptr;
+      CU(cudaMemsetAsync(sc.small, 0, sc.small_words * 4, s));
+      CU(cudaMemsetAsync(sc.status, 0, (size_t)ceil_div<int64_t>(n_upper, SORT_TILE_MIN) * RADIX * sizeof(uint64_t), s));
+    }
     const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
     const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
     LAUNCH("hist_all", s, hist_all_kernel<HIST_THREADS, HIST_ITEMS><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.common(), sc.hist(0)));
@@ -596,7 +682,13 @@ static bool log_on() {
 }
 
 extern "C" int kmg_build(const char *seq, int64_t len, int k, kmg_index **out) {
+  return kmg_build_ordered(seq, len, k, KMG_ORDER_GROUPED, out);
+}
+extern "C" int kmg_index_order(const kmg_index *ix) { return !ix ? fail(KMG_ERR_ARG, "index is NULL") : (ix->grouped ? KMG_ORDER_GROUPED : KMG_ORDER_SORTED); }
+
+extern "C" int kmg_build_ordered(const char *seq, int64_t len, int k, int order, kmg_index **out) {
   if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  if (order != KMG_ORDER_SORTED && order != KMG_ORDER_GROUPED) return fail(KMG_ERR_ARG, "order must be KMG_ORDER_SORTED or KMG_ORDER_GROUPED");
   *out = nullptr;
   if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be a positive integer less than 1+MAX_K");
   if (len < 0 || (len > 0 && !seq)) return fail(KMG_ERR_ARG, "bad sequence pointer/length");
@@ -608,7 +700,7 @@ extern "C" int kmg_build(const char *seq, int64_t len, int k, kmg_index **out) {
   const double t1 = wall_ms();
   SeqView sv;
   sv.base = ds.base; sv.nstarts = len - k + 1 > 0 ? len - k + 1 : 0; sv.avail = len; sv.s0 = 0; sv.L = len; sv.k = k;
-  int rc = build_from_view(sv, k, out);
+  int rc = build_from_view(sv, k, out, order);
   dfree(ds.buf, s);
   if (log_on())
     fprintf(stderr, "[kmergpu] build len=%lld k=%d: upload(enqueue) %.3f ms, build %.3f ms (host wall clock)\n", (long long)len, k, t1 - t0, wall_ms() - t1);
@@ -835,7 +927,7 @@ static int ensure_hash(kmg_index *ix) {
 }
 
 static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, const uint64_t *d_keys,
-                        const int32_t *d_i, int64_t n, kmg_query **out, uint64_t *M, const uint64_t *d_n = nullptr) {
+                        const int32_t *d_i, int64_t n, kmg_query **out, uint64_t *M, const uint64_t *d_n = nullptr, bool mixed = false) {
   kmg_index *ix = const_cast<kmg_index *>(cix);
   cudaStream_t s = g_ctx.stream();
   kmg_query *q = new (std::nothrow) kmg_query();
@@ -868,7 +960,7 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
       LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, COMPACT_ITEMS, true><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
                                      found, sv.s0 + sv.k, nullptr, total, nullptr, q->hit_i, q->hit_start, q->row_off, qs, status, ticket));
     } else {
-      LAUNCH("probe_lookup_rec", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<ltiles, PROBE_THREADS, 0, s>>>(sv, d_keys, n, d_n, kt, found));
+      LAUNCH("probe_lookup_rec", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<ltiles, PROBE_THREADS, 0, s>>>(sv, d_keys, n, d_n, kt, found, mixed));
       LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, COMPACT_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
                                      found, 0, d_i, n, d_n, q->hit_i, q->hit_start, q->row_off, qs, status, ticket));
     }
@@ -1236,6 +1328,7 @@ extern "C" int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, i
 // ------------------------------------------------------------------------------------------------
 struct kmg_shard {
   int device = 0;
+  bool hashed = false;     // grouped sharded build: records and owner ranges are those of mix64(key)
   DevSeq ds;
   SeqView sv;
 };
@@ -1258,6 +1351,11 @@ extern "C" int kmg_shard_close(kmg_shard *sh) {
   if (g_ctx.ready && g_ctx.device == sh->device) dfree(sh->ds.buf, g_ctx.stream());
   else { cudaSetDevice(sh->device); g_arena[sh->device & 63].put(sh->ds.buf, nullptr, false); }
   delete sh;
+  return KMG_OK;
+}
+extern "C" int kmg_shard_set_mixed(kmg_shard *sh, int mixed) {
+  if (!sh) return fail(KMG_ERR_ARG, "shard is NULL");
+  sh->hashed = mixed != 0;     // count / scatter then work on mix64(key): the owner ranges of a grouped sharded index
   return KMG_OK;
 }
 extern "C" int kmg_shard_windows(const kmg_shard *sh, int64_t *nstarts) {
@@ -1291,7 +1389,10 @@ extern "C" int kmg_shard_count(const kmg_shard *sh, const uint64_t *d_splitters,
     OwnerBin ob{d_splitters, nparts};
     const int64_t tiles = ceil_div<int64_t>(sh->sv.nstarts, HIST_TILE);
     const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
-    LAUNCH("hist_seq_owner", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, OwnerBin><<<hgrid, HIST_THREADS, 0, s>>>(sh->sv, hist, ob));
+    if (sh->hashed)
+      LAUNCH("hist_seq_owner", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, HashOwnerBin><<<hgrid, HIST_THREADS, 0, s>>>(sh->sv, hist, HashOwnerBin{ob}));
+    else
+      LAUNCH("hist_seq_owner", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, OwnerBin><<<hgrid, HIST_THREADS, 0, s>>>(sh->sv, hist, ob));
     prof_bytes("hist_seq_owner", (double)sh->sv.avail);
   }
   LAUNCH("widen_counts", s, widen_counts_kernel<<<1, MAX_PEERS, 0, s>>>(hist, nparts, d_counts));
@@ -1323,6 +1424,7 @@ extern "C" int kmg_shard_scatter(const kmg_shard *sh, const uint64_t *d_splitter
     P.gbase = sc.gbase(0); P.hist_next = nullptr;
     P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
     P.pos_add = (uint32_t)pos_add;
+    P.hashed = sh->hashed ? 1u : 0u;                    // the owner is then looked up for mix64(key), which is what is written
     P.peer = tab;
     P.bin = ob;
     // few bins, many lanes per bin: the bitmap variant measured best here (0.51 ms at N=2; ballots 0.54 ms)
@@ -1340,7 +1442,8 @@ __global__ void set_n_kernel(const uint64_t *info, uint64_t cap, uint64_t *n) { 
 
 // Index from the records peers scattered into (d_keys, d_pos): their number is on the device (d_info[0]).
 // Everything is sized by `capacity`; the one host synchronisation is the read of the finished index's stats.
-extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, const uint64_t *d_info, int k, kmg_index **out) {
+extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, const uint64_t *d_info, int k, int order,
+                                  kmg_index **out) {
   if (!out) return fail(KMG_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
@@ -1356,6 +1459,7 @@ extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t ca
   uint64_t *ka = d_keys, *kb = nullptr;
   uint32_t *pa = d_pos, *pb = nullptr, *pfinal = nullptr;
   uint64_t h_info[2] = {0, 0};
+  const bool grouped = grouped_for(k, order);
   auto body = [&]() -> int {
     TRY(scratch_alloc(sc, n, s));
     TRY(dalloc(&kb, (size_t)n, s));
@@ -1365,20 +1469,44 @@ extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t ca
     LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, &sc.stats()->n, sc.hist(0), DigitBin{0}));
     LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), nullptr));
     TRY(dalloc(&pfinal, (size_t)n, s));
-    TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s, pfinal));
     CU(cudaMemcpyAsync(h_info, d_info, sizeof h_info, cudaMemcpyDeviceToHost, s));
-    TRY(finish_index(ix, sc, ka, pfinal, n, s));            // synchronises
+    if (grouped) {
+      // records carry mix64(key): sort on its low bits, then partition the groups in which k-mers share them.
+      // The passes ping-pong (caller's arrays <-> ours); the fix-up needs the result and a scratch pair, so the
+      // last pass may not divert into pfinal: copy the positions at the end instead.
+      const int R = g_hash_bits / RADIX_BITS;
+      TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s, nullptr, R));
+      uint32_t h_cnt[4] = {0, 0, 0, 0};
+      uint32_t *fixmem = nullptr;
+      int rc = fix_groups(sc, ka, pa, kb, pb, n, s, h_cnt, &fixmem);
+      if (rc == KMG_OK && pa != d_pos) {                     // the sorted positions are in an array of ours: the index keeps it
+        dfree(pfinal, s);
+        pfinal = pa;
+        pa = nullptr;
+      } else if (rc == KMG_OK && cudaMemcpyAsync(pfinal, pa, (size_t)n * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+        rc = fail(KMG_ERR_CUDA, "copy failed");
+      }
+      if (rc == KMG_OK) rc = finish_index(ix, sc, ka, pfinal, n, s, true);   // synchronises
+      dfree(fixmem, s);
+      TRY(rc);
+      if (h_cnt[2]) return fail(KMG_ERR_RANGE, "more colliding groups than the task lists hold");
+      ix->grouped = true;
+    } else {
+      TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s, pfinal));
+      TRY(finish_index(ix, sc, ka, pfinal, n, s));            // synchronises
+    }
     pfinal = nullptr;
-    const int R = num_passes(k);
+    const int R = grouped ? g_hash_bits / RADIX_BITS : num_passes(k);
     prof_bytes("hist_rec", 8.0 * (double)ix->N);
     if (R > 1) prof_bytes("sort_pass_hist", 24.0 * (double)ix->N * (R - 1));
     prof_bytes("sort_pass", 24.0 * (double)ix->N);
+    if (grouped) prof_bytes("group_detect", 8.0 * (double)ix->N);
     return KMG_OK;
   };
   int rc = body();
   if (ka != d_keys) dfree(ka, s);
   if (kb != d_keys) dfree(kb, s);
-  if (pa != d_pos) dfree(pa, s);
+  if (pa && pa != d_pos) dfree(pa, s);
   if (pb != d_pos) dfree(pb, s);
   dfree(pfinal, s);
   scratch_free(sc, s);
@@ -1421,7 +1549,7 @@ extern "C" int kmg_ipc_close(void *dptr) {
 
 // match the (key, i) records peers scattered into (d_keys, d_i); their number is d_info[0] on the device
 extern "C" int kmg_query_received(const kmg_index *ix, const uint64_t *d_keys, const int32_t *d_i, uint64_t capacity,
-                                  const uint64_t *d_info, kmg_query **st, uint64_t *M) {
+                                  const uint64_t *d_info, int mixed, kmg_query **st, uint64_t *M) {
   if (!st) return fail(KMG_ERR_ARG, "st is NULL");
   *st = nullptr;
   if (capacity == 0 || capacity > (uint64_t)INT32_MAX || !d_keys || !d_i || !d_info) return fail(KMG_ERR_ARG, "bad record arrays");
@@ -1429,7 +1557,7 @@ extern "C" int kmg_query_received(const kmg_index *ix, const uint64_t *d_keys, c
   uint64_t h_info[2] = {0, 0};
   CU(cudaMemcpyAsync(h_info, d_info, sizeof h_info, cudaMemcpyDeviceToHost, g_ctx.stream()));
   SeqView sv{};
-  int rc = query_common(ix, false, sv, d_keys, d_i, (int64_t)capacity, st, M, d_info);
+  int rc = query_common(ix, false, sv, d_keys, d_i, (int64_t)capacity, st, M, d_info, mixed != 0);
   cudaStreamSynchronize(g_ctx.stream());
   if (rc == KMG_OK && h_info[1]) {
     kmg_query_free(*st);
@@ -1448,7 +1576,7 @@ constexpr int PACK_HDR = 48;
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-shard_pack_kernel(const uint8_t *__restrict__ own, int64_t n_own, int k, int n, uint8_t *__restrict__ pack) {
+shard_pack_kernel(const uint8_t *__restrict__ own, int64_t n_own, int k, int n, const bool mixed, uint8_t *__restrict__ pack) {
   extern __shared__ uint64_t sk[];                       // n keys (n a power of two)
   const int tid = threadIdx.x;
   if (tid < PACK_HDR) {
@@ -1466,7 +1594,7 @@ shard_pack_kernel(const uint8_t *__restrict__ own, int64_t n_own, int k, int n, 
       const uint8_t c = o < n_own ? own[o] : 0;
       w = (w << 2) | ((c >> 1) & 3u);
     }
-    sk[i] = w & key_mask(k);
+    sk[i] = mixed ? mix64(w & key_mask(k)) : (w & key_mask(k));   // grouped build: owners hold ranges of the mix
   }
   __syncthreads();
   for (int size = 2; size <= n; size <<= 1)              // bitonic sort, ascending
@@ -1486,13 +1614,13 @@ shard_pack_kernel(const uint8_t *__restrict__ own, int64_t n_own, int k, int n, 
 
 extern "C" int kmg_shard_pack_bytes(int n_samples) { return PACK_HDR + 8 * n_samples; }
 
-extern "C" int kmg_shard_pack(const void *d_own, int64_t n_own, int k, int n_samples, void *d_pack) {
+extern "C" int kmg_shard_pack(const void *d_own, int64_t n_own, int k, int n_samples, int order, void *d_pack) {
   if (!d_pack || (n_own > 0 && !d_own) || n_own < 0) return fail(KMG_ERR_ARG, "bad arguments");
   if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
   if (n_samples < 2 || n_samples > 4096 || (n_samples & (n_samples - 1))) return fail(KMG_ERR_ARG, "n_samples must be a power of two in [2,4096]");
   TRY(ctx_init());
   cudaStream_t s = g_ctx.stream();
-  LAUNCH("shard_pack", s, shard_pack_kernel<1024><<<1, 1024, (size_t)n_samples * 8, s>>>((const uint8_t *)d_own, n_own, k, n_samples, (uint8_t *)d_pack));
+  LAUNCH("shard_pack", s, shard_pack_kernel<1024><<<1, 1024, (size_t)n_samples * 8, s>>>((const uint8_t *)d_own, n_own, k, n_samples, grouped_for(k, order), (uint8_t *)d_pack));
   return KMG_OK;
 }
 
@@ -1538,7 +1666,7 @@ __global__ void select_splitters_kernel(const uint8_t *__restrict__ allpack, int
 }
 
 extern "C" int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L, int world, int rank, int k, int n_samples,
-                                     const void *d_allpack, kmg_shard **out, uint64_t *d_splitters) {
+                                     int order, const void *d_allpack, kmg_shard **out, uint64_t *d_splitters) {
   if (!out) return fail(KMG_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
@@ -1552,6 +1680,7 @@ extern "C" int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L
   kmg_shard *sh = new (std::nothrow) kmg_shard();
   if (!sh) return fail(KMG_ERR_NOMEM, "host allocation failed");
   sh->device = g_ctx.device;
+  sh->hashed = grouped_for(k, order);
   const int pack_bytes = PACK_HDR + 8 * n_samples;
   auto body = [&]() -> int {
     const int64_t need_hi = std::min<int64_t>(L, s1 + k - 1);

@@ -60,6 +60,22 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// A bijection of 64-bit words with good avalanche (the murmur3 finaliser) and its inverse.  The grouped
+// build sorts records by mix64(key): equal words <=> equal k-mers, and the low 40 bits of the mix tell almost
+// all distinct k-mers of a genome apart, whereas all 64 bits of the key itself are needed to do so.
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+__host__ __device__ inline uint64_t unmix64(uint64_t x) {
+  x ^= x >> 33; x *= 0x9cb4b2f8129337dbULL;      // inverse of 0xc4ceb9fe1a85ec53 mod 2^64
+  x ^= x >> 33; x *= 0x4f74430c22a54005ULL;      // inverse of 0xff51afd7ed558ccd mod 2^64
+  x ^= x >> 33;
+  return x;
+}
+
 // warp-level inclusive scans
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 #pragma unroll

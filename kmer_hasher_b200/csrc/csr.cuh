@@ -33,7 +33,7 @@ __global__ void sum_hist_kernel(const uint32_t *hist, IndexStats *st) {
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)
 rle_kernel(const uint64_t *__restrict__ keys, IndexStats *st, uint64_t *__restrict__ ukeys,
-           uint32_t *__restrict__ ustart, Pair64 *status, uint32_t *ticket) {
+           uint32_t *__restrict__ ustart, Pair64 *status, uint32_t *ticket, const bool hashed) {
   constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32;
   __shared__ uint32_t s_tile, s_wsum[WARPS];
   __shared__ uint64_t s_base;
@@ -86,7 +86,7 @@ rle_kernel(const uint64_t *__restrict__ keys, IndexStats *st, uint64_t *__restri
   for (int i = 0; i < ITEMS; ++i) {
     if ((heads >> i) & 1u) {
       const uint64_t u = base + before[i];
-      ukeys[u] = key[i];
+      ukeys[u] = hashed ? unmix64(key[i]) : key[i];        // grouped build: records carry mix64(key)
       ustart[u] = (uint32_t)(w0 + i * 32 + lane);
     }
   }
@@ -94,6 +94,145 @@ rle_kernel(const uint64_t *__restrict__ keys, IndexStats *st, uint64_t *__restri
     const uint64_t U = s_base + total;
     ustart[U] = (uint32_t)n;
     st->U = U;
+  }
+}
+
+// ---- grouped build: make equal k-mers contiguous after a sort on the low `bits` bits of mix64(key) -------
+// Records are ordered by the low bits of h = mix64(key), stably.  A "group" is a run of equal low bits; almost
+// every group holds one k-mer.  Where it holds several (a collision of the low bits: ~N^2 / 2^(bits+1) pairs)
+// they interleave and the group has to be partitioned by h, stably.  group_detect_kernel finds those groups
+// (read-only), small_fix_kernel sorts the short ones in place, big_fix_kernel partitions the long ones.
+constexpr int SMALL_GROUP = 64;
+constexpr uint32_t CLAIM_SLOTS = 1u << 16;
+
+struct FixLists {
+  uint2 *small_tasks;      // (start, end) of dirty groups of at most SMALL_GROUP records
+  uint2 *big_tasks;        // (start, end) of longer ones
+  uint32_t *counters;      // [0] small tasks, [1] big tasks, [2] overflow flag
+  uint32_t *claim;         // CLAIM_SLOTS words, zero: one task per big group
+  uint32_t small_cap, big_cap;
+};
+
+__device__ __forceinline__ uint64_t first_at_least(const uint64_t *h, uint64_t n, uint64_t lowmask, uint64_t v) {
+  uint64_t lo = 0, hi = n;                               // first j with (h[j] & lowmask) >= v
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if ((h[mid] & lowmask) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void group_detect_kernel(const uint64_t *__restrict__ h, const IndexStats *st, int bits, FixLists fl) {
+  const uint64_t n = st->n;
+  const uint64_t lowmask = bits >= 64 ? ~uint64_t(0) : ((uint64_t(1) << bits) - 1);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t a = h[i - 1], b = h[i];
+    if (((a ^ b) & lowmask) != 0 || a == b) continue;    // not a boundary between two k-mers inside one group
+    const uint64_t low = b & lowmask;
+    const uint64_t s = first_at_least(h, n, lowmask, low);
+    const uint64_t e = low == lowmask ? n : first_at_least(h, n, lowmask, low + 1);
+    if (e - s <= SMALL_GROUP) {
+      bool first = true;                                 // the group's first boundary files the task
+      const uint64_t h0 = h[s];
+      for (uint64_t j = s + 1; j < i; ++j) first &= h[j] == h0;
+      if (first) {
+        const uint32_t t = atomicAdd(fl.counters + 0, 1u);
+        if (t < fl.small_cap) fl.small_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
+      }
+    } else {
+      uint32_t slot = (uint32_t)(mix64(s) & (CLAIM_SLOTS - 1));
+      bool mine = false;
+      for (uint32_t probe = 0; probe < CLAIM_SLOTS; ++probe) {
+        const uint32_t old = atomicCAS(fl.claim + slot, 0u, (uint32_t)s + 1u);
+        if (old == 0u) { mine = true; break; }
+        if (old == (uint32_t)s + 1u) break;              // another boundary of the same group got there first
+        slot = (slot + 1) & (CLAIM_SLOTS - 1);
+      }
+      if (mine) {
+        const uint32_t t = atomicAdd(fl.counters + 1, 1u);
+        if (t < fl.big_cap) fl.big_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
+      }
+    }
+  }
+}
+
+// one thread per short dirty group: stable insertion sort of its records by h, in place
+__global__ void small_fix_kernel(uint64_t *__restrict__ h, uint32_t *__restrict__ pos, FixLists fl) {
+  const uint32_t nt = min(fl.counters[0], fl.small_cap);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const uint2 se = fl.small_tasks[t];
+    const int c = (int)(se.y - se.x);
+    uint64_t hh[SMALL_GROUP];
+    uint32_t pp[SMALL_GROUP];
+    for (int j = 0; j < c; ++j) { hh[j] = h[se.x + j]; pp[j] = pos[se.x + j]; }
+    for (int j = 1; j < c; ++j) {
+      const uint64_t x = hh[j];
+      const uint32_t y = pp[j];
+      int m = j - 1;
+      while (m >= 0 && hh[m] > x) { hh[m + 1] = hh[m]; pp[m + 1] = pp[m]; --m; }
+      hh[m + 1] = x; pp[m + 1] = y;
+    }
+    for (int j = 0; j < c; ++j) { h[se.x + j] = hh[j]; pos[se.x + j] = pp[j]; }
+  }
+}
+
+// one CTA per long dirty group: its distinct h values in ascending order, each compacted (stably) into scratch
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+big_fix_kernel(uint64_t *__restrict__ h, uint32_t *__restrict__ pos, uint64_t *__restrict__ sh, uint32_t *__restrict__ sp, FixLists fl) {
+  __shared__ uint64_t s_min[THREADS / 32];
+  __shared__ uint32_t s_cnt[THREADS / 32];
+  __shared__ uint64_t s_cur;
+  __shared__ uint32_t s_placed;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t nt = min(fl.counters[1], fl.big_cap);
+  for (uint32_t t = blockIdx.x; t < nt; t += gridDim.x) {
+    const uint2 se = fl.big_tasks[t];
+    const uint32_t s = se.x, e = se.y;
+    uint32_t placed = 0;
+    bool have_last = false;
+    uint64_t last = 0;
+    while (placed < e - s) {
+      uint64_t m = ~uint64_t(0);                         // smallest h not placed yet (h > last)
+      bool any = false;
+      for (uint32_t j = s + tid; j < e; j += THREADS) {
+        const uint64_t v = h[j];
+        if (!have_last || v > last) { if (!any || v < m) m = v; any = true; }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) { const uint64_t o = __shfl_xor_sync(FULL, m, d); m = o < m ? o : m; }
+      if (lane == 0) s_min[warp] = m;
+      __syncthreads();
+      if (tid == 0) {
+        uint64_t mm = s_min[0];
+        for (int w = 1; w < THREADS / 32; ++w) mm = s_min[w] < mm ? s_min[w] : mm;
+        s_cur = mm;                                      // exists: placed < e - s
+        s_placed = placed;
+      }
+      __syncthreads();
+      const uint64_t cur = s_cur;
+      for (uint32_t base = s; base < e; base += THREADS) {
+        const uint32_t j = base + tid;
+        const bool hit = j < e && h[j] == cur;
+        const unsigned bal = __ballot_sync(FULL, hit);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) { if (w < (int)warp) before += s_cnt[w]; total += s_cnt[w]; }
+        const uint32_t at = s + s_placed + before + __popc(bal & lanemask_lt());
+        if (hit) { sh[at] = cur; sp[at] = pos[j]; }
+        __syncthreads();
+        if (tid == 0) s_placed += total;
+        __syncthreads();
+      }
+      placed = s_placed;
+      last = cur;
+      have_last = true;
+      __syncthreads();
+    }
+    for (uint32_t j = s + tid; j < e; j += THREADS) { h[j] = sh[j]; pos[j] = sp[j]; }
+    __syncthreads();
   }
 }
 

@@ -91,7 +91,7 @@ __device__ __forceinline__ uint2 resolve_key(const KeyHash &kh, uint64_t key, ui
 template <int THREADS, int ITEMS, bool FROM_SEQ>
 __global__ void __launch_bounds__(THREADS, 3)
 probe_lookup_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, int64_t n_in, const uint64_t *__restrict__ n_dev,
-                    const KeyHash kh, uint2 *__restrict__ found) {
+                    const KeyHash kh, uint2 *__restrict__ found, const bool mixed = false) {
   constexpr int TILE = THREADS * ITEMS;
   __shared__ TileCodes<FROM_SEQ ? TILE : 16> tc;
   const unsigned tid = threadIdx.x;
@@ -124,6 +124,7 @@ probe_lookup_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, int6
       } else {
         ok[j] = q0 + t0 + i < total;
         key = ok[j] ? ld_stream_u64(keys_in + q0 + t0 + i) : 0;
+        if (mixed) key = unmix64(key);                      // records of a grouped sharded index carry mix64(key)
       }
       kk[j] = key;
       home[j] = hash64(key) & kh.bmask;

@@ -45,6 +45,18 @@ struct OwnerBin {
     return (uint32_t)lo;
   }
 };
+// owner of the mixed key (grouped sharded build: owners hold ranges of mix64(key))
+struct HashOwnerBin {
+  static constexpr bool CHEAP = false;
+  OwnerBin ob;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return ob(mix64(key)); }
+};
+// digit of the mixed key (grouped build: histogram of pass 0 taken straight from the sequence)
+struct HashDigitBin {
+  static constexpr bool CHEAP = true;
+  int shift;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(mix64(key) >> shift) & (RADIX - 1); }
+};
 struct NoBin {
   static constexpr bool CHEAP = true;
   __device__ __forceinline__ uint32_t operator()(uint64_t) const { return 0; }
@@ -73,6 +85,7 @@ struct PassParams {
   uint32_t *ticket;           // tile id dispenser (zero before launch)
   const uint64_t *n_records;  // record source: exact number of records (device scalar)
   uint32_t epoch;
+  uint32_t hashed;            // FROM_SEQ: records carry mix64(key) instead of the key (grouped build)
   uint32_t pos_add;           // FROM_SEQ: added to the 1-based start (k-1 turns it into the 1-based end of a query window)
   const PeerTable *peer;      // PEER: per-bin destination arrays (own or NVLink-mapped peer memory)
   unsigned long long *trace;  // tuning runs only: 8 clock64 stamps per tile, or nullptr
@@ -192,6 +205,7 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     for (int i = 0; i < ITEMS; ++i) {
       const int t = t0 + i * 32;
       key[i] = tile_key<TILE>(sm.tc, t, P.sv.k);
+      if (P.hashed) key[i] = mix64(key[i]);
       if constexpr (!FULL)
         if (tile_valid<TILE>(P.sv, sm.tc, q0, t, special)) valid |= 1u << i;
     }

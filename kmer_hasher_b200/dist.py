@@ -77,15 +77,15 @@ class CudaEngine:
         self._lib.check(self.L.kmg_shard_open(shard.data_ptr(), g0, g1, L, s0, s1, k, C.byref(h)))
         return h
 
-    def shard_pack(self, own, k, n_samples):
+    def shard_pack(self, own, k, n_samples, order=0):
         pack = torch.empty(self.L.kmg_shard_pack_bytes(n_samples), dtype=torch.uint8, device=self.device)
-        self._lib.check(self.L.kmg_shard_pack(own.data_ptr(), own.numel(), k, n_samples, pack.data_ptr()))
+        self._lib.check(self.L.kmg_shard_pack(own.data_ptr(), own.numel(), k, n_samples, order, pack.data_ptr()))
         return pack
 
-    def shard_open_packed(self, own, L, world, rank, k, n_samples, allpack):
+    def shard_open_packed(self, own, L, world, rank, k, n_samples, allpack, order=0):
         h = C.c_void_p()
         spl = torch.empty(max(world - 1, 1), dtype=torch.int64, device=self.device)
-        self._lib.check(self.L.kmg_shard_open_packed(own.data_ptr(), own.numel(), L, world, rank, k, n_samples,
+        self._lib.check(self.L.kmg_shard_open_packed(own.data_ptr(), own.numel(), L, world, rank, k, n_samples, order,
                                                      allpack.data_ptr(), C.byref(h), spl.data_ptr()))
         return h, spl[:world - 1]
 
@@ -108,16 +108,16 @@ class CudaEngine:
                                                  capacity, matrix.data_ptr(), pos_add, info.data_ptr()))
         return info
 
-    def build_received(self, slot, capacity, info, k):
+    def build_received(self, slot, capacity, info, k, order=1):
         from . import KmerHash
         h = C.c_void_p()
-        self._lib.check(self.L.kmg_build_received(slot.keys, slot.pos, capacity, info.data_ptr(), k, C.byref(h)))
+        self._lib.check(self.L.kmg_build_received(slot.keys, slot.pos, capacity, info.data_ptr(), k, order, C.byref(h)))
         return KmerHash(h.value, k)
 
-    def query_received(self, index, slot, capacity, info):
+    def query_received(self, index, slot, capacity, info, mixed=False):
         st, M = C.c_void_p(), C.c_uint64()
         self._lib.check(self.L.kmg_query_received(index._handle(), slot.keys, slot.pos, capacity, info.data_ptr(),
-                                                  C.byref(st), C.byref(M)))
+                                                  int(mixed), C.byref(st), C.byref(M)))
         rows = torch.empty((M.value, 2), dtype=torch.int32, device=self.device)
         try:
             self._lib.check(self.L.kmg_query_emit(st, rows.data_ptr()))
@@ -303,6 +303,7 @@ class ShardedIndex:
         self.local, self.k, self.rank, self.world = local, k, rank, world
         self._U_all, self._N_all, self._splitters, self.engine = U_all, N_all, splitters, engine
         self.splitters_dev, self.group = splitters_dev, group
+        self.mixed, self.order = False, 1                    # set by the peer-memory build when owners hold ranges of the mix
 
     def _gather_sizes(self):
         if self._U_all is None:
@@ -394,7 +395,7 @@ def sharded_build(own_bytes, L: int, k: int, engine, group=None, n_samples: int 
 
 
 def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerExchange, group=None,
-                      n_samples: int = 2048) -> ShardedIndex:
+                      n_samples: int = 2048, order: int = 0) -> ShardedIndex:
     """sharded_build with the exchange fused into the partitioning pass: records go straight into the
     owners' arrays over NVLink (kmg_shard_scatter); the host never waits between the halo and the
     finished index.  Falls back to sharded_build if an owner's share exceeds the exchange capacity."""
@@ -407,11 +408,13 @@ def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerE
             _MARKS.append((name, e, time.perf_counter()))
     ev("start")
     own = own_bytes if isinstance(own_bytes, torch.Tensor) else engine.upload(np.asarray(own_bytes, np.uint8))
-    pack = engine.shard_pack(own, k, n_samples)              # halo bytes + sorted splitter sample: ONE exchange
+    # order 0 (KMG_ORDER_GROUPED, as make.kmer.hash defaults to): for k >= 25 the sample, the owner ranges and the
+    # records are those of the mixed key and every owner builds a grouped index; order 1: ascending keys
+    pack = engine.shard_pack(own, k, n_samples, order)       # halo bytes + sorted splitter sample: ONE exchange
     allpack = torch.empty(world * pack.numel(), dtype=torch.uint8, device=engine.device)
     dist.all_gather_into_tensor(allpack, pack, group=group)
     ev("halo")
-    sh, spl = engine.shard_open_packed(own, L, world, rank, k, n_samples, allpack)
+    sh, spl = engine.shard_open_packed(own, L, world, rank, k, n_samples, allpack, order)
     try:
         ev("splitters")
         counts = engine.shard_count(sh, spl, world)
@@ -425,7 +428,7 @@ def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerE
         ev("barrier")
         from ._lib import KmgError
         try:
-            local = engine.build_received(slot, xchg.capacity, info, k)
+            local = engine.build_received(slot, xchg.capacity, info, k, order)
         except KmgError as e:
             if e.code != -3:
                 raise
@@ -435,7 +438,10 @@ def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerE
     ev("built")
     if local is None:          # an owner overflowed; every rank saw the same flag (it is computed from the shared
         return sharded_build(own, L, k, engine, group)       # count matrix), so all take the general path together
-    return ShardedIndex(local, k, rank, world, None, None, None, engine, splitters_dev=spl, group=group)
+    ix = ShardedIndex(local, k, rank, world, None, None, None, engine, splitters_dev=spl, group=group)
+    ix.mixed = engine.L.kmg_index_order(local._handle()) == 0   # owner ranges are those of the mixed key
+    ix.order = order
+    return ix
 
 
 def sharded_query_p2p(index: ShardedIndex, own_query_bytes, Lq: int, k: int, xchg: PeerExchange, group=None) -> torch.Tensor:
@@ -450,13 +456,15 @@ def sharded_query_p2p(index: ShardedIndex, own_query_bytes, Lq: int, k: int, xch
         spl = torch.from_numpy(np.ascontiguousarray(index.splitters).view(np.int64)).to(engine.device)
     sh = engine.shard_open(shard, g0, g1, Lq, s0, s1, k)
     try:
+        if index.mixed:                                      # owners hold ranges of the mixed key: route by it
+            engine._lib.check(engine.L.kmg_shard_set_mixed(sh, 1))
         counts = engine.shard_count(sh, spl, world)
         matrix = torch.empty(world * world, dtype=torch.int64, device=engine.device)
         dist.all_gather_into_tensor(matrix, counts, group=group)
         slot = xchg.next_slot()
         info = engine.shard_scatter(sh, spl, world, rank, slot, xchg.capacity, matrix, k - 1)   # 1-based END (src/kmer_pos.c:127)
         xchg.barrier()
-        return engine.query_received(index.local, slot, xchg.capacity, info)
+        return engine.query_received(index.local, slot, xchg.capacity, info, index.mixed)
     finally:
         engine.shard_close(sh)
 

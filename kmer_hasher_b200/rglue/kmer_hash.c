@@ -12,8 +12,8 @@
  *   kmer_pair_pos(ptr.a, ptr.b)             replaces src/kmer_hash.c:1174-1203 (which crashes: test.R:330-331)
  *   R_init_kmer_hash                        replaces src/kmer_hash.c:1221-1224
  *
- * Differences a user can observe: k-mers come out ordered by 2-bit key instead of khash bucket order
- * (not semantic); results too large for an R matrix raise a clean error before anything is
+ * Differences a user can observe: k-mers come out in the order of a mix of their 2-bit key (ascending key
+ * with do.sort = TRUE) instead of khash bucket order (not semantic); results too large for an R matrix raise a clean error before anything is
  * allocated (the reference overflows or leaks, README "pair.pos"); do.sort is a no-op (lists are
  * always ascending).  Set KMERGPU_ALLOW_K32=1 to lift the reference's k <= 31 limit of seq.kmer.pos
  * (its C core handles 32; the limit is only in its R entry, src/kmer_hash.c:1163).
@@ -88,7 +88,11 @@ SEXP make_kmer_h_index(SEXP seq_r, SEXP k_r, SEXP sort_pos_r) {
   kmer_handle *h = (kmer_handle *)calloc(1, sizeof *h);
   if (!h) error("out of memory");
   h->k = k;
-  if (kmg_build(CHAR(s), (int64_t)len, k, &h->index) != KMG_OK) {
+  /* do.sort: position lists are always ascending, so there is nothing to sort there (src/kmer_pos.c:21-33 is a
+   * no-op in the reference too); it selects the order of the k-mers instead: TRUE = ascending key, FALSE (the R
+   * default) = the faster grouped build.  Neither order is semantic (the reference's is khash bucket order). */
+  const int order = INTEGER(sort_pos_r)[0] ? KMG_ORDER_SORTED : KMG_ORDER_GROUPED;
+  if (kmg_build_ordered(CHAR(s), (int64_t)len, k, order, &h->index) != KMG_OK) {
     free(h);
     error("make.kmer.hash failed: %s", kmg_last_error());
   }

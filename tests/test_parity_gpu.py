@@ -24,8 +24,8 @@ def compare_index(kh, oracle, seq, k, flags=15, guard=True):
     g = kh.make_kmer_hash(seq, k)
     assert g.sizes == (o.U, o.N, o.P), (g.sizes, (o.U, o.N, o.P))
     eo = o.extract(flags)
-    eg = kh.kmer_pos(g, flags)
-    assert np.array_equal(kh.kmer_keys(g), eo["keys"])
+    eg = kh.kmer_pos(g, flags, canonical=True)
+    assert np.array_equal(kh.kmer_keys(g, canonical=True), eo["keys"])
     if flags & 1:
         want = np.ascontiguousarray(eo["kmer"].reshape(o.U, k + 1)[:, :k]).view(f"S{k}").ravel()
         assert np.array_equal(eg["kmer"], want)
@@ -54,8 +54,8 @@ def test_golden_small(kh, oracle, golden):
             continue
         g = kh.make_kmer_hash(s, k)
         assert g.sizes == (c["U"], c["N"], c["P"]), (k, s)
-        e = kh.kmer_pos(g, 15)
-        assert kh.kmer_keys(g).tolist() == c["keys"]
+        e = kh.kmer_pos(g, 15, canonical=True)
+        assert kh.kmer_keys(g, canonical=True).tolist() == c["keys"]
         assert [x.decode() for x in e["kmer"]] == c["kmer"]
         assert e["count"].tolist() == c["count"]
         assert e["pos"].ravel().tolist() == c["pos"]
@@ -70,8 +70,8 @@ def test_golden_test_fa(kh, golden, test_fa, k):
     g = golden["test_fa"][str(k)]
     ix = kh.make_kmer_hash(test_fa, k)
     assert ix.sizes == (g["U"], g["N"], g["P"])
-    e = kh.kmer_pos(ix, 15)
-    assert sha(kh.kmer_keys(ix)) == g["sha_keys"]
+    e = kh.kmer_pos(ix, 15, canonical=True)
+    assert sha(kh.kmer_keys(ix, canonical=True)) == g["sha_keys"]
     assert sha(e["count"]) == g["sha_count"]
     assert sha(e["pos"]) == g["sha_pos"]
     assert sha(e["pair.pos"]) == g["sha_pair_pos"]
@@ -132,7 +132,7 @@ def test_pairs_chunked_equals_whole(kh, oracle, test_fa):
     L = _lib.load()
     ix = kh.make_kmer_hash(test_fa, 16)
     U, N, P = ix.sizes
-    whole = kh.kmer_pos(ix, 4)["pair.pos"]
+    whole = kh.kmer_pos(ix, 4)["pair.pos"]              # the index's own order: chunks are slices of it
     rng = np.random.default_rng(3)
     for _ in range(6):
         first = int(rng.integers(0, P))
@@ -159,9 +159,9 @@ def test_r_level_guards(kh):
         kh.seq_kmer_pos(ix, "ACGTACGT", 8)
     with pytest.raises(ValueError, match="single sequence"):
         kh.seq_kmer_pos(ix, [s, s], 8)
-    r = kh.kmer_pos(ix, 8)
+    r = kh.kmer_pos(ix, 8, canonical=True)
     assert r["kmer"] is None and r["pos"] is None and r["pair.pos"] is None and r["count"] is not None
-    r = kh.kmer_pos(ix, 0)
+    r = kh.kmer_pos(ix, 0, canonical=True)
     assert all(v is None for v in r.values())
 
 
@@ -170,11 +170,11 @@ def test_handles_coexist_and_free(kh, oracle):
     hs = [kh.make_kmer_hash(s, 9 + i) for i, s in enumerate(seqs)]
     for i in (3, 0, 4, 1, 2):
         o = oracle.build(seqs[i], 9 + i)
-        assert np.array_equal(kh.kmer_pos(hs[i], 2)["pos"].ravel(), o.extract(2)["pos"])
+        assert np.array_equal(kh.kmer_pos(hs[i], 2, canonical=True)["pos"].ravel(), o.extract(2)["pos"])
     hs[2].free()
     hs[2].free()                         # finaliser tolerates a cleared pointer
     with pytest.raises(ValueError):
-        kh.kmer_pos(hs[2], 2)
+        kh.kmer_pos(hs[2], 2, canonical=True)
 
 
 def test_pinned_and_device_buffers(kh, oracle):
@@ -184,14 +184,14 @@ def test_pinned_and_device_buffers(kh, oracle):
     # pinned host input + pinned outputs
     pin = kh.pinned_empty(len(s), np.uint8)
     pin[:] = s
-    g = kh.make_kmer_hash(pin, 21)
+    g = kh.make_kmer_hash(pin, 21, do_sort=True)
     out = {"pos": kh.pinned_empty((o.N, 2), np.int32), "count": kh.pinned_empty(o.U, np.int32)}
     e = kh.kmer_pos(g, 10, out=out)
     assert np.array_equal(e["pos"].ravel(), o.extract(2)["pos"])
     assert np.array_equal(e["count"], o.extract(8)["count"])
     # device-resident input and output
     d = torch.from_numpy(s).cuda()
-    g2 = kh.make_kmer_hash(d, 21)
+    g2 = kh.make_kmer_hash(d, 21, do_sort=True)
     dout = torch.empty((o.N, 2), dtype=torch.int32, device="cuda")
     e2 = kh.kmer_pos(g2, 2, out={"pos": dout})
     torch.cuda.synchronize()
@@ -221,9 +221,9 @@ def test_full_size_properties(kh):
     g = kh.make_kmer_hash(s, k)
     U, N, P = g.sizes
     assert N == len(s) - k + 1                       # no N in config 2
-    e = kh.kmer_pos(g, 2 | 8)
+    e = kh.kmer_pos(g, 2 | 8)                        # the index's own (grouped) order: every property below holds in any order
     keys = kh.kmer_keys(g)
-    assert np.all(keys[1:] > keys[:-1])              # distinct, ascending
+    assert len(np.unique(keys)) == U                 # distinct
     cnt = e["count"].astype(np.int64)
     assert cnt.sum() == N and cnt.min() >= 1
     assert P == int((cnt * (cnt - 1) // 2).sum())
@@ -307,8 +307,8 @@ def test_sharded_engine_single_process(kh, oracle, world, k):
         kk = torch.cat(per_owner_k[o]); pp = torch.cat(per_owner_p[o])
         ix = eng.build_records(kk.clone(), pp.clone(), kk.numel(), k)
         U, N, _ = ix.sizes
-        e = kh.kmer_pos(ix, 2 | 8)
-        got_keys.append(kh.kmer_keys(ix)); got_cnt.append(e["count"])
+        e = kh.kmer_pos(ix, 2 | 8, canonical=True)
+        got_keys.append(kh.kmer_keys(ix, canonical=True)); got_cnt.append(e["count"])
         p = e["pos"].copy(); p[:, 0] += offs; got_pos.append(p)
         offs += U
         # routed probe: this owner's share of the query windows
@@ -325,8 +325,9 @@ def test_sharded_engine_single_process(kh, oracle, world, k):
     assert np.array_equal(rows.ravel(), qo)
 
 
-@pytest.mark.parametrize("world,k,L", [(2, 32, 500_000), (3, 21, 500_000), (8, 12, 500_000), (8, 32, 100), (5, 7, 23)])
-def test_peer_scatter_single_process(kh, oracle, world, k, L):
+@pytest.mark.parametrize("world,k,L,order", [(2, 32, 500_000, 1), (2, 32, 500_000, 0), (4, 27, 300_000, 0), (3, 21, 500_000, 0),
+                                             (8, 12, 500_000, 1), (8, 32, 100, 1), (8, 32, 100, 0), (5, 7, 23, 0)])
+def test_peer_scatter_single_process(kh, oracle, world, k, L, order):
     """The fused partition + exchange (kmg_shard_count / kmg_shard_scatter / kmg_build_received /
     kmg_query_received) with the ranks played one after another on one GPU: every "peer" array lives on
     this device, so the scatter's addressing (lower ranks first inside each owner's arrays), the
@@ -334,6 +335,7 @@ def test_peer_scatter_single_process(kh, oracle, world, k, L):
     import ctypes as C
     import torch
     from kmer_hasher_b200 import dist as kdist, synth, _lib
+    L_ = _lib.load()
     dev = torch.device("cuda", 0)
     eng = kdist.CudaEngine(dev)
     seq = synth.config_c3(L, tail_k=k) if L > 1000 else synth.generate(L, 11, n_single=2)
@@ -345,11 +347,12 @@ def test_peer_scatter_single_process(kh, oracle, world, k, L):
     # halo + splitter sample in one exchange (kmg_shard_pack -> "all-gather" -> kmg_shard_open_packed)
     ns = 512 if L > 1000 else 4
     owns = [eng.upload(seq[min(r * per, L):min((r + 1) * per, L)]) for r in range(world)]
-    packs = [eng.shard_pack(o, k, ns) for o in owns]
+    mixed = order == 0 and k >= 25                          # owners then hold ranges of the mixed key
+    packs = [eng.shard_pack(o, k, ns, order) for o in owns]
     allpack = torch.cat(packs)
     handles, spls = [], []
     for r in range(world):
-        h, spl_r = eng.shard_open_packed(owns[r], L, world, r, k, ns, allpack)
+        h, spl_r = eng.shard_open_packed(owns[r], L, world, r, k, ns, allpack, order)
         handles.append(h); spls.append(spl_r.cpu().numpy().view(np.uint64))
     smp = np.concatenate([p.cpu().numpy()[48:].view(np.uint64) for p in packs])
     for r in range(world):
@@ -378,17 +381,25 @@ def test_peer_scatter_single_process(kh, oracle, world, k, L):
     got_keys, got_cnt, got_pos, offs, owners = [], [], [], 0, []
     for o, (sl, info) in enumerate(infos):
         assert info.cpu().tolist() == [int(m[:, o].sum()), 0]
-        ix = eng.build_received(sl, cap, info, k)
+        ix = eng.build_received(sl, cap, info, k, order)
         U, N, _ = ix.sizes
         assert N == m[:, o].sum()
+        assert (L_.kmg_index_order(ix._handle()) == 0) == mixed
         e = kh.kmer_pos(ix, 2 | 8)
         got_keys.append(kh.kmer_keys(ix)); got_cnt.append(e["count"])
         p = e["pos"].copy(); p[:, 0] += offs; got_pos.append(p)
         offs += U
         owners.append(ix)
-    assert np.array_equal(np.concatenate(got_keys), want["keys"])
-    assert np.array_equal(np.concatenate(got_cnt), want["count"])
-    assert np.array_equal(np.concatenate(got_pos).ravel(), want["pos"])
+    allk, allc, allp = np.concatenate(got_keys), np.concatenate(got_cnt), np.concatenate(got_pos)
+    if mixed:                                               # owners hold ranges of the mix: order everything by key
+        assert len(np.unique(allk)) == len(allk)
+        order_k = np.argsort(allk, kind="stable")
+        rank = np.empty(len(allk), np.int64); rank[order_k] = np.arange(len(allk))
+        allk, allc = allk[order_k], allc[order_k]
+        allp = kh._renumber(allp, rank)
+    assert np.array_equal(allk, want["keys"])
+    assert np.array_equal(allc, want["count"])
+    assert np.array_equal(allp.ravel(), want["pos"])
 
     if L <= 1000:
         for ix in owners:
@@ -404,11 +415,13 @@ def test_peer_scatter_single_process(kh, oracle, world, k, L):
     for r in range(world):
         s0, s1, g0, g1 = kdist.shard_bounds(Lq, world, r, k)
         qh.append(eng.shard_open(eng.upload(q[g0:g1]), g0, g1, Lq, s0, s1, k))
+        if mixed:
+            _lib.check(L_.kmg_shard_set_mixed(qh[-1], 1))
     qmat = torch.cat([eng.shard_count(h, spl, world) for h in qh])
     qcap = int(qmat.cpu().numpy().reshape(world, world).sum(axis=0).max()) + 1
     qkeep_k, qkeep_p, qinfos = scatter_all(qcap, k - 1, qh, qmat)      # keep the receive arrays alive
-    rows = np.concatenate([eng.query_received(owners[o], sl, qcap, info).cpu().numpy() for o, (sl, info) in enumerate(qinfos)])
-    rows = rows[np.argsort(rows[:, 0], kind="stable")]
+    rows = np.concatenate([eng.query_received(owners[o], sl, qcap, info, mixed).cpu().numpy() for o, (sl, info) in enumerate(qinfos)])
+    rows = rows[np.lexsort((rows[:, 1], rows[:, 0]))]      # rows of one i may now come from... one owner still; j ascending
     assert np.array_equal(rows.ravel(), qo)
 
     # an exchange that is too small is reported, not silently truncated
@@ -417,7 +430,7 @@ def test_peer_scatter_single_process(kh, oracle, world, k, L):
     big = int(np.argmax(m.sum(axis=0)))
     assert infos2[big][1].cpu().tolist()[1] == 1
     with pytest.raises(_lib.KmgError):
-        eng.build_received(infos2[big][0], small, infos2[big][1], k)
+        eng.build_received(infos2[big][0], small, infos2[big][1], k, order)
     for ix in owners:
         ix.free()
     for h in handles + qh:
@@ -431,12 +444,16 @@ def test_kmer_pairs(kh, oracle, ka, kb):
     from kmer_hasher_b200 import synth
     a_seq = synth.config_c3(300_000, tail_k=ka)
     b_seq = synth.config_c4_query(a_seq, 150_000)
-    ia, ib = kh.make_kmer_hash(a_seq, ka), kh.make_kmer_hash(b_seq, kb)
+    ia, ib = kh.make_kmer_hash(a_seq, ka, do_sort=True), kh.make_kmer_hash(b_seq, kb)   # rows follow a's k-mer order
     oa, ob = oracle.build(a_seq, ka), oracle.build(b_seq, kb)
     want = oracle_mod.pairs_join(oa.extract(2 | 8), ob.extract(2 | 8))
     got = kh.kmer_pairs(ia, ib)
     assert got.shape == (len(want) // 2, 2)
     assert np.array_equal(got.ravel(), want)
+    ig = kh.make_kmer_hash(a_seq, ka)                     # grouped order of a: the same rows, k-mers in another order
+    gg = kh.kmer_pairs(ig, ib)
+    assert np.array_equal(gg[np.lexsort((gg[:, 1], gg[:, 0]))], got[np.lexsort((got[:, 1], got[:, 0]))])
+    ig.free()
     # chunked emission == whole, pinned output, and an index joined with itself = sum of squares of the counts
     import ctypes as C
     from kmer_hasher_b200 import _lib
@@ -453,7 +470,7 @@ def test_kmer_pairs(kh, oracle, ka, kb):
     L.kmg_join_free(st)
     if ka == kb:
         self_rows = kh.kmer_pairs(ia, ia)
-        cnt = kh.kmer_pos(ia, 8)["count"].astype(np.int64)
+        cnt = kh.kmer_pos(ia, 8, canonical=True)["count"].astype(np.int64)
         assert len(self_rows) == int((cnt * cnt).sum())
     empty = kh.make_kmer_hash("A" * 40, 16)
     other = kh.make_kmer_hash("C" * 40, 16)
@@ -511,11 +528,50 @@ def test_every_sort_pass_variant_is_exact(kh, oracle, cfg):
         _lib.check(L.kmg_tune(b"sort_cfg", cfg))
         for k in (32, 21, 9):
             ix = kh.make_kmer_hash(seq, k)
-            got = kh.kmer_pos(ix, 2 | 8)
+            got = kh.kmer_pos(ix, 2 | 8, canonical=True)
             want = oracle.build(seq, k).extract(2 | 8)
-            assert np.array_equal(kh.kmer_keys(ix), want["keys"])
+            assert np.array_equal(kh.kmer_keys(ix, canonical=True), want["keys"])
             assert np.array_equal(got["count"], want["count"])
             assert np.array_equal(got["pos"].ravel(), want["pos"])
             ix.free()
     finally:
         _lib.check(L.kmg_tune(b"sort_cfg", 3))
+
+
+@pytest.mark.parametrize("bits", [16, 24, 40])
+def test_grouped_build_with_forced_collisions(kh, oracle, bits):
+    """KMG_ORDER_GROUPED sorts on `bits` bits of a mix of the key and partitions the groups in which several
+    k-mers share those bits.  Few bits force such groups everywhere: 8 bits -> every group is long (the
+    block-level partition), 16 bits -> every group is short (the in-place insertion sort), 24 -> a mixture."""
+    import ctypes as C
+    from kmer_hasher_b200 import synth, _lib
+    L = _lib.load()
+    seq = synth.generate(200_000, 0xC2, repeat=0.3, lower=0.2)
+    seq[1000:1900] = ord("A")                              # a k-mer with ~870 positions: its group is a long one
+    seq[9000:10200] = np.frombuffer(b"CA" * 600, np.uint8)
+    seq[50000:50003] = ord("n")
+    try:
+        _lib.check(L.kmg_tune(b"hash_bits", bits))
+        for k in (32, 27):
+            if bits // 8 + 1 >= (2 * k + 7) // 8:          # not worth grouping: the build is sorted anyway
+                continue
+            ix = kh.make_kmer_hash(seq, k)
+            assert L.kmg_index_order(ix._handle()) == 0
+            o = oracle.build(seq, k)
+            want = o.extract(15)
+            assert ix.sizes == (o.U, o.N, o.P)
+            got = kh.kmer_pos(ix, 15, canonical=True)
+            assert np.array_equal(kh.kmer_keys(ix, canonical=True), want["keys"])
+            assert np.array_equal(got["count"], want["count"])
+            assert np.array_equal(got["pos"].ravel(), want["pos"])
+            assert np.array_equal(got["pair.pos"].ravel(), want["pair_pos"])
+            raw = kh.kmer_pos(ix, 2 | 8)                   # in the index's own order: rows grouped by i, lists ascending
+            assert np.array_equal(raw["pos"][:, 0], np.repeat(np.arange(1, o.U + 1, dtype=np.int32), raw["count"]))
+            q = synth.config_c4_query(seq, 80_000)
+            assert np.array_equal(kh.seq_kmer_pos(ix, q, k, allow_k32=True).ravel(), o.query(q, k))
+            srt = kh.make_kmer_hash(seq, k, do_sort=True)  # the sorted build gives ascending keys directly
+            assert L.kmg_index_order(srt._handle()) == 1
+            assert np.array_equal(kh.kmer_keys(srt), want["keys"])
+            ix.free(); srt.free()
+    finally:
+        _lib.check(L.kmg_tune(b"hash_bits", 40))

@@ -65,10 +65,21 @@ for name, ix in (("general", kdist.sharded_build(own4, Lq4 * world, k, eng)), ("
     ix.local.free()
 dist.barrier()
 if rank == 0:
-    for what in ("keys", "count", "pos"):
-        g = np.concatenate([np.load(f"/tmp/p2p_general_{r}_{what}.npy") for r in range(world)])
-        p = np.concatenate([np.load(f"/tmp/p2p_peer_{r}_{what}.npy") for r in range(world)])
-        assert np.array_equal(g, p), what
+    def canon(name):
+        keys = np.concatenate([np.load(f"/tmp/p2p_{name}_{r}_keys.npy") for r in range(world)])
+        cnt = np.concatenate([np.load(f"/tmp/p2p_{name}_{r}_count.npy") for r in range(world)])
+        pos = np.concatenate([np.load(f"/tmp/p2p_{name}_{r}_pos.npy") for r in range(world)])
+        start = np.concatenate([[0], np.cumsum(cnt, dtype=np.int64)])
+        o = np.argsort(keys, kind="stable")             # the peer path builds grouped indexes: order by key to compare
+        lists = np.concatenate([pos[start[u]:start[u + 1]] for u in o]) if len(o) < 3_000_000 else None
+        return keys[o], cnt[o], lists, pos
+    gk, gc, gl, gp = canon("general")
+    pk, pc, pl, pp = canon("peer")
+    assert np.array_equal(gk, pk) and np.array_equal(gc, pc)
+    if gl is not None:
+        assert np.array_equal(gl, pl)
+    else:                                               # large: the multiset of positions and every list ascending
+        assert np.array_equal(np.sort(gp), np.sort(pp))
     g = np.concatenate([np.load(f"/tmp/p2p_general_{r}_rows.npy") for r in range(world)])
     p = np.concatenate([np.load(f"/tmp/p2p_peer_{r}_rows.npy") for r in range(world)])
     g = g[np.lexsort((g[:, 1], g[:, 0]))]; p = p[np.lexsort((p[:, 1], p[:, 0]))]
