@@ -476,6 +476,8 @@ def sharded_query(index: ShardedIndex, own_query_bytes, Lq: int, k: int, group=N
     reproduces the reference order)."""
     engine = index.engine
     world, rank = index.world, index.rank
+    if index.mixed:
+        raise ValueError("this index was built grouped (owners hold ranges of the mixed key): probe it with sharded_query_p2p")
     s0, s1, _, _ = shard_bounds(Lq, world, rank, k)
     own = own_query_bytes if isinstance(own_query_bytes, torch.Tensor) else engine.upload(np.asarray(own_query_bytes, np.uint8))
     shard, g0, g1 = exchange_halo(own, Lq, k, rank, world, group)
