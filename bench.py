@@ -307,6 +307,8 @@ def bench_single(args, kh, torch, w, k, L, steps, warm, hbm_peak, peak_src, dev)
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": w["name"], "k": k, "bases": L, "kmers": int(N), "distinct": int(U),
+                       "kmer_order": "grouped (make.kmer.hash default for k >= 25: 5 radix passes on a mix of the key; "
+                                     "do.sort=TRUE would give ascending keys in 8)" if k >= 25 else "ascending key",
                        "l2": "inputs_exceed_l2 (keys 8N + pos 4N bytes per pass >> 126 MB)"},
             "e2e": {"value": N / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
