@@ -122,36 +122,56 @@ __device__ __forceinline__ uint64_t first_at_least(const uint64_t *h, uint64_t n
   return lo;
 }
 
+__device__ __forceinline__ void file_group(const uint64_t *__restrict__ h, uint64_t n, uint64_t lowmask, uint64_t i, const FixLists &fl) {
+  // h[i-1] and h[i] share the low bits and differ: a boundary between two k-mers inside one group
+  const uint64_t low = h[i] & lowmask;
+  const uint64_t s = first_at_least(h, n, lowmask, low);
+  const uint64_t e = low == lowmask ? n : first_at_least(h, n, lowmask, low + 1);
+  if (e - s <= SMALL_GROUP) {
+    bool first = true;                                   // the group's first boundary files the task
+    const uint64_t h0 = h[s];
+    for (uint64_t j = s + 1; j < i; ++j) first &= h[j] == h0;
+    if (first) {
+      const uint32_t t = atomicAdd(fl.counters + 0, 1u);
+      if (t < fl.small_cap) fl.small_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
+    }
+  } else {
+    uint32_t slot = (uint32_t)(mix64(s) & (CLAIM_SLOTS - 1));
+    bool mine = false;
+    for (uint32_t probe = 0; probe < CLAIM_SLOTS; ++probe) {
+      const uint32_t old = atomicCAS(fl.claim + slot, 0u, (uint32_t)s + 1u);
+      if (old == 0u) { mine = true; break; }
+      if (old == (uint32_t)s + 1u) break;                // another boundary of the same group got there first
+      slot = (slot + 1) & (CLAIM_SLOTS - 1);
+    }
+    if (mine) {
+      const uint32_t t = atomicAdd(fl.counters + 1, 1u);
+      if (t < fl.big_cap) fl.big_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
+    }
+  }
+}
+
+// four records per thread (two 16-byte loads + the predecessor); boundaries are rare, the stream is the cost
 __global__ void group_detect_kernel(const uint64_t *__restrict__ h, const IndexStats *st, int bits, FixLists fl) {
   const uint64_t n = st->n;
   const uint64_t lowmask = bits >= 64 ? ~uint64_t(0) : ((uint64_t(1) << bits) - 1);
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t a = h[i - 1], b = h[i];
-    if (((a ^ b) & lowmask) != 0 || a == b) continue;    // not a boundary between two k-mers inside one group
-    const uint64_t low = b & lowmask;
-    const uint64_t s = first_at_least(h, n, lowmask, low);
-    const uint64_t e = low == lowmask ? n : first_at_least(h, n, lowmask, low + 1);
-    if (e - s <= SMALL_GROUP) {
-      bool first = true;                                 // the group's first boundary files the task
-      const uint64_t h0 = h[s];
-      for (uint64_t j = s + 1; j < i; ++j) first &= h[j] == h0;
-      if (first) {
-        const uint32_t t = atomicAdd(fl.counters + 0, 1u);
-        if (t < fl.small_cap) fl.small_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
-      }
-    } else {
-      uint32_t slot = (uint32_t)(mix64(s) & (CLAIM_SLOTS - 1));
-      bool mine = false;
-      for (uint32_t probe = 0; probe < CLAIM_SLOTS; ++probe) {
-        const uint32_t old = atomicCAS(fl.claim + slot, 0u, (uint32_t)s + 1u);
-        if (old == 0u) { mine = true; break; }
-        if (old == (uint32_t)s + 1u) break;              // another boundary of the same group got there first
-        slot = (slot + 1) & (CLAIM_SLOTS - 1);
-      }
-      if (mine) {
-        const uint32_t t = atomicAdd(fl.counters + 1, 1u);
-        if (t < fl.big_cap) fl.big_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
-      }
+  const uint64_t quads = n / 4;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 a = ld_stream_u4(reinterpret_cast<const uint4 *>(h) + 2 * q);
+    const uint4 b = ld_stream_u4(reinterpret_cast<const uint4 *>(h) + 2 * q + 1);
+    const uint64_t v[5] = {q ? h[4 * q - 1] : 0, (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
+                           (uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (q == 0 && j == 0) continue;
+      if (((v[j] ^ v[j + 1]) & lowmask) == 0 && v[j] != v[j + 1]) file_group(h, n, lowmask, 4 * q + j, fl);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - 4 * quads) {
+    const uint64_t i = 4 * quads + threadIdx.x;
+    if (i > 0) {
+      const uint64_t x = h[i - 1], y = h[i];
+      if (((x ^ y) & lowmask) == 0 && x != y) file_group(h, n, lowmask, i, fl);
     }
   }
 }

@@ -628,18 +628,25 @@ hist_seq_kernel(const SeqView sv, uint32_t *hist, BinFn bin) {
   constexpr int TILE = THREADS * ITEMS;
   __shared__ TileCodes<TILE> tc;
   __shared__ uint32_t sh[RADIX];
-  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const unsigned tid = threadIdx.x;
   for (int b = tid; b < RADIX; b += THREADS) sh[b] = 0;
   const int64_t tiles = ceil_div<int64_t>(sv.nstarts, TILE);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t q0 = tile * TILE;
     __syncthreads();                                   // previous tile's readers are done
     const bool special = tile_pack<TILE, THREADS>(sv, q0, tc);
-    const int t0 = warp * (32 * ITEMS) + lane;
+    // a histogram does not care about order: a thread takes ITEMS consecutive windows and rolls the key from
+    // one to the next (one base in) instead of extracting every window from the packed tile
+    const int t0 = tid * ITEMS;
+    const uint64_t kmask = key_mask(sv.k);
+    uint64_t key = tile_key<TILE>(tc, t0, sv.k);
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-      const int t = t0 + i * 32;
-      if (tile_valid<TILE>(sv, tc, q0, t, special)) atomicAdd(&sh[bin(tile_key<TILE>(tc, t, sv.k))], 1u);
+      if (i > 0) {
+        const int p = t0 + i + sv.k - 1;
+        key = ((key << 2) | ((tc.codes[p >> 4] >> (30 - 2 * (p & 15))) & 3u)) & kmask;
+      }
+      if (tile_valid<TILE>(sv, tc, q0, t0 + i, special)) atomicAdd(&sh[bin(key)], 1u);
     }
   }
   __syncthreads();
