@@ -137,13 +137,14 @@ __device__ __forceinline__ void file_group(const uint64_t *__restrict__ h, uint6
     }
   } else {
     uint32_t slot = (uint32_t)(mix64(s) & (CLAIM_SLOTS - 1));
-    bool mine = false;
-    for (uint32_t probe = 0; probe < CLAIM_SLOTS; ++probe) {
+    bool mine = false, seen = false;
+    for (uint32_t probe = 0; probe < CLAIM_SLOTS && !mine && !seen; ++probe) {
       const uint32_t old = atomicCAS(fl.claim + slot, 0u, (uint32_t)s + 1u);
-      if (old == 0u) { mine = true; break; }
-      if (old == (uint32_t)s + 1u) break;                // another boundary of the same group got there first
+      mine = old == 0u;
+      seen = old == (uint32_t)s + 1u;                    // another boundary of the same group got there first
       slot = (slot + 1) & (CLAIM_SLOTS - 1);
     }
+    if (!mine && !seen) fl.counters[2] = 1;              // claim table full: the caller rebuilds sorted by key
     if (mine) {
       const uint32_t t = atomicAdd(fl.counters + 1, 1u);
       if (t < fl.big_cap) fl.big_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
