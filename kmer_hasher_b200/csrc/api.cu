@@ -361,6 +361,7 @@ constexpr int N_SORT_CFG = 8;
 // Bits of mix64(key) the grouped build sorts on (kmg_tune "hash_bits", a multiple of 8; tests lower it to
 // force collisions).  40 bits: ~N^2 / 2^41 colliding pairs (730 at 40 M k-mers, 1 M at 1.5 G).
 static int g_hash_bits = 40;
+static int g_fix_cap = 0;      // kmg_tune "fix_cap": capacity of the short-group task list (0 = max(2^20, N/8)); tests shrink it
 static int g_sort_cfg = -1;
 static uint32_t g_sort_dbg = 0;
 static int lane_order_failures(uint32_t *failures);
@@ -394,6 +395,7 @@ extern "C" int kmg_tune(const char *key, int value) {
     return KMG_OK;
   }
   if (key && !strcmp(key, "sort_dbg")) { g_sort_dbg = (uint32_t)value; return KMG_OK; }
+  if (key && !strcmp(key, "fix_cap")) { g_fix_cap = value > 0 ? value : 0; return KMG_OK; }
   if (key && !strcmp(key, "hash_bits")) {
     if (value < 8 || value > 56 || value % RADIX_BITS) return fail(KMG_ERR_ARG, "hash_bits must be a multiple of 8 in [8,56]");
     g_hash_bits = value;
@@ -547,7 +549,7 @@ static int fix_groups(SortScratch &sc, uint64_t *keys, uint32_t *pos, uint64_t *
                       uint32_t *h_cnt /* [4], pinned or stack read after a sync */, uint32_t **fixmem_out) {
   FixLists fl{};
   uint32_t *fixmem = nullptr;
-  fl.small_cap = (uint32_t)std::max<int64_t>(1 << 20, n_upper / 8);
+  fl.small_cap = g_fix_cap > 0 ? (uint32_t)g_fix_cap : (uint32_t)std::max<int64_t>(1 << 20, n_upper / 8);
   fl.big_cap = 1 << 16;
   const size_t words = 4 + CLAIM_SLOTS + 2 * (size_t)fl.small_cap + 2 * (size_t)fl.big_cap;
   TRY(dalloc(&fixmem, words, s));

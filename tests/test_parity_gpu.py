@@ -575,3 +575,43 @@ def test_grouped_build_with_forced_collisions(kh, oracle, bits):
             ix.free(); srt.free()
     finally:
         _lib.check(L.kmg_tune(b"hash_bits", 40))
+
+
+def test_grouped_build_falls_back_when_the_task_list_overflows(kh, oracle):
+    """More colliding groups than the fix-up's task list holds (forced: 16 hash bits, a 16-entry list): the
+    build notices and redoes itself sorted by key; the sharded owner build reports the condition instead."""
+    import ctypes as C
+    import torch
+    from kmer_hasher_b200 import synth, _lib, dist as kdist
+    L = _lib.load()
+    seq = synth.generate(100_000, 5, repeat=0.2)
+    k = 32
+    try:
+        _lib.check(L.kmg_tune(b"hash_bits", 16))
+        _lib.check(L.kmg_tune(b"fix_cap", 16))
+        ix = kh.make_kmer_hash(seq, k)
+        assert L.kmg_index_order(ix._handle()) == 1          # fell back to the sorted build
+        want = oracle.build(seq, k).extract(2 | 8)
+        got = kh.kmer_pos(ix, 2 | 8)
+        assert np.array_equal(kh.kmer_keys(ix), want["keys"])
+        assert np.array_equal(got["count"], want["count"]) and np.array_equal(got["pos"].ravel(), want["pos"])
+        ix.free()
+        # owner-side build of received records: refused with KMG_ERR_RANGE (dist.py then takes the general path)
+        eng = kdist.CudaEngine(torch.device("cuda", 0))
+        own = eng.upload(seq)
+        pack = eng.shard_pack(own, k, 64, 0)
+        h, spl = eng.shard_open_packed(own, len(seq), 1, 0, k, 64, pack, 0)
+        counts = eng.shard_count(h, spl, 1)
+        cap = len(seq)
+        keys = torch.zeros(cap, dtype=torch.int64, device="cuda"); pos = torch.zeros(cap, dtype=torch.int32, device="cuda")
+        sl = kdist._Slot()
+        sl.keys, sl.pos = keys.data_ptr(), pos.data_ptr()
+        sl.peer_keys, sl.peer_pos = (C.c_void_p * 1)(keys.data_ptr()), (C.c_void_p * 1)(pos.data_ptr())
+        info = eng.shard_scatter(h, spl, 1, 0, sl, cap, counts, 0)
+        with pytest.raises(_lib.KmgError) as e:
+            eng.build_received(sl, cap, info, k, 0)
+        assert e.value.code == -3
+        eng.shard_close(h)
+    finally:
+        _lib.check(L.kmg_tune(b"hash_bits", 40))
+        _lib.check(L.kmg_tune(b"fix_cap", 0))
