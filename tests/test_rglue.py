@@ -118,3 +118,35 @@ def test_glue_guards_on_device(R, oracle, monkeypatch):
     assert R.stub.rstub_live_objects() == live           # nothing was allocated before the refusal
     assert R.kmer_pos(pb, 8)["count"].tolist() == [69989]
     R.stub.rstub_finalize(ptr); R.stub.rstub_finalize(pb)
+
+
+@pytest.mark.gpu
+def test_default_call_uses_the_grouped_build_and_do_sort_orders_by_key(R, oracle, test_fa):
+    """make.kmer.hash(seq, 32) as R calls it (do.sort = FALSE) builds grouped: the k-mers come in another order
+    than with do.sort = TRUE, and k-mer for k-mer the strings, counts and position lists are the reference's."""
+    k = 32
+    o = oracle.build(test_fa, k)
+    want = o.extract(1 | 2 | 8)
+    want_kmers = [bytes(want["kmer"][i * (k + 1):i * (k + 1) + k]).decode() for i in range(o.U)]
+    wpos = want["pos"].reshape(-1, 2)
+    starts = np.concatenate([[0], np.cumsum(want["count"])])
+    want_lists = {want_kmers[u]: wpos[starts[u]:starts[u + 1], 1].tolist() for u in range(o.U)}
+    srt = R.make_kmer_hash(test_fa, k, do_sort=True)
+    assert R.kmer_pos(srt, 1)["kmer"] == want_kmers                      # ascending key
+    grp = R.make_kmer_hash(test_fa, k)
+    got = R.kmer_pos(grp, 1 | 2 | 8)
+    assert got["kmer"] != want_kmers and sorted(got["kmer"]) == sorted(want_kmers)
+    gstarts = np.concatenate([[0], np.cumsum(got["count"])])
+    assert np.array_equal(got["pos"][:, 0], np.repeat(np.arange(1, o.U + 1), got["count"]))
+    for u, km in enumerate(got["kmer"]):
+        assert got["pos"][gstarts[u]:gstarts[u + 1], 1].tolist() == want_lists[km]
+    # probes do not depend on the order of the k-mers
+    import os
+    os.environ["KMERGPU_ALLOW_K32"] = "1"
+    try:
+        q = test_fa[3000:9000]
+        assert np.array_equal(R.seq_kmer_pos(grp, q, k).ravel(), o.query(q, k))
+    finally:
+        del os.environ["KMERGPU_ALLOW_K32"]
+    R.stub.rstub_finalize(srt); R.stub.rstub_finalize(grp)
+    assert R.stub.rstub_protect_depth() == 0
