@@ -34,7 +34,7 @@ def show_profile(tag):
 
 
 kh.profile(enable=True, reset=True)
-if what & {"c3", "c4", "ref"}:
+if what & {"c3", "c4", "ref", "ref32"}:
     t0 = time.time()
     seq = synth.config_c3(250_000_000)
     print(f"C3 sequence generated in {time.time() - t0:.1f}s; N bytes {(seq | 0x20 == ord('n')).sum()}")
@@ -84,6 +84,27 @@ if "c3" in what:
         print("C3 FULL-SIZE PARITY with the reference engine: keys, counts, (i,pos) identical")
         r.close()
     del pos, cnt
+    ix.free()
+
+if "ref32" in what:
+    # grouped build at scale against the reference engine: 100 Mbp, k=32 (thousands of colliding 40-bit groups)
+    from oracle import Reference
+    Lr = 100_000_000
+    sub = np.ascontiguousarray(seq[:Lr])
+    ix, ms = timed(lambda: kh.make_kmer_hash(torch.from_numpy(sub).cuda(), 32))
+    U, N, P = ix.sizes
+    assert L.kmg_index_order(ix._handle()) == 0
+    t0 = time.time()
+    r = Reference().build(sub, 32)
+    print(f"ref32: reference seq_to_hash 100 Mbp k=32: {r.build_seconds:.1f}s -> {r.N / r.build_seconds / 1e6:.2f} M k-mers/s; ours (grouped) {ms:.2f} ms")
+    e = r.extract(2 | 8)
+    assert (r.U, r.N, r.P) == (U, N, P)
+    got = kh.kmer_pos(ix, 2 | 8, canonical=True)
+    assert np.array_equal(kh.kmer_keys(ix, canonical=True), e["keys"])
+    assert np.array_equal(got["count"], e["count"])
+    assert np.array_equal(got["pos"].ravel(), e["pos"])
+    print(f"ref32 FULL-SIZE PARITY of the grouped build with the reference engine (after ordering by k-mer): keys, counts, (i,pos) identical; took {time.time() - t0:.0f}s")
+    r.close()
     ix.free()
 
 if "c4" in what:
