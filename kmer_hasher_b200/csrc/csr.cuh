@@ -16,19 +16,6 @@ struct IndexStats {
   uint32_t pad;
 };
 
-__global__ void sum_hist_kernel(const uint32_t *hist, IndexStats *st) {
-  uint32_t v = hist[threadIdx.x];               // launched with RADIX threads
-  __shared__ uint64_t part[RADIX / 32];
-  uint64_t s = warp_sum64(v);
-  if (lane_id() == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint64_t t = 0;
-    for (int i = 0; i < RADIX / 32; ++i) t += part[i];
-    st->n = t;
-  }
-}
-
 // ---- run-length pass: one head per distinct key, in order (single pass, chained scan) ----------------
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)

@@ -19,28 +19,7 @@ __device__ __forceinline__ uint64_t st_flag(uint64_t w, uint32_t epoch) {
   return (((w >> 56) & 63u) == (epoch & 63u)) ? (w >> 62) : 0;
 }
 
-// ---- per-bin look-back used by the sort/partition pass ----------------------------------------------
-// Called by thread `bin` (one bin per thread).  status is [tiles][RADIX].  Returns the number of
-// records of `bin` in all earlier tiles and publishes this tile's inclusive prefix.
-__device__ __forceinline__ uint64_t bin_lookback(uint64_t *status, uint32_t tile, uint32_t bin,
-                                                 uint32_t epoch, uint64_t count) {
-  uint64_t *mine = status + (size_t)tile * RADIX + bin;
-  if (tile == 0) {
-    st_relaxed_u64(mine, st_pack(ST_INCL, epoch, count));
-    return 0;
-  }
-  st_relaxed_u64(mine, st_pack(ST_AGG, epoch, count));
-  uint64_t excl = 0;
-  for (int64_t t = (int64_t)tile - 1; t >= 0; --t) {
-    const uint64_t *p = status + (size_t)t * RADIX + bin;
-    uint64_t w, f;
-    do { w = ld_relaxed_u64(p); f = st_flag(w, epoch); } while (f == 0);
-    excl += st_value(w);
-    if (f == ST_INCL) break;
-  }
-  st_relaxed_u64(mine, st_pack(ST_INCL, epoch, excl + count));
-  return excl;
-}
+// (the sort pass does its per-bin look-back inline, one bin per thread: sort.cuh)
 
 // ---- two-value scalar look-back used by the compaction kernels -------------------------------------
 // One 16-byte status per tile: (a, b) each carrying the flag in bits [63:62] (values < 2^62).
