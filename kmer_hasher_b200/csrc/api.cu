@@ -1488,7 +1488,10 @@ extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t ca
       } else if (rc == KMG_OK && cudaMemcpyAsync(pfinal, pa, (size_t)n * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
         rc = fail(KMG_ERR_CUDA, "copy failed");
       }
-      if (rc == KMG_OK) rc = finish_index(ix, sc, ka, pfinal, n, s, true);   // synchronises
+      if (rc == KMG_OK) {
+        rc = finish_index(ix, sc, ka, pfinal, n, s, true);   // synchronises
+        if (rc == KMG_OK) pfinal = nullptr;                  // the index owns it now (it is freed with the index)
+      }
       dfree(fixmem, s);
       TRY(rc);
       if (h_cnt[2]) return fail(KMG_ERR_RANGE, "more colliding groups than the task lists hold");
