@@ -260,7 +260,11 @@ struct Arena {
     if (!p) return;
     std::lock_guard<std::mutex> g(mu);
     auto it = live.find(p);
-    if (it == live.end()) { cudaFree(p); return; }
+    if (it == live.end()) {
+      for (auto &kv : cache) if (kv.second.p == p) return;   // already given back: a second put must not free a cached block
+      cudaFree(p);                                            // not from this arena (or from before a trim)
+      return;
+    }
     Block b = it->second;
     live.erase(it);
     b.last = s; b.synced = synced;
