@@ -9,16 +9,17 @@
 //   - records come either from HBM arrays or straight from the ASCII sequence (the 2-bit encoder
 //     of windows.cuh is fused into the first pass: keys are never written unsorted, and windows
 //     that contain an N are dropped by simply not being ranked);
-//   - ranks inside the tile come from warp-level matching of the 8 bin bits (ballots; a
-//     shared-memory bitmap variant is kept for comparison), so the pass is insensitive to skew
-//     (homopolymers, microsatellites);
+//   - the rank of a record inside the tile comes from one shared-memory atomic per record on its warp's
+//     bin counter (where the device applies colliding lanes in lane order, checked once; otherwise
+//     from a per-warp bitmap match), so the pass is insensitive to skew (homopolymers, microsatellites);
 //   - the tile is regrouped by bin in shared memory and written out in runs;
 //   - tile offsets chain through a decoupled look-back, one status word per (tile, bin).
-// Bin bases come from histograms that are complete before the pass starts: for a build from the
-// sequence all passes' histograms are taken up front by one kernel (hist_all_kernel); for a build
-// from records (sharded build) the histogram of the NEXT pass's digit is taken while the regrouped
-// keys stream out (HAS_NEXT).
-// The same kernel with OwnerBin (key-range owner instead of digit) is the multi-GPU partitioner.
+// Bin bases come from histograms that are complete before the pass starts: for a sorted build from the
+// sequence all passes' histograms are taken up front by one kernel (hist_all_kernel); for the grouped
+// build (digits of mix64(key)) and for builds from records (sharded build) the histogram of the NEXT
+// pass's digit is taken while the regrouped keys stream out (HAS_NEXT).
+// The same kernel with OwnerBin (key-range owner instead of digit) is the multi-GPU partitioner; with PEER
+// it writes every record straight into its owner's arrays over NVLink.
 #pragma once
 #include "common.cuh"
 #include "lookback.cuh"
