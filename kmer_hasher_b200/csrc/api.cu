@@ -357,10 +357,10 @@ using Cfg0 = PassCfg<256, 24, 2, 0, 8>;   // bitmap match: the default where the
 using Cfg1 = PassCfg<256, 24, 2, 1, 8>;   // ballot match
 using Cfg2 = PassCfg<256, 24, 2, 2, 8>;   // half ballots, half bitmaps
 using Cfg3 = PassCfg<256, 24, 2, 3, 4>;   // one atomic per record: the default where the lane-order check passes
-using Cfg4 = PassCfg<256, 24, 2, 3, 8>;
+using Cfg4 = PassCfg<256, 24, 2, 3, 2>;   // look-back width 2 (and 1 below): measured, slower
 using Cfg5 = PassCfg<256, 16, 3, 3, 8>;
 using Cfg6 = PassCfg<512, 12, 2, 3, 8>;
-using Cfg7 = PassCfg<256, 24, 2, 3, 16>;
+using Cfg7 = PassCfg<256, 24, 2, 3, 1>;
 constexpr int N_SORT_CFG = 8;
 // Bits of mix64(key) the grouped build sorts on (kmg_tune "hash_bits", a multiple of 8; tests lower it to
 // force collisions).  40 bits: ~N^2 / 2^41 colliding pairs (730 at 40 M k-mers, 1 M at 1.5 G).
