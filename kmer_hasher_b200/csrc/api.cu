@@ -1014,22 +1014,24 @@ extern "C" int kmg_query_begin_rc(const kmg_index *ix, const char *qseq, int64_t
   TRY(use_index(ix));
   cudaStream_t s = g_ctx.stream();
   DevSeq fwd, rc;
-  TRY(upload_seq(qseq, qlen, s, &fwd));
-  const size_t cap = 16 + (size_t)((qlen + 15) / 16) * 16 + 16;
-  int rcode = dalloc(&rc.buf, cap, s);
-  if (rcode != KMG_OK) { dfree(fwd.buf, s); return rcode; }
-  rc.base = rc.buf + 16; rc.len = qlen;
-  cudaMemsetAsync(rc.buf, 0, 16, s);
-  cudaMemsetAsync(rc.buf + cap - 32, 0, 32, s);
-  if (qlen > 0) {
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(qlen, 256), (int64_t)g_ctx.sms * 16);
-    LAUNCH("revcomp", s, revcomp_kernel<<<grid, 256, 0, s>>>(fwd.base, qlen, rc.base));
-    prof_bytes("revcomp", 2.0 * qlen);
-  }
-  SeqView sv;
-  sv.base = rc.base; sv.nstarts = qlen - k + 1 > 0 ? qlen - k + 1 : 0; sv.avail = qlen; sv.s0 = 0; sv.L = qlen; sv.k = k;
-  int rv = query_common(ix, true, sv, nullptr, nullptr, 0, st, M);
-  dfree(fwd.buf, s); dfree(rc.buf, s);
+  auto body = [&]() -> int {
+    TRY(upload_seq(qseq, qlen, s, &fwd));
+    const size_t cap = 16 + (size_t)((qlen + 15) / 16) * 16 + 16;
+    TRY(dalloc(&rc.buf, cap, s));
+    rc.base = rc.buf + 16; rc.len = qlen;
+    CU(cudaMemsetAsync(rc.buf, 0, 16, s));
+    CU(cudaMemsetAsync(rc.buf + cap - 32, 0, 32, s));
+    if (qlen > 0) {
+      const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(qlen, 256), (int64_t)g_ctx.sms * 16);
+      LAUNCH("revcomp", s, revcomp_kernel<<<grid, 256, 0, s>>>(fwd.base, qlen, rc.base));
+      prof_bytes("revcomp", 2.0 * qlen);
+    }
+    SeqView sv;
+    sv.base = rc.base; sv.nstarts = qlen - k + 1 > 0 ? qlen - k + 1 : 0; sv.avail = qlen; sv.s0 = 0; sv.L = qlen; sv.k = k;
+    return query_common(ix, true, sv, nullptr, nullptr, 0, st, M);
+  };
+  const int rv = body();
+  dfree(fwd.buf, s); dfree(rc.buf, s);               // on every path
   return rv;
 }
 
