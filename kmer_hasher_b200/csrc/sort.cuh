@@ -149,36 +149,45 @@ __device__ __forceinline__ uint32_t match_bin(uint32_t d, uint32_t active) {
   return peers;
 }
 
-// Do the lanes of one shared-memory atomic instruction that hit the same address get their old values in
-// ascending lane order?  (RANK 3 needs it.)  Several collision patterns, many repetitions; *bad counts failures.
+// Do the shared-memory atomics of one warp take effect in (instruction, lane) order, i.e. do colliding lanes of
+// one instruction get their old values in ascending lane order and do back-to-back instructions stay in issue
+// order?  (RANK 3 needs it.)  Several collision patterns, many repetitions, every SM; *bad counts failures.
 __global__ void lane_order_selftest_kernel(uint32_t *bad) {
+  // As in the pass: STEPS atomics per lane issued back to back (no result consumed in between) on the warp's
+  // own table; then lane 0 replays them in (step, lane) order and compares every returned value.
+  constexpr int STEPS = 8;
   __shared__ uint32_t tab[8][RADIX];
+  __shared__ uint32_t sim[8][RADIX];
+  __shared__ uint8_t dig[8][STEPS][32];
+  __shared__ uint32_t got[8][STEPS][32];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint32_t fails = 0;
-  for (int rep = 0; rep < 64; ++rep) {
-    for (int b = lane; b < RADIX; b += 32) tab[warp][b] = 0;
-    __syncwarp();
+  for (int rep = 0; rep < 32; ++rep) {
     for (int pattern = 0; pattern < 6; ++pattern) {
-      uint32_t d;
-      switch (pattern) {
-        case 0: d = 7; break;                                   // all lanes one address
-        case 1: d = lane & 1; break;                            // two addresses, interleaved
-        case 2: d = lane >> 3; break;                           // four runs
-        case 3: d = (lane * 2654435761u + rep * 40503u) >> 29; break;   // 8 addresses, scattered
-        case 4: d = (lane * 2246822519u + rep * 97u) & 255u; break;     // mostly distinct
-        default: d = (lane % 3 == 0) ? 200 : lane; break;
-      }
-      const uint32_t before = tab[warp][d];
+      for (int b = lane; b < RADIX; b += 32) { tab[warp][b] = 0; sim[warp][b] = 0; }
       __syncwarp();
-      const uint32_t got = atomicAdd(&tab[warp][d], 1u);
-      uint32_t peers = FULL_MASK_;
+      uint32_t d[STEPS], g[STEPS];
 #pragma unroll
-      for (int b = 0; b < RADIX_BITS; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const uint32_t bal = __ballot_sync(FULL_MASK_, bit);
-        peers &= bit ? bal : ~bal;
+      for (int j = 0; j < STEPS; ++j) {
+        switch (pattern) {
+          case 0: d[j] = 7; break;                                                  // all lanes, all steps one address
+          case 1: d[j] = (lane + j) & 1; break;                                     // two addresses, interleaved
+          case 2: d[j] = (lane >> 3) + (j & 1); break;                              // runs
+          case 3: d[j] = ((lane + 7 * j) * 2654435761u + rep * 40503u) >> 29; break;   // 8 addresses, scattered
+          case 4: d[j] = ((lane + 32 * j) * 2246822519u + rep * 97u) & 255u; break;    // mostly distinct
+          default: d[j] = (lane % 3 == 0) ? 200 : ((lane * 5 + j) & 255u); break;
+        }
       }
-      if (got != before + __popc(peers & lanemask_lt())) ++fails;
+#pragma unroll
+      for (int j = 0; j < STEPS; ++j) g[j] = atomicAdd(&tab[warp][d[j]], 1u);
+#pragma unroll
+      for (int j = 0; j < STEPS; ++j) { dig[warp][j][lane] = (uint8_t)d[j]; got[warp][j][lane] = g[j]; }
+      __syncwarp();
+      if (lane == 0) {
+        for (int j = 0; j < STEPS; ++j)
+          for (int l = 0; l < 32; ++l)
+            if (got[warp][j][l] != sim[warp][dig[warp][j][l]]++) ++fails;
+      }
       __syncwarp();
     }
   }
