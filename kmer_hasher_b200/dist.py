@@ -114,10 +114,13 @@ class CudaEngine:
         self._lib.check(self.L.kmg_build_received(slot.keys, slot.pos, capacity, info.data_ptr(), k, order, C.byref(h)))
         return KmerHash(h.value, k)
 
-    def query_received(self, index, slot, capacity, info, mixed=False):
+    def query_received(self, index, slot, capacity, info, mixed=False, count_only=False):
         st, M = C.c_void_p(), C.c_uint64()
         self._lib.check(self.L.kmg_query_received(index._handle(), slot.keys, slot.pos, capacity, info.data_ptr(),
                                                   int(mixed), C.byref(st), C.byref(M)))
+        if count_only:                                       # lookups + compaction + row count, rows not emitted
+            self.L.kmg_query_free(st)
+            return int(M.value)
         rows = torch.empty((M.value, 2), dtype=torch.int32, device=self.device)
         try:
             self._lib.check(self.L.kmg_query_emit(st, rows.data_ptr()))
@@ -444,17 +447,21 @@ def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerE
     return ix
 
 
-def sharded_query_p2p(index: ShardedIndex, own_query_bytes, Lq: int, k: int, xchg: PeerExchange, group=None) -> torch.Tensor:
-    """sharded_query with query (key, i) records scattered straight to the key's owner over NVLink."""
+def sharded_query_p2p(index: ShardedIndex, own_query_bytes, Lq: int, k: int, xchg: PeerExchange, group=None,
+                      count_only: bool = False):
+    """sharded_query with query (key, i) records scattered straight to the key's owner over NVLink.
+    count_only: return this owner's number of result rows instead of the rows (what kmg_query_begin gives)."""
     engine = index.engine
     world, rank = index.world, index.rank
-    s0, s1, _, _ = shard_bounds(Lq, world, rank, k)
     own = own_query_bytes if isinstance(own_query_bytes, torch.Tensor) else engine.upload(np.asarray(own_query_bytes, np.uint8))
-    shard, g0, g1 = exchange_halo(own, Lq, k, rank, world, group)
     spl = index.splitters_dev
     if spl is None:
         spl = torch.from_numpy(np.ascontiguousarray(index.splitters).view(np.int64)).to(engine.device)
-    sh = engine.shard_open(shard, g0, g1, Lq, s0, s1, k)
+    # halo through the same one-exchange pack as the build (its splitter sample is not needed: two keys, ignored)
+    pack = engine.shard_pack(own, k, 2, 1)
+    allpack = torch.empty(world * pack.numel(), dtype=torch.uint8, device=engine.device)
+    dist.all_gather_into_tensor(allpack, pack, group=group)
+    sh, _ = engine.shard_open_packed(own, Lq, world, rank, k, 2, allpack, 1)
     try:
         if index.mixed:                                      # owners hold ranges of the mixed key: route by it
             engine._lib.check(engine.L.kmg_shard_set_mixed(sh, 1))
@@ -464,7 +471,7 @@ def sharded_query_p2p(index: ShardedIndex, own_query_bytes, Lq: int, k: int, xch
         slot = xchg.next_slot()
         info = engine.shard_scatter(sh, spl, world, rank, slot, xchg.capacity, matrix, k - 1)   # 1-based END (src/kmer_pos.c:127)
         xchg.barrier()
-        return engine.query_received(index.local, slot, xchg.capacity, info, index.mixed)
+        return engine.query_received(index.local, slot, xchg.capacity, info, index.mixed, count_only)
     finally:
         engine.shard_close(sh)
 
@@ -569,6 +576,32 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
         step_e2e()
     ms_e2e = timed(step_e2e, steps)
 
+    # ---- probe leg (seq.kmer.pos, weak scaling): every rank holds 10 Mbp of the query; windows are routed to the
+    #      k-mer's owner by the same fused scatter, matched there (lookups + compaction + row count, as at N=1)
+    probe = None
+    if xchg is not None and not getattr(args, "no_probe", False):
+        Lq = min(10_000_000, L // 4)
+        q = synth.generate(Lq, 0xC4 + 31 * rank)
+        rng = np.random.default_rng(4 + rank)
+        src = np.asarray(own_pin)
+        for _ in range(Lq // 50_000):                          # sprinkle 2 kb copies of this rank's index sequence
+            a, b = int(rng.integers(0, L - 2000)), int(rng.integers(0, Lq - 2000))
+            q[b:b + 2000] = src[a:a + 2000]
+        q_dev = torch.from_numpy(q).to(dev)
+        ixq = build(own_dev)
+        rows = [0]
+
+        def probe_step():
+            rows[0] = sharded_query_p2p(ixq, q_dev, Lq * world, k, xchg, count_only=True)
+        for _ in range(3):
+            probe_step()
+        ms_q = timed(probe_step, max(3, steps // 3))
+        tot_rows = torch.tensor([rows[0]], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot_rows)
+        probe = {"metric": "kmers_queried_per_s", "value": world * (Lq - k + 1) / (ms_q * 1e-3), "unit": "k-mers/s",
+                 "query_bases": Lq * world, "rows": int(tot_rows.item()), "ms": ms_q,
+                 "what": "sharded seq.kmer.pos: halo, owner counts, fused scatter over NVLink, lookups + compaction + row count on the owners"}
+        ixq.free()
     sizes = torch.tensor([N, U], dtype=torch.int64, device=dev)
     all_sizes = [torch.empty_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
@@ -597,7 +630,7 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
             "e2e": {"value": ntot / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(L * world),
                     "d2h_bytes_per_step": int((8 * all_sizes[:, 0] + 4 * all_sizes[:, 1]).sum()), "ms_per_step": ms_e2e,
                     "what": "per rank: pinned host shard -> device, sharded build, kmer_pos(2|8) into pinned host arrays"},
-            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": None,
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": None, "probe": probe,
             "exchange": {"bytes_per_gpu_per_step": exchanged, "what": "12-byte records leaving each GPU over NVLink (estimate, uniform owners)",
                          "kernel": "scatter_peer", "ms_per_step": (prof.get("scatter_peer", (0, 0, 0))[0] / steps)},
             "kernels": kernels}
