@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 from conftest import ROOT
@@ -51,3 +53,20 @@ def test_product_does_not_touch_the_oracle():
                 text = open(os.path.join(dp, fn), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), (dp, fn)
                 assert "libkmer_oracle" not in text and "libkmer_ref" not in text and "kmer_oracle.c" not in text, (dp, fn)
+
+
+def test_canonical_renumbering_is_a_stable_regrouping():
+    """kmer_pos(..., canonical=True) re-orders a grouped index by key: rows keep their order inside a k-mer,
+    k-mers are renumbered by rank.  Pure host logic (numpy), checked here on a hand-made index."""
+    import kmer_hasher_b200 as kh
+    # three k-mers in index order with keys 50, 10, 30 -> canonical order: 10 (was i=2), 30 (i=3), 50 (i=1)
+    keys = np.array([50, 10, 30], np.uint64)
+    order = np.argsort(keys, kind="stable")
+    rank = np.empty(3, np.int64)
+    rank[order] = np.arange(3)
+    pos = np.array([[1, 7], [1, 9], [2, 3], [3, 1], [3, 4], [3, 8]], np.int32)
+    got = kh._renumber(pos, rank)
+    assert got.tolist() == [[1, 3], [2, 1], [2, 4], [2, 8], [3, 7], [3, 9]]
+    pairs = np.array([[1, 7, 9], [3, 1, 4], [3, 1, 8], [3, 4, 8]], np.int32)
+    assert kh._renumber(pairs, rank).tolist() == [[2, 1, 4], [2, 1, 8], [2, 4, 8], [3, 7, 9]]
+    assert kh._renumber(np.empty((0, 2), np.int32), rank).shape == (0, 2)
