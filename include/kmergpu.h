@@ -38,7 +38,9 @@ typedef enum {
   KMG_ERR_RANGE = -3,  /* a size does not fit the reference's `int` coordinates/extents  */
   KMG_ERR_CUDA = -4,   /* CUDA runtime error; message carries the CUDA error string       */
   KMG_ERR_NOMEM = -5,  /* host or device allocation failed                                */
-  KMG_ERR_NODEV = -6   /* no usable sm_100 device                                         */
+  KMG_ERR_NODEV = -6,  /* no usable sm_100 device                                         */
+  KMG_ERR_UNSTABLE = -7 /* (builds from records) the always-on check found a position list not ascending: the
+                          one-atomic sort variant's hardware assumption failed; it is now disabled: rebuild */
 } kmg_status;
 
 typedef struct kmg_index kmg_index; /* replaces khash_ptr            (src/kmer_pos.h:43-48)  */
@@ -101,6 +103,10 @@ int kmg_positions(const kmg_index *idx, int32_t *out /* 2N */);
  * kmg_pairs_chunk writes rows [first, first+n) so > 2^31-row results can be streamed. */
 int kmg_pairs(const kmg_index *idx, int32_t *out /* 3P */);
 int kmg_pairs_chunk(const kmg_index *idx, uint64_t first, uint64_t n, int32_t *out /* 3n */);
+/* The same two with the k-mer number offset by i_base: the owners of a sharded index each write their slice of ONE
+ * caller matrix with global k-mer numbers (i_base = distinct k-mers of the owners before; SURVEY.md 8e "Extraction"). */
+int kmg_positions_base(const kmg_index *idx, uint64_t i_base, int32_t *out);
+int kmg_pairs_chunk_base(const kmg_index *idx, uint64_t i_base, uint64_t first, uint64_t n, int32_t *out);
 
 /* ---- seq.kmer.pos --------------------------------------------------------------------------
  * kmg_query_begin + kmg_query_emit replace seq_kmer_positions  src/kmer_pos.c:110-136
@@ -213,7 +219,13 @@ int kmg_profile_get(int i, const char **name, double *total_ms, uint64_t *launch
                     double *algo_bytes);
 uint64_t kmg_launch_count(void);         /* kernels launched by this library since load         */
 int kmg_selftest_lane_order(uint32_t *failures); /* precondition of the one-atomic rank variant (sort.cuh) */
-int kmg_tune(const char *key, int value); /* tuning runs only: "sort_cfg" selects a pass variant  */
+int kmg_tune(const char *key, int value); /* tests and tuning runs: "sort_cfg" (rank variant: -1 auto, 0 bitmap, 3 one
+                                            atomic, 4 unstable on purpose), "sort_shape", "hash_bits" (0 = from the record
+                                            count), "hash_rb", "fix_cap", "reset_rank", "sort_dbg", "sort_trace" */
+int64_t kmg_tune_get(const char *key, int64_t arg); /* "rank_variant" in use on this device, "unstable_rebuilds" so far,
+                                            "hash_bits" / "hash_rb" the grouped build picks for `arg` records */
+int kmg_trim(void);                      /* return the library's cached (free) device blocks of this device to the driver */
+uint64_t kmg_cached_bytes(void);         /* bytes held in that cache (KMERGPU_CACHE_MB caps it; default a quarter of the device) */
 
 #ifdef __cplusplus
 }

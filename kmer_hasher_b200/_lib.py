@@ -73,6 +73,11 @@ SIGNATURES = {
     "kmg_launch_count": (C.c_uint64, []),
     "kmg_selftest_lane_order": (C.c_int, [C.POINTER(C.c_uint32)]),
     "kmg_tune": (C.c_int, [C.c_char_p, C.c_int]),
+    "kmg_tune_get": (C.c_int64, [C.c_char_p, C.c_int64]),
+    "kmg_trim": (C.c_int, []),
+    "kmg_cached_bytes": (C.c_uint64, []),
+    "kmg_positions_base": (C.c_int, [vp, C.c_uint64, vp]),
+    "kmg_pairs_chunk_base": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
 }
 
 _lib = None

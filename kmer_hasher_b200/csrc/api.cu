@@ -6,6 +6,7 @@
 #include <cstring>
 #include <ctime>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -81,8 +82,8 @@ static int ctx_init() {
   CU(cudaSetDevice(c.device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, c.device));
-  if (prop.major < 10)
-    return fail(KMG_ERR_NODEV, "device %d is sm_%d%d; libkmergpu is built for sm_100a only", c.device, prop.major, prop.minor);
+  if (prop.major != 10 || prop.minor != 0)     // the library carries sm_100a SASS only (no PTX): other parts cannot run it
+    return fail(KMG_ERR_NODEV, "device %d is sm_%d%d; libkmergpu is built for sm_100a (B200) only", c.device, prop.major, prop.minor);
   c.sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
@@ -268,9 +269,12 @@ struct Arena {
     Block b = it->second;
     live.erase(it);
     b.last = s; b.synced = synced;
-    if (limit == 0) {
+    if (limit == 0) {                                   // KMERGPU_CACHE_MB, else a quarter of the device
+      const char *e = getenv("KMERGPU_CACHE_MB");
       size_t fr = 0, tot = 0;
-      limit = cudaMemGetInfo(&fr, &tot) == cudaSuccess ? tot / 2 : (size_t(32) << 30);
+      if (e && atoll(e) >= 0) limit = (size_t)atoll(e) << 20;
+      else limit = cudaMemGetInfo(&fr, &tot) == cudaSuccess ? tot / 4 : (size_t(32) << 30);
+      if (limit == 0) limit = 1;
     }
     if (cached_bytes + b.cap > limit) trim_locked();
     cache.emplace(b.cap, b);
@@ -278,6 +282,23 @@ struct Arena {
   }
 };
 static Arena g_arena[64];
+
+// Give the cached device blocks of this thread's device back to the driver (live indexes are untouched).  An R
+// session calls it (or sets KMERGPU_CACHE_MB=0) when it wants the memory of freed indexes returned at once.
+extern "C" int kmg_trim(void) {
+  TRY(ctx_init());
+  cudaStreamSynchronize(g_ctx.stream());
+  Arena &a = g_arena[g_ctx.device & 63];
+  std::lock_guard<std::mutex> g(a.mu);
+  for (auto &kv : a.cache) if (!kv.second.synced && kv.second.last && kv.second.last != g_ctx.stream()) cudaStreamSynchronize(kv.second.last);
+  a.trim_locked();
+  return KMG_OK;
+}
+extern "C" uint64_t kmg_cached_bytes(void) {
+  Arena &a = g_arena[g_ctx.device & 63];
+  std::lock_guard<std::mutex> g(a.mu);
+  return a.cached_bytes;
+}
 
 template <typename T>
 static int dalloc(T **p, size_t count, cudaStream_t s) {
@@ -326,6 +347,8 @@ struct kmg_index {
   uint64_t U = 0, N = 0, P = 0, multi = 0;
   uint32_t maxc = 0;
   bool grouped = false;         // k-mers in the order of the grouped build instead of ascending key
+  int hbits = 0;                // grouped: the records were sorted on the low hbits bits of mix64(key), then by mix64(key)
+  bool unstable = false;        // a position list was found not ascending (never true of an index handed out)
   uint64_t *ukeys = nullptr;    // [U]
   uint32_t *ustart = nullptr;   // [U+1]
   uint32_t *pos = nullptr;      // [N]
@@ -351,41 +374,67 @@ constexpr int COMPACT_ITEMS = 8, COMPACT_TILE = PROBE_THREADS * COMPACT_ITEMS;
 constexpr int EMIT_THREADS = 256, EMIT_TILE = EMIT_THREADS * 8;
 constexpr int PIDX_THREADS = 256, PIDX_ITEMS = 8, PIDX_TILE = PIDX_THREADS * PIDX_ITEMS;
 
-// Pass configurations selectable at run time (KMG_SORT_CFG=<index>, for tuning runs):
-// <threads, records per thread, CTAs per SM, rank variant (1 ballots, 0 bitmap), look-back width>.
-using Cfg0 = PassCfg<256, 24, 2, 0, 8>;   // bitmap match: the default where the lane-order check fails
-using Cfg1 = PassCfg<256, 24, 2, 1, 8>;   // ballot match
-using Cfg2 = PassCfg<256, 24, 2, 2, 8>;   // half ballots, half bitmaps
-using Cfg3 = PassCfg<256, 24, 2, 3, 4>;   // one atomic per record: the default where the lane-order check passes
-using Cfg4 = PassCfg<256, 24, 2, 3, 2>;   // look-back width 2 (and 1 below): measured, slower
-using Cfg5 = PassCfg<256, 16, 3, 3, 8>;
-using Cfg6 = PassCfg<512, 12, 2, 3, 8>;
-using Cfg7 = PassCfg<256, 24, 2, 3, 1>;
-constexpr int N_SORT_CFG = 8;
-// Bits of mix64(key) the grouped build sorts on (kmg_tune "hash_bits", a multiple of 8; tests lower it to
-// force collisions).  40 bits: ~N^2 / 2^41 colliding pairs (730 at 40 M k-mers, 1 M at 1.5 G).
-static int g_hash_bits = 40;
-static int g_fix_cap = 0;      // kmg_tune "fix_cap": capacity of the short-group task list (0 = max(2^20, N/8)); tests shrink it
-static int g_sort_cfg = -1;
+// ---- the sort pass: shape x rank variant x digit width ------------------------------------------------------
+// Shapes <threads, records per thread, CTAs per SM> (kmg_tune "sort_shape", tuning runs): 0 = 256 x 24 x 2 (default),
+// 1 = 256 x 28 x 2, 2 = 256 x 20 x 3 (8-bit digits only: three tiles must fit an SM's shared memory).
+// Rank variant: 3 = one shared-memory atomic per record (needs lane-ordered atomics: checked per device, and every
+// finished index is checked for ascending position lists), 0 = bitmap match (assumes nothing).
+// Digit width: chosen per build (SortPlan).
+static int g_sort_shape = 0;
+static int g_rank_override = -1;               // kmg_tune "sort_cfg": -1 auto, 0 bitmap, 3 one-atomic
+static std::atomic<int> g_rank_dev[64];        // per device: 0 unknown, 1 bitmap, 2 one-atomic
+static std::atomic<uint64_t> g_unstable_rebuilds{0};
 static uint32_t g_sort_dbg = 0;
 static int lane_order_failures(uint32_t *failures);
 static bool log_on();
-// The pass variant: KMG_SORT_CFG / kmg_tune if given; else the one-atomic variant (3) when this device applies
-// colliding shared-memory atomics of one instruction in lane order (checked once), the bitmap variant (0) if not.
-static int sort_cfg() {
-  if (g_sort_cfg < 0) {
-    const char *e = getenv("KMG_SORT_CFG");
-    if (e) {
-      const int v = atoi(e);
-      g_sort_cfg = (v >= 0 && v < N_SORT_CFG) ? v : 0;
-    } else {
+
+static int rank_variant() {
+  if (g_rank_override >= 0) return g_rank_override;
+  const int dev = g_ctx.device & 63;
+  int v = g_rank_dev[dev].load(std::memory_order_acquire);
+  if (v == 0) {
+    const char *e = getenv("KMG_SORT_RANK");
+    if (e) v = atoi(e) == 3 ? 2 : 1;
+    else {
       uint32_t f = 1;
-      g_sort_cfg = (lane_order_failures(&f) == KMG_OK && f == 0) ? 3 : 0;
-      if (log_on()) fprintf(stderr, "[kmergpu] lane-order self-test: %u failures -> sort pass variant %d\n", f, g_sort_cfg);
+      v = (lane_order_failures(&f) == KMG_OK && f == 0) ? 2 : 1;
+      if (log_on()) fprintf(stderr, "[kmergpu] device %d lane-order self-test: %u failures -> rank variant %d\n", dev, f, v == 2 ? 3 : 0);
     }
+    int expect = 0;
+    g_rank_dev[dev].compare_exchange_strong(expect, v, std::memory_order_acq_rel);   // a concurrent thread found the same answer
+    v = g_rank_dev[dev].load(std::memory_order_acquire);
   }
-  return g_sort_cfg;
+  return v == 2 ? 3 : 0;
 }
+// An index built with the one-atomic variant had a descending position pair: never use that variant on this device again.
+static void demote_rank_variant() {
+  g_rank_dev[g_ctx.device & 63].store(1, std::memory_order_release);
+  g_unstable_rebuilds.fetch_add(1);
+  if (g_rank_override >= 3) g_rank_override = -1;
+  if (log_on()) fprintf(stderr, "[kmergpu] device %d: position lists not ascending after a one-atomic sort pass; switching to the bitmap variant\n", g_ctx.device);
+}
+
+// Digits of one build: `passes` passes of `rb` bits each.
+struct SortPlan { int rb, passes; int bits() const { return rb * passes; } };
+// Bits of mix64(key) the grouped build sorts on (kmg_tune "hash_bits": 0 = chosen from the record count, else a multiple
+// of 8 or 9; tests lower it to force collisions).  With b bits ~N^2 / 2^(b+1) pairs of distinct k-mers collide and are
+// fixed up afterwards; b >= log2(N) + 5 keeps that below N/64: 32 bits (4 x 8) up to 2^27 records, 36 bits (4 x 9) beyond.
+static int g_hash_bits = 0;
+static int g_hash_rb = 0;      // kmg_tune "hash_rb": force the digit width (tuning runs)
+static int g_fix_cap = 0;      // kmg_tune "fix_cap": capacity of the short-group task list (0 = max(2^20, N/8)); tests shrink it
+static SortPlan grouped_plan(int64_t n_upper) {
+  if (g_hash_bits > 0) {
+    const int rb = g_hash_rb > 0 && g_hash_bits % g_hash_rb == 0 ? g_hash_rb : (g_hash_bits % 8 == 0 ? 8 : 9);
+    return SortPlan{rb, g_hash_bits / rb};
+  }
+  if (g_hash_rb > 0) return SortPlan{g_hash_rb, n_upper <= (int64_t(1) << 27) ? (32 + g_hash_rb - 1) / g_hash_rb : (36 + g_hash_rb - 1) / g_hash_rb};
+  return n_upper <= (int64_t(1) << 27) ? SortPlan{8, 4} : SortPlan{9, 4};
+}
+// is the grouped build used for this k, requested order and size?  (it has to save at least two 8-bit passes)
+static bool grouped_for(int k, int order, int64_t n_upper) {
+  return order == KMG_ORDER_GROUPED && num_passes(k) > grouped_plan(n_upper).passes + 1;
+}
+
 static unsigned long long *g_trace = nullptr;
 static int g_trace_tiles = 0;
 extern "C" int kmg_trace_read(unsigned long long *host, int tiles) {
@@ -393,16 +442,30 @@ extern "C" int kmg_trace_read(unsigned long long *host, int tiles) {
   return cudaMemcpy(host, g_trace, (size_t)tiles * 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -4;
 }
 extern "C" int kmg_tune(const char *key, int value) {
-  if (key && !strcmp(key, "sort_cfg")) {
-    if (value < 0 || value >= N_SORT_CFG) return fail(KMG_ERR_ARG, "sort_cfg out of range");
-    g_sort_cfg = value;
+  if (key && !strcmp(key, "sort_cfg")) {              // rank variant: -1 auto, 0 bitmap, 3 one atomic per record
+    if (value != -1 && value != 0 && value != 3 && value != 4) return fail(KMG_ERR_ARG, "sort_cfg must be -1 (auto), 0 (bitmap), 3 (one atomic) or 4 (tests: unstable on purpose)");
+    g_rank_override = value;
+    return KMG_OK;
+  }
+  if (key && !strcmp(key, "sort_shape")) {
+    if (value < 0 || value > 2) return fail(KMG_ERR_ARG, "sort_shape out of range");
+    g_sort_shape = value;
     return KMG_OK;
   }
   if (key && !strcmp(key, "sort_dbg")) { g_sort_dbg = (uint32_t)value; return KMG_OK; }
   if (key && !strcmp(key, "fix_cap")) { g_fix_cap = value > 0 ? value : 0; return KMG_OK; }
   if (key && !strcmp(key, "hash_bits")) {
-    if (value < 8 || value > 56 || value % RADIX_BITS) return fail(KMG_ERR_ARG, "hash_bits must be a multiple of 8 in [8,56]");
+    if (value != 0 && (value < 8 || value > 56 || (value % 8 && value % 9 && value % 10))) return fail(KMG_ERR_ARG, "hash_bits must be 0 (auto) or a multiple of 8, 9 or 10 in [8,56]");
     g_hash_bits = value;
+    return KMG_OK;
+  }
+  if (key && !strcmp(key, "hash_rb")) {
+    if (value != 0 && (value < 8 || value > 10)) return fail(KMG_ERR_ARG, "hash_rb must be 0, 8, 9 or 10");
+    g_hash_rb = value;
+    return KMG_OK;
+  }
+  if (key && !strcmp(key, "reset_rank")) {            // tests: forget what this device's self-test / index checks said
+    for (auto &v : g_rank_dev) v.store(0);
     return KMG_OK;
   }
   if (key && !strcmp(key, "sort_trace")) {          // value = tiles to trace (0 = off); buffer read by kmg_trace_read
@@ -412,6 +475,14 @@ extern "C" int kmg_tune(const char *key, int value) {
     return KMG_OK;
   }
   return fail(KMG_ERR_ARG, "unknown tuning key");
+}
+// what the library decided: "rank_variant" (0/3 for the current device), "unstable_rebuilds", "hash_bits" for n records
+extern "C" int64_t kmg_tune_get(const char *key, int64_t arg) {
+  if (key && !strcmp(key, "rank_variant")) return ctx_init() == KMG_OK ? rank_variant() : -1;
+  if (key && !strcmp(key, "unstable_rebuilds")) return (int64_t)g_unstable_rebuilds.load();
+  if (key && !strcmp(key, "hash_bits")) return grouped_plan(arg).bits();
+  if (key && !strcmp(key, "hash_rb")) return grouped_plan(arg).rb;
+  return -1;
 }
 // RANK 3's precondition, checked on the current device: failures = 0 means the lanes of one shared-memory
 // atomic instruction that collide on an address are applied in ascending lane order.
@@ -431,7 +502,7 @@ extern "C" int kmg_selftest_lane_order(uint32_t *failures) {
   if (!failures) return fail(KMG_ERR_ARG, "failures is NULL");
   return lane_order_failures(failures);
 }
-constexpr int SORT_TILE_MIN = 2048;   // status/scratch sizing: smallest tile of any configuration
+constexpr int SORT_TILE_MIN = 5120;   // status sizing: smallest tile of any shape
 
 template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false>
 static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
@@ -443,40 +514,71 @@ static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P,
   LAUNCH(name, s, kern<<<(unsigned)tiles, Cfg::THREADS, sizeof(S), s>>>(P));
   return KMG_OK;
 }
+// rb: digit width of the pass (bins = 2^rb); P.bin / P.next must carry the matching mask
 template <bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
-static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
-  switch (sort_cfg()) {
-#define KMG_CASE(i) case i: return launch_pass_cfg<Cfg##i, FROM_SEQ, BinFn, NextFn, HAS_NEXT>(name, P, n_upper, s);
-    KMG_CASE(0) KMG_CASE(1) KMG_CASE(2) KMG_CASE(3) KMG_CASE(4) KMG_CASE(5) KMG_CASE(6) KMG_CASE(7)
-#undef KMG_CASE
+static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s, int rb = RADIX_BITS) {
+  const int rank = rank_variant();
+  const int shape = (rb == 8) ? g_sort_shape : (g_sort_shape == 2 ? 0 : g_sort_shape);
+#define KMG_GO(T, I, M, RK, RB) return launch_pass_cfg<PassCfg<T, I, M, RK, (RK >= 3 ? 4 : 8), RB>, FROM_SEQ, BinFn, NextFn, HAS_NEXT>(name, P, n_upper, s)
+#define KMG_SHAPES(RK, RB)                         \
+  do {                                             \
+    if (shape == 1) KMG_GO(256, 28, 2, RK, RB);    \
+    KMG_GO(256, 24, 2, RK, RB);                    \
+  } while (0)
+  if (rb == 8) {
+    if (rank == 4) KMG_GO(256, 24, 2, 4, 8);       // tests: deliberately unstable
+    if (shape == 2) { if (rank == 3) KMG_GO(256, 20, 3, 3, 8); else KMG_GO(256, 20, 3, 0, 8); }
+    if (rank == 3) KMG_SHAPES(3, 8); else KMG_SHAPES(0, 8);
+  } else if (rb == 9) {
+    if (rank == 4) KMG_GO(256, 24, 2, 4, 9);
+    if (rank == 3) KMG_SHAPES(3, 9); else KMG_SHAPES(0, 9);
+  } else if (rb == 10) {
+    if (rank == 3) KMG_GO(256, 24, 2, 3, 10); else KMG_GO(256, 24, 2, 0, 10);
   }
+#undef KMG_SHAPES
+#undef KMG_GO
   return fail(KMG_ERR_ARG, "bad sort configuration");
 }
 
 // Scratch shared by the sort passes of one build.
 struct SortScratch {
-  uint32_t *small = nullptr;     // hist[(MAX_PASSES+1)][RADIX] | gbase[(MAX_PASSES+1)][RADIX] | common[RADIX] | tickets[16] | IndexStats
-  uint64_t *status = nullptr;    // [tiles][RADIX]
-  size_t small_words = 0;
-  static constexpr size_t H = (size_t)(MAX_PASSES + 1) * RADIX;
-  uint32_t *hist(int r) const { return small + (size_t)r * RADIX; }
-  uint32_t *gbase(int r) const { return small + H + (size_t)r * RADIX; }
+  uint32_t *small = nullptr;     // hist[(MAX_PASSES+1)][MAX_NB] | gbase[(MAX_PASSES+1)][MAX_NB] | common[RADIX] | tickets[16] | IndexStats
+  uint64_t *status = nullptr;    // [tiles][bins]
+  size_t small_words = 0, status_words = 0;
+  static constexpr size_t H = (size_t)(MAX_PASSES + 1) * MAX_NB;
+  uint32_t *hist(int r) const { return small + (size_t)r * MAX_NB; }
+  uint32_t *gbase(int r) const { return small + H + (size_t)r * MAX_NB; }
   uint32_t *common() const { return small + 2 * H; }
   uint32_t *ticket(int i) const { return small + 2 * H + RADIX + i; }
   IndexStats *stats() const { return reinterpret_cast<IndexStats *>(small + 2 * H + RADIX + 16); }
 };
-static int scratch_alloc(SortScratch &sc, int64_t n_upper, cudaStream_t s) {
+static int scratch_clear(SortScratch &sc, cudaStream_t s) {
+  CU(cudaMemsetAsync(sc.small, 0, sc.small_words * 4, s));
+  CU(cudaMemsetAsync(sc.status, 0, sc.status_words * sizeof(uint64_t), s));
+  return KMG_OK;
+}
+static int scratch_alloc(SortScratch &sc, int64_t n_upper, cudaStream_t s, int rb = RADIX_BITS) {
   sc.small_words = 2 * SortScratch::H + RADIX + 16 + sizeof(IndexStats) / 4;
   TRY(dalloc(&sc.small, sc.small_words, s));
-  CU(cudaMemsetAsync(sc.small, 0, sc.small_words * 4, s));
   const size_t tiles = (size_t)ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, SORT_TILE_MIN);
-  TRY(dalloc(&sc.status, tiles * RADIX, s));
-  CU(cudaMemsetAsync(sc.status, 0, tiles * RADIX * sizeof(uint64_t), s));
-  return KMG_OK;
+  sc.status_words = tiles << rb;
+  TRY(dalloc(&sc.status, sc.status_words, s));
+  return scratch_clear(sc, s);
 }
 static void scratch_free(SortScratch &sc, cudaStream_t s) { dfree(sc.small, s); dfree(sc.status, s); }
 
-// Sorted records -> CSR; reads the stats back (one synchronisation) and fills the handle.
+template <class... A>
+static int launch_scan_hist(int rb, cudaStream_t s, A... args) {
+  if (rb == 8) LAUNCH("scan_hist", s, scan_hist_kernel<256><<<1, 256, 0, s>>>(args...));
+  else if (rb == 9) LAUNCH("scan_hist", s, scan_hist_kernel<512><<<1, 512, 0, s>>>(args...));
+  else if (rb == 10) LAUNCH("scan_hist", s, scan_hist_kernel<1024><<<1, 1024, 0, s>>>(args...));
+  else return fail(KMG_ERR_ARG, "bad digit width");
+  return KMG_OK;
+}
+
+// Sorted records -> CSR; reads the stats back (one synchronisation) and fills the handle.  The same sweep checks that
+// positions ascend inside every k-mer (IndexStats::unstable): what a stable sort guarantees and the reference's
+// insertion order gives; the caller rebuilds with the order-independent rank variant if it ever fails.
 static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, uint32_t *pos_sorted,
                         int64_t n_upper, cudaStream_t s, bool hashed = false) {
   IndexStats *st = sc.stats();
@@ -489,13 +591,13 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
   TRY(dalloc(&status2, (size_t)tiles, s));
   CU(cudaMemsetAsync(status2, 0, (size_t)tiles * sizeof(Pair64), s));
   LAUNCH("rle", s, rle_kernel<RLE_THREADS, RLE_ITEMS><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(
-                       keys_sorted, st, ukeys, ustart, status2, sc.ticket(MAX_PASSES + 1), hashed));
+                       keys_sorted, pos_sorted, st, ukeys, ustart, status2, sc.ticket(MAX_PASSES + 1), hashed));
   const unsigned sgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, 256 * 16), g_ctx.sms * 8);
   LAUNCH("stats", s, stats_kernel<256><<<sgrid, 256, 0, s>>>(ustart, st));
   IndexStats h;
   CU(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  ix->N = h.n; ix->U = h.U; ix->P = h.P; ix->multi = h.multi; ix->maxc = h.maxc;
+  ix->N = h.n; ix->U = h.U; ix->P = h.P; ix->multi = h.multi; ix->maxc = h.maxc; ix->unstable = h.unstable != 0;
   dfree(status2, s);
   // keep exact-size arrays when the over-allocation is large
   if (h.U * 2 < (uint64_t)n_upper) {
@@ -509,33 +611,34 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
   }
   ix->ukeys = ukeys; ix->ustart = ustart; ix->pos = pos_sorted;
   const double N = (double)h.n, U = (double)h.U;
-  prof_bytes("rle", 8 * N + 12 * U);
+  prof_bytes("rle", 12 * N + 12 * U);
   prof_bytes("stats", 4 * U);
   return KMG_OK;
 }
 
-// LSD passes first_pass..R-1 over record buffers.  has_next: only hist/gbase of first_pass exist, each
-// pass takes the next one's histogram as it writes (builds from records); otherwise every pass's
-// gbase is already there (builds from the sequence, hist_all_kernel).
+// LSD passes first_pass..plan.passes-1 over record buffers, digits of plan.rb bits.  has_next: only hist/gbase of
+// first_pass exist, each pass takes the next one's histogram as it writes (grouped builds, builds from records);
+// otherwise every pass's gbase is already there (sorted builds from the sequence, hist_all_kernel).
 // final_pos (optional): the last pass writes its positions there instead of into the ping-pong buffer
 // (the array the index keeps), so `pa` is meaningless afterwards.
-static int sort_tail(SortScratch &sc, int k, int first_pass, bool has_next, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
-                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr, int passes = 0) {
-  const int R = passes > 0 ? passes : num_passes(k);
+static int sort_tail(SortScratch &sc, SortPlan plan, int first_pass, bool has_next, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
+                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr) {
+  const int R = plan.passes, rb = plan.rb;
+  const uint32_t mask = (1u << rb) - 1;
   for (int r = first_pass; r < R; ++r) {
     PassParams<DigitBin, DigitBin> P{};
     P.keys_in = ka; P.pos_in = pa; P.keys_out = kb; P.pos_out = (final_pos && r == R - 1) ? final_pos : pb;
     P.gbase = sc.gbase(r); P.hist_next = sc.hist(r + 1);
     P.status = sc.status; P.ticket = sc.ticket(r); P.epoch = (uint32_t)(r + 1);
     P.n_records = &sc.stats()->n;
-    P.bin = DigitBin{r * RADIX_BITS}; P.next = DigitBin{(r + 1) * RADIX_BITS};
+    P.bin = DigitBin{r * rb, mask}; P.next = DigitBin{(r + 1) * rb, mask};
     P.dbg = g_sort_dbg;
-    P.trace = (r == 2 && g_trace && ceil_div<int64_t>(n_upper, 2048) <= g_trace_tiles) ? g_trace : nullptr;   // trace the third pass
+    P.trace = (r == 2 && g_trace && ceil_div<int64_t>(n_upper, SORT_TILE_MIN) <= g_trace_tiles) ? g_trace : nullptr;   // trace the third pass
     if (has_next && r + 1 < R) {
-      TRY((launch_pass<false, DigitBin, DigitBin, true>("sort_pass_hist", P, n_upper, s)));
-      LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(r + 1), sc.gbase(r + 1), nullptr));
+      TRY((launch_pass<false, DigitBin, DigitBin, true>("sort_pass_hist", P, n_upper, s, rb)));
+      TRY(launch_scan_hist(rb, s, sc.hist(r + 1), sc.gbase(r + 1), (uint64_t *)nullptr));
     } else {
-      TRY((launch_pass<false, DigitBin, DigitBin, false>("sort_pass", P, n_upper, s)));
+      TRY((launch_pass<false, DigitBin, DigitBin, false>("sort_pass", P, n_upper, s, rb)));
     }
     std::swap(ka, kb);
     std::swap(pa, pb);
@@ -543,13 +646,9 @@ static int sort_tail(SortScratch &sc, int k, int first_pass, bool has_next, uint
   return KMG_OK;
 }
 
-
-// is the grouped build used for this k and requested order?  (it has to save at least two passes)
-static bool grouped_for(int k, int order) { return order == KMG_ORDER_GROUPED && num_passes(k) > g_hash_bits / RADIX_BITS + 1; }
-
 // Collisions of the low bits of the mix: partition those groups by the whole mix (sk, sp: scratch of the
 // same size).  Returns the detect counters through h_cnt after the caller's next synchronisation.
-static int fix_groups(SortScratch &sc, uint64_t *keys, uint32_t *pos, uint64_t *sk, uint32_t *sp, int64_t n_upper, cudaStream_t s,
+static int fix_groups(SortScratch &sc, int bits, uint64_t *keys, uint32_t *pos, uint64_t *sk, uint32_t *sp, int64_t n_upper, cudaStream_t s,
                       uint32_t *h_cnt /* [4], pinned or stack read after a sync */, uint32_t **fixmem_out) {
   FixLists fl{};
   uint32_t *fixmem = nullptr;
@@ -563,7 +662,7 @@ static int fix_groups(SortScratch &sc, uint64_t *keys, uint32_t *pos, uint64_t *
   fl.small_tasks = reinterpret_cast<uint2 *>(fixmem + 4 + CLAIM_SLOTS);
   fl.big_tasks = fl.small_tasks + fl.small_cap;
   const unsigned dgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper, 256 * 8), (int64_t)g_ctx.sms * 16);
-  LAUNCH("group_detect", s, group_detect_kernel<<<dgrid, 256, 0, s>>>(keys, sc.stats(), g_hash_bits, fl));
+  LAUNCH("group_detect", s, group_detect_kernel<<<dgrid, 256, 0, s>>>(keys, sc.stats(), bits, fl));
   LAUNCH("small_fix", s, small_fix_kernel<<<g_ctx.sms * 4, 128, 0, s>>>(keys, pos, fl));
   LAUNCH("big_fix", s, big_fix_kernel<256><<<g_ctx.sms, 256, 0, s>>>(keys, pos, sk, sp, fl));
   CU(cudaMemcpyAsync(h_cnt, fl.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -571,34 +670,37 @@ static int fix_groups(SortScratch &sc, uint64_t *keys, uint32_t *pos, uint64_t *
 }
 
 // Grouped build: equal k-mers contiguous, k-mers in the order of (low bits of mix64(key), mix64(key)).
-static int build_grouped(const SeqView &sv, int k, kmg_index *ix, SortScratch &sc, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
+static int build_grouped(const SeqView &sv, SortPlan plan, kmg_index *ix, SortScratch &sc, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
                          uint32_t *&pb, int64_t n_upper, cudaStream_t s, bool *overflow) {
-  const int bits = g_hash_bits, R = bits / RADIX_BITS;
+  const int R = plan.passes, rb = plan.rb;
+  const uint32_t mask = (1u << rb) - 1;
   const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
   const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
-  LAUNCH("hist_seq", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, HashDigitBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), HashDigitBin{0}));
-  LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), &sc.stats()->n));
+  LAUNCH("hist_seq", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, HashDigitBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), HashDigitBin{0, mask}));
+  TRY(launch_scan_hist(rb, s, sc.hist(0), sc.gbase(0), &sc.stats()->n));
   {
     PassParams<DigitBin, DigitBin> P{};
     P.sv = sv; P.keys_out = ka; P.pos_out = pa;
     P.gbase = sc.gbase(0); P.hist_next = sc.hist(1);
     P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
     P.hashed = 1;
-    P.bin = DigitBin{0}; P.next = DigitBin{RADIX_BITS};
+    P.dbg = g_sort_dbg;
+    P.bin = DigitBin{0, mask}; P.next = DigitBin{rb, mask};
     if (R > 1) {
-      TRY((launch_pass<true, DigitBin, DigitBin, true>("sort_pass_seq", P, n_upper, s)));
-      LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(1), sc.gbase(1), nullptr));
+      TRY((launch_pass<true, DigitBin, DigitBin, true>("sort_pass_seq", P, n_upper, s, rb)));
+      TRY(launch_scan_hist(rb, s, sc.hist(1), sc.gbase(1), (uint64_t *)nullptr));
     } else {
-      TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq", P, n_upper, s)));
+      TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq", P, n_upper, s, rb)));
     }
   }
-  TRY(sort_tail(sc, k, 1, true, ka, pa, kb, pb, n_upper, s, nullptr, R));   // records ordered by the low bits of the mix, in (ka, pa)
+  TRY(sort_tail(sc, plan, 1, true, ka, pa, kb, pb, n_upper, s));   // records ordered by the low bits of the mix, in (ka, pa)
   uint32_t h_cnt[4] = {0, 0, 0, 0};
   uint32_t *fixmem = nullptr;
-  int rc = fix_groups(sc, ka, pa, kb, pb, n_upper, s, h_cnt, &fixmem);       // kb, pb are free: scratch
+  int rc = fix_groups(sc, plan.bits(), ka, pa, kb, pb, n_upper, s, h_cnt, &fixmem);   // kb, pb are free: scratch
   if (rc == KMG_OK) rc = finish_index(ix, sc, ka, pa, n_upper, s, true);      // synchronises
   dfree(fixmem, s);
   *overflow = h_cnt[2] != 0;
+  ix->hbits = plan.bits();
   const double N = (double)ix->N, L = (double)sv.avail;
   prof_bytes("hist_seq", L);
   prof_bytes("sort_pass_seq", L + 12 * N);
@@ -606,6 +708,66 @@ static int build_grouped(const SeqView &sv, int k, kmg_index *ix, SortScratch &s
   if (R > 1) prof_bytes("sort_pass", 24 * N);
   prof_bytes("group_detect", 8 * N);
   return rc;
+}
+
+// One attempt at an index of the windows of `sv` (the caller retries once if the position lists came out unordered).
+static int build_attempt(const SeqView &sv, int k, kmg_index *ix, int order, cudaStream_t s) {
+  const int64_t n_upper = sv.nstarts;
+  SortScratch sc;
+  uint64_t *ka = nullptr, *kb = nullptr;
+  uint32_t *pa = nullptr, *pb = nullptr;
+  auto body = [&]() -> int {
+    const int R = num_passes(k);
+    const bool grouped = grouped_for(k, order, n_upper);
+    const SortPlan gp = grouped_plan(n_upper);
+    TRY(scratch_alloc(sc, n_upper, s, grouped ? gp.rb : RADIX_BITS));
+    TRY(dalloc(&ka, (size_t)n_upper, s));
+    TRY(dalloc(&pa, (size_t)n_upper, s));
+    if (R > 1) { TRY(dalloc(&kb, (size_t)n_upper, s)); TRY(dalloc(&pb, (size_t)n_upper, s)); }
+    if (grouped) {
+      bool overflow = false;
+      TRY(build_grouped(sv, gp, ix, sc, ka, pa, kb, pb, n_upper, s, &overflow));
+      if (!overflow) { pa = nullptr; ix->grouped = true; return KMG_OK; }
+      // more colliding groups than the task lists hold (not seen in practice): rebuild sorted by key
+      void *old[3] = {ix->ukeys, ix->ustart, nullptr};
+      for (void *p : old) g_arena[ix->device & 63].put(p, s, false);
+      ix->ukeys = nullptr; ix->ustart = nullptr; ix->pos = nullptr; ix->hbits = 0;
+      scratch_free(sc, s);
+      TRY(scratch_alloc(sc, n_upper, s, RADIX_BITS));
+    }
+    const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
+    const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
+    LAUNCH("hist_all", s, hist_all_kernel<HIST_THREADS, HIST_ITEMS><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.common(), sc.hist(0), MAX_NB));
+    LAUNCH("hist_finish", s, hist_finish_kernel<<<R, RADIX, 0, s>>>(k, sc.common(), sc.hist(0), sc.gbase(0), MAX_NB, &sc.stats()->n));
+    {
+      PassParams<DigitBin, DigitBin> P{};
+      P.sv = sv; P.keys_out = ka; P.pos_out = pa;
+      P.gbase = sc.gbase(0);
+      P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
+      P.dbg = g_sort_dbg;
+      P.bin = DigitBin{0}; P.next = DigitBin{RADIX_BITS};
+      TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq", P, n_upper, s)));
+    }
+    TRY(sort_tail(sc, SortPlan{RADIX_BITS, R}, 1, false, ka, pa, kb, pb, n_upper, s));   // result ends in (ka, pa)
+    TRY(finish_index(ix, sc, ka, pa, n_upper, s));
+    pa = nullptr;                                          // now owned by the index
+    const double N = (double)ix->N, L = (double)sv.avail;
+    prof_bytes("hist_all", L);
+    prof_bytes("sort_pass_seq", L + 12 * N);
+    if (R > 1) prof_bytes("sort_pass", 24 * N * (R - 1));
+    return KMG_OK;
+  };
+  const int rc = body();
+  dfree(ka, s); dfree(kb, s); dfree(pa, s); dfree(pb, s);
+  scratch_free(sc, s);
+  return rc;
+}
+
+static void release_index_arrays(kmg_index *ix, cudaStream_t s) {
+  void *ptrs[3] = {ix->ukeys, ix->ustart, ix->pos};
+  for (void *p : ptrs) g_arena[ix->device & 63].put(p, s, false);
+  ix->ukeys = nullptr; ix->ustart = nullptr; ix->pos = nullptr;
+  ix->grouped = false; ix->hbits = 0; ix->unstable = false;
 }
 
 static int build_from_view(const SeqView &sv, int k, kmg_index **out, int order = KMG_ORDER_SORTED) {
@@ -624,53 +786,19 @@ static int build_from_view(const SeqView &sv, int k, kmg_index **out, int order 
     return KMG_OK;
   }
   if (n_upper > (int64_t)INT32_MAX) { delete ix; return fail(KMG_ERR_RANGE, "%lld windows exceed the 32-bit coordinates of the reference", (long long)n_upper); }
-
-  SortScratch sc;
-  uint64_t *ka = nullptr, *kb = nullptr;
-  uint32_t *pa = nullptr, *pb = nullptr;
-  int rc = KMG_OK;
-  auto body = [&]() -> int {
-    TRY(scratch_alloc(sc, n_upper, s));
-    TRY(dalloc(&ka, (size_t)n_upper, s));
-    TRY(dalloc(&pa, (size_t)n_upper, s));
-    const int R = num_passes(k);
-    const bool grouped = order == KMG_ORDER_GROUPED && R > g_hash_bits / RADIX_BITS + 1;   // worth it from two saved passes on
-    if (R > 1) { TRY(dalloc(&kb, (size_t)n_upper, s)); TRY(dalloc(&pb, (size_t)n_upper, s)); }
-    if (grouped) {
-      bool overflow = false;
-      TRY(build_grouped(sv, k, ix, sc, ka, pa, kb, pb, n_upper, s, &overflow));
-      if (!overflow) { pa = nullptr; ix->grouped = true; return KMG_OK; }
-      // more colliding groups than the task lists hold (not seen in practice): rebuild sorted by key
-      void *old[3] = {ix->ukeys, ix->ustart, nullptr};
-      for (void *p : old) g_arena[ix->device & 63].put(p, s, false);
-      ix->ukeys = nullptr; ix->ustart = nullptr; ix->pos = nullptr;
-      CU(cudaMemsetAsync(sc.small, 0, sc.small_words * 4, s));
-      CU(cudaMemsetAsync(sc.status, 0, (size_t)ceil_div<int64_t>(n_upper, SORT_TILE_MIN) * RADIX * sizeof(uint64_t), s));
+  int rc = build_attempt(sv, k, ix, order, s);
+  if (rc == KMG_OK && ix->unstable) {
+    // A k-mer's positions are not ascending: the one-atomic rank variant's hardware assumption failed here.
+    // Never use it on this device again and redo the build with the bitmap variant, which assumes nothing.
+    const bool was_atomic = rank_variant() >= 3;
+    release_index_arrays(ix, s);
+    if (!was_atomic) rc = fail(KMG_ERR_CUDA, "internal error: position lists not ascending after a stable sort");
+    else {
+      demote_rank_variant();
+      rc = build_attempt(sv, k, ix, order, s);
+      if (rc == KMG_OK && ix->unstable) rc = fail(KMG_ERR_CUDA, "internal error: position lists not ascending after a stable sort");
     }
-    const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
-    const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
-    LAUNCH("hist_all", s, hist_all_kernel<HIST_THREADS, HIST_ITEMS><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.common(), sc.hist(0)));
-    LAUNCH("hist_finish", s, hist_finish_kernel<<<R, RADIX, 0, s>>>(k, sc.common(), sc.hist(0), sc.gbase(0), &sc.stats()->n));
-    {
-      PassParams<DigitBin, DigitBin> P{};
-      P.sv = sv; P.keys_out = ka; P.pos_out = pa;
-      P.gbase = sc.gbase(0);
-      P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
-      P.bin = DigitBin{0}; P.next = DigitBin{RADIX_BITS};
-      TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq", P, n_upper, s)));
-    }
-    TRY(sort_tail(sc, k, 1, false, ka, pa, kb, pb, n_upper, s));   // result ends in (ka, pa)
-    TRY(finish_index(ix, sc, ka, pa, n_upper, s));
-    pa = nullptr;                                          // now owned by the index
-    const double N = (double)ix->N, L = (double)sv.avail;
-    prof_bytes("hist_all", L);
-    prof_bytes("sort_pass_seq", L + 12 * N);
-    if (R > 1) prof_bytes("sort_pass", 24 * N * (R - 1));
-    return KMG_OK;
-  };
-  rc = body();
-  dfree(ka, s); dfree(kb, s); dfree(pa, s); dfree(pb, s);
-  scratch_free(sc, s);
+  }
   if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_free(ix); return rc; }
   *out = ix;
   return KMG_OK;
@@ -747,10 +875,13 @@ extern "C" int kmg_index_stats(const kmg_index *ix, uint64_t *multi, uint32_t *m
 // ------------------------------------------------------------------------------------------------
 // extraction
 // ------------------------------------------------------------------------------------------------
+// An index is used on the device it lives on: this thread's streams, events and arena belong to its current device
+// (kmg_set_device), so an index of another device is refused rather than driven with the wrong resources.
 static int use_index(const kmg_index *ix) {
   if (!ix) return fail(KMG_ERR_ARG, "index is NULL");
   TRY(ctx_init());
-  if (ix->device != g_ctx.device) CU(cudaSetDevice(ix->device));
+  if (ix->device != g_ctx.device)
+    return fail(KMG_ERR_ARG, "the index lives on device %d but this thread works on device %d: call kmg_set_device(%d) first", ix->device, g_ctx.device, ix->device);
   return KMG_OK;
 }
 
@@ -850,15 +981,20 @@ extern "C" int kmg_counts(const kmg_index *ix, int32_t *out) {
   return rc;
 }
 
-extern "C" int kmg_positions(const kmg_index *ix, int32_t *out) {
+extern "C" int kmg_positions(const kmg_index *ix, int32_t *out) { return kmg_positions_base(ix, 0, out); }
+
+// kmg_positions with the k-mer number offset by i_base: a rank of a sharded index writes its slice of one caller
+// matrix with GLOBAL k-mer numbers (i_base = distinct k-mers held by the owners before it; SURVEY.md 8e "Extraction")
+extern "C" int kmg_positions_base(const kmg_index *ix, uint64_t i_base, int32_t *out) {
   TRY(use_index(ix));
   if (!out && ix->N) return fail(KMG_ERR_ARG, "out is NULL");
+  if (i_base + ix->U > (uint64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "k-mer numbers exceed int");
   const uint32_t *ustart = ix->ustart, *pos = ix->pos;
   const uint64_t U = ix->U, N = ix->N;
   int rc = stream_rows(N, 8, out, CHUNK_BYTES / 8, [=](uint64_t first, uint64_t rows, void *dst, uint64_t *blk, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
     TRY(block_starts(ustart, U, first, rows, s, blk));
-    LAUNCH("positions", s, positions_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, U, pos, first, rows, blk, (int2 *)dst));
+    LAUNCH("positions", s, positions_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, U, pos, first, rows, blk, (int2 *)dst, (uint32_t)i_base));
     return KMG_OK;
   });
   prof_bytes("positions", 4.0 * U + 12.0 * N);
@@ -888,8 +1024,11 @@ static int ensure_pair_index(kmg_index *ix) {
   return KMG_OK;
 }
 
-extern "C" int kmg_pairs_chunk(const kmg_index *cix, uint64_t first, uint64_t n, int32_t *out) {
+extern "C" int kmg_pairs_chunk(const kmg_index *cix, uint64_t first, uint64_t n, int32_t *out) { return kmg_pairs_chunk_base(cix, 0, first, n, out); }
+
+extern "C" int kmg_pairs_chunk_base(const kmg_index *cix, uint64_t i_base, uint64_t first, uint64_t n, int32_t *out) {
   TRY(use_index(cix));
+  if (i_base + cix->U > (uint64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "k-mer numbers exceed int");
   kmg_index *ix = const_cast<kmg_index *>(cix);
   if (first > ix->P || n > ix->P - first) return fail(KMG_ERR_ARG, "pair rows [%llu,+%llu) outside [0,%llu)", (unsigned long long)first, (unsigned long long)n, (unsigned long long)ix->P);
   if (n == 0) return KMG_OK;
@@ -901,7 +1040,7 @@ extern "C" int kmg_pairs_chunk(const kmg_index *cix, uint64_t first, uint64_t n,
   int rc = stream_rows(n, 12, out, CHUNK_BYTES / 12, [=](uint64_t f, uint64_t rows, void *dst, uint64_t *blk, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)ceil_div<uint64_t>(rows, EMIT_TILE);
     TRY(block_starts(pair_off, n_multi, first + f, rows, s, blk));
-    LAUNCH("pairs", s, pairs_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, pos, multi_u, pair_off, n_multi, first + f, rows, blk, (int32_t *)dst));
+    LAUNCH("pairs", s, pairs_kernel<EMIT_THREADS><<<grid, EMIT_THREADS, 0, s>>>(ustart, pos, multi_u, pair_off, n_multi, first + f, rows, blk, (int32_t *)dst, (uint32_t)i_base));
     return KMG_OK;
   });
   prof_bytes("pairs", 12.0 * n);
@@ -1071,12 +1210,15 @@ extern "C" int kmg_query_emit(kmg_query *q, int32_t *out) {
 extern "C" int kmg_query_free(kmg_query *q) {
   if (!q) return KMG_OK;
   const int dev = q->idx ? q->idx->device : g_ctx.device;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(dev);
   const bool mine = g_ctx.ready && g_ctx.device == dev;
   if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
   void *ptrs[3] = {q->hit_i, q->hit_start, q->row_off};
   for (void *p : ptrs) g_arena[dev & 63].put(p, nullptr, true);
   cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
   delete q;
   return KMG_OK;
 }
@@ -1094,12 +1236,15 @@ struct kmg_join {
 extern "C" int kmg_join_free(kmg_join *j) {
   if (!j) return KMG_OK;
   const int dev = j->a ? j->a->device : g_ctx.device;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(dev);
   const bool mine = g_ctx.ready && g_ctx.device == dev;
   if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
   void *ptrs[4] = {j->hit_astart, j->hit_bstart, j->hit_cb, j->row_off};
   for (void *p : ptrs) g_arena[dev & 63].put(p, nullptr, true);
   cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
   delete j;
   return KMG_OK;
 }
@@ -1254,7 +1399,7 @@ extern "C" int kmg_shard_partition(const void *d_seq, int64_t g0, int64_t g1, in
     const int64_t tiles = ceil_div<int64_t>(sv.nstarts, HIST_TILE);
     const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
     LAUNCH("hist_seq_owner", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, OwnerBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), ob));
-    LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), nullptr));
+    TRY(launch_scan_hist(RADIX_BITS, s, sc.hist(0), sc.gbase(0), (uint64_t *)nullptr));
     PassParams<OwnerBin, NoBin> P{};
     P.sv = sv; P.keys_out = d_keys; P.pos_out = d_pos;
     P.gbase = sc.gbase(0); P.hist_next = nullptr;
@@ -1306,11 +1451,12 @@ extern "C" int kmg_build_records(uint64_t *d_keys, uint32_t *d_pos, int64_t n, i
     TRY(dalloc(&pb, (size_t)n, s));
     const unsigned hgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 16), (int64_t)g_ctx.sms * 8);
     LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, nullptr, sc.hist(0), DigitBin{0}));
-    LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), &sc.stats()->n));
+    TRY(launch_scan_hist(RADIX_BITS, s, sc.hist(0), sc.gbase(0), &sc.stats()->n));
     TRY(dalloc(&pfinal, (size_t)n, s));                    // the index must own its positions
-    TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s, pfinal));      // keys end in ka (may be the caller's array)
+    TRY(sort_tail(sc, SortPlan{RADIX_BITS, num_passes(k)}, 0, true, ka, pa, kb, pb, n, s, pfinal));      // keys end in ka (may be the caller's array)
     TRY(finish_index(ix, sc, ka, pfinal, n, s));
     pfinal = nullptr;
+    if (ix->unstable) { demote_rank_variant(); return fail(KMG_ERR_UNSTABLE, "position lists not ascending after the one-atomic sort pass; rebuild (the bitmap variant is now selected)"); }
     const int R = num_passes(k);
     prof_bytes("hist_rec", 8.0 * n);
     if (R > 1) prof_bytes("sort_pass_hist", 24.0 * n * (R - 1));
@@ -1436,7 +1582,7 @@ extern "C" int kmg_shard_scatter(const kmg_shard *sh, const uint64_t *d_splitter
     P.peer = tab;
     P.bin = ob;
     // few bins, many lanes per bin: the bitmap variant measured best here (0.51 ms at N=2; ballots 0.54 ms)
-    TRY((launch_pass_cfg<Cfg0, true, OwnerBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
+    TRY((launch_pass_cfg<PassCfg<256, 24, 2, 0, 8, 8>, true, OwnerBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
     prof_bytes("scatter_peer", (double)sh->sv.avail + 12.0 * (double)sh->sv.nstarts);
     return KMG_OK;
   };
@@ -1467,26 +1613,27 @@ extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t ca
   uint64_t *ka = d_keys, *kb = nullptr;
   uint32_t *pa = d_pos, *pb = nullptr, *pfinal = nullptr;
   uint64_t h_info[2] = {0, 0};
-  const bool grouped = grouped_for(k, order);
+  const bool grouped = grouped_for(k, order, n);
+  const SortPlan gp = grouped_plan(n);
   auto body = [&]() -> int {
-    TRY(scratch_alloc(sc, n, s));
+    TRY(scratch_alloc(sc, n, s, grouped ? gp.rb : RADIX_BITS));
     TRY(dalloc(&kb, (size_t)n, s));
     TRY(dalloc(&pb, (size_t)n, s));
     LAUNCH("set_n", s, set_n_kernel<<<1, 1, 0, s>>>(d_info, capacity, &sc.stats()->n));
     const unsigned hgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 16), (int64_t)g_ctx.sms * 8);
-    LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, &sc.stats()->n, sc.hist(0), DigitBin{0}));
-    LAUNCH("scan_hist", s, scan_hist_kernel<<<1, RADIX, 0, s>>>(sc.hist(0), sc.gbase(0), nullptr));
+    const int rb0 = grouped ? gp.rb : RADIX_BITS;
+    LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, &sc.stats()->n, sc.hist(0), DigitBin{0, (1u << rb0) - 1}));
+    TRY(launch_scan_hist(rb0, s, sc.hist(0), sc.gbase(0), (uint64_t *)nullptr));
     TRY(dalloc(&pfinal, (size_t)n, s));
     CU(cudaMemcpyAsync(h_info, d_info, sizeof h_info, cudaMemcpyDeviceToHost, s));
     if (grouped) {
       // records carry mix64(key): sort on its low bits, then partition the groups in which k-mers share them.
       // The passes ping-pong (caller's arrays <-> ours); the fix-up needs the result and a scratch pair, so the
       // last pass may not divert into pfinal: copy the positions at the end instead.
-      const int R = g_hash_bits / RADIX_BITS;
-      TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s, nullptr, R));
+      TRY(sort_tail(sc, gp, 0, true, ka, pa, kb, pb, n, s, nullptr));
       uint32_t h_cnt[4] = {0, 0, 0, 0};
       uint32_t *fixmem = nullptr;
-      int rc = fix_groups(sc, ka, pa, kb, pb, n, s, h_cnt, &fixmem);
+      int rc = fix_groups(sc, gp.bits(), ka, pa, kb, pb, n, s, h_cnt, &fixmem);
       if (rc == KMG_OK && pa != d_pos) {                     // the sorted positions are in an array of ours: the index keeps it
         dfree(pfinal, s);
         pfinal = pa;
@@ -1502,12 +1649,14 @@ extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t ca
       TRY(rc);
       if (h_cnt[2]) return fail(KMG_ERR_RANGE, "more colliding groups than the task lists hold");
       ix->grouped = true;
+      ix->hbits = gp.bits();
     } else {
-      TRY(sort_tail(sc, k, 0, true, ka, pa, kb, pb, n, s, pfinal));
+      TRY(sort_tail(sc, SortPlan{RADIX_BITS, num_passes(k)}, 0, true, ka, pa, kb, pb, n, s, pfinal));
       TRY(finish_index(ix, sc, ka, pfinal, n, s));            // synchronises
     }
     pfinal = nullptr;
-    const int R = grouped ? g_hash_bits / RADIX_BITS : num_passes(k);
+    if (ix->unstable) { demote_rank_variant(); return fail(KMG_ERR_UNSTABLE, "position lists not ascending after the one-atomic sort pass; rebuild (the bitmap variant is now selected)"); }
+    const int R = grouped ? gp.passes : num_passes(k);
     prof_bytes("hist_rec", 8.0 * (double)ix->N);
     if (R > 1) prof_bytes("sort_pass_hist", 24.0 * (double)ix->N * (R - 1));
     prof_bytes("sort_pass", 24.0 * (double)ix->N);
@@ -1631,7 +1780,7 @@ extern "C" int kmg_shard_pack(const void *d_own, int64_t n_own, int k, int n_sam
   if (n_samples < 2 || n_samples > 4096 || (n_samples & (n_samples - 1))) return fail(KMG_ERR_ARG, "n_samples must be a power of two in [2,4096]");
   TRY(ctx_init());
   cudaStream_t s = g_ctx.stream();
-  LAUNCH("shard_pack", s, shard_pack_kernel<1024><<<1, 1024, (size_t)n_samples * 8, s>>>((const uint8_t *)d_own, n_own, k, n_samples, grouped_for(k, order), (uint8_t *)d_pack));
+  LAUNCH("shard_pack", s, shard_pack_kernel<1024><<<1, 1024, (size_t)n_samples * 8, s>>>((const uint8_t *)d_own, n_own, k, n_samples, grouped_for(k, order, 0), (uint8_t *)d_pack));
   return KMG_OK;
 }
 
@@ -1691,7 +1840,7 @@ extern "C" int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L
   kmg_shard *sh = new (std::nothrow) kmg_shard();
   if (!sh) return fail(KMG_ERR_NOMEM, "host allocation failed");
   sh->device = g_ctx.device;
-  sh->hashed = grouped_for(k, order);
+  sh->hashed = grouped_for(k, order, 0);
   const int pack_bytes = PACK_HDR + 8 * n_samples;
   auto body = [&]() -> int {
     const int64_t need_hi = std::min<int64_t>(L, s1 + k - 1);

@@ -10,7 +10,8 @@
 namespace kmg {
 
 constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;   // bins of one sort pass
+constexpr int RADIX = 1 << RADIX_BITS;   // bins of one sort pass with 8-bit digits (the sorted build's; the grouped build may use wider ones)
+constexpr int MAX_NB = 1024;             // most bins any pass uses (10-bit digits)
 constexpr int MAX_PASSES = 8;            // ceil(64 / RADIX_BITS)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr unsigned FULL_MASK_ = 0xffffffffu;   // for scopes where a template parameter is named FULL

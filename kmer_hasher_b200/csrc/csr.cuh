@@ -13,13 +13,17 @@ struct IndexStats {
   uint64_t P;        // sum n(n-1)/2 (= rows of `pair.pos`)
   uint64_t multi;    // k-mers with more than one position
   uint32_t maxc;     // longest position list
-  uint32_t pad;
+  uint32_t unstable; // != 0: some k-mer's positions are not ascending (the sort was not stable): the caller rebuilds
 };
 
 // ---- run-length pass: one head per distinct key, in order (single pass, chained scan) ----------------
+// The same sweep reads the positions and checks that they ascend inside every run of equal keys: that is what the
+// stable sort promises (and the reference's insertion order gives), and the one-atomic rank variant of the sort pass
+// only delivers it where the hardware applies colliding shared-memory atomics in lane order.  A violation sets
+// st->unstable; the host then rebuilds with the order-independent variant (api.cu, build_from_view).
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)
-rle_kernel(const uint64_t *__restrict__ keys, IndexStats *st, uint64_t *__restrict__ ukeys,
+rle_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos, IndexStats *st, uint64_t *__restrict__ ukeys,
            uint32_t *__restrict__ ustart, Pair64 *status, uint32_t *ticket, const bool hashed) {
   constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32;
   __shared__ uint32_t s_tile, s_wsum[WARPS];
@@ -38,21 +42,28 @@ rle_kernel(const uint64_t *__restrict__ keys, IndexStats *st, uint64_t *__restri
   uint64_t key[ITEMS];
   uint32_t heads = 0, before[ITEMS], running = 0;
   uint64_t carry = 0;                                  // key just before this warp item (lane 0's predecessor)
-  if (lane == 0 && w0 > 0 && w0 < n) carry = ld_stream_u64(keys + w0 - 1);
+  uint32_t pcarry = 0;                                 // and its position
+  bool bad = false;
+  if (lane == 0 && w0 > 0 && w0 < n) { carry = ld_stream_u64(keys + w0 - 1); pcarry = ld_stream_u32(pos + w0 - 1); }
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint64_t idx = w0 + i * 32 + lane;
     const bool ok = idx < n;
     key[i] = ok ? ld_stream_u64(keys + idx) : 0;
+    const uint32_t p = ok ? ld_stream_u32(pos + idx) : 0;
     uint64_t prev = __shfl_up_sync(FULL, key[i], 1);
-    if (lane == 0) prev = carry;
+    uint32_t pprev = __shfl_up_sync(FULL, p, 1);
+    if (lane == 0) { prev = carry; pprev = pcarry; }
     const bool head = ok && (idx == 0 || key[i] != prev);
+    bad |= ok && !head && p <= pprev;                  // same k-mer as the record before: its position must be larger
     const unsigned bal = __ballot_sync(FULL, head);
     before[i] = running + __popc(bal & lanemask_lt());
     running += __popc(bal);
     if (head) heads |= 1u << i;
     carry = __shfl_sync(FULL, key[i], 31);             // lane 0 uses it next round
+    pcarry = __shfl_sync(FULL, p, 31);
   }
+  if (__any_sync(FULL, bad) && lane == 0) st->unstable = 1;
   if (lane == 0) s_wsum[warp] = running;
   __syncthreads();
   uint32_t wbase = 0, total = 0;
@@ -354,7 +365,7 @@ __global__ void counts_kernel(const uint32_t *__restrict__ ustart, uint64_t U, i
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 positions_kernel(const uint32_t *__restrict__ ustart, uint64_t U, const uint32_t *__restrict__ pos, uint64_t first,
-                 uint64_t nrows, const uint64_t *__restrict__ blk_first, int2 *__restrict__ out) {
+                 uint64_t nrows, const uint64_t *__restrict__ blk_first, int2 *__restrict__ out, const uint32_t i_base) {
   constexpr int PER = 8, T = THREADS * PER;
   __shared__ __align__(16) uint8_t s_flag[T];
   __shared__ __align__(16) uint32_t s_seg[T];
@@ -367,7 +378,7 @@ positions_kernel(const uint32_t *__restrict__ ustart, uint64_t U, const uint32_t
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const uint32_t s = j * THREADS + threadIdx.x;
-    if (b0 + s < nrows) out[b0 + s] = make_int2((int)(u0 + s_seg[s] + 1), (int)ld_stream_u32(pos + r0 + s));
+    if (b0 + s < nrows) out[b0 + s] = make_int2((int)(i_base + u0 + s_seg[s] + 1), (int)ld_stream_u32(pos + r0 + s));
   }
 }
 
@@ -446,7 +457,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 pairs_kernel(const uint32_t *__restrict__ ustart, const uint32_t *__restrict__ pos,
              const uint32_t *__restrict__ multi_u, const uint64_t *__restrict__ pair_off, uint64_t n_multi,
-             uint64_t first, uint64_t nrows, const uint64_t *__restrict__ blk_first, int32_t *__restrict__ out) {
+             uint64_t first, uint64_t nrows, const uint64_t *__restrict__ blk_first, int32_t *__restrict__ out, const uint32_t i_base) {
   constexpr int PER = 8, T = THREADS * PER;
   __shared__ __align__(16) uint8_t s_flag[T];
   __shared__ __align__(16) uint32_t s_seg[T];
@@ -466,7 +477,7 @@ pairs_kernel(const uint32_t *__restrict__ ustart, const uint32_t *__restrict__ p
     uint32_t a, b;
     unrank_pair(r0 + s - pair_off[m], cnt, a, b);
     int32_t *row = out + 3 * (b0 + s);
-    row[0] = (int32_t)(u + 1);
+    row[0] = (int32_t)(i_base + u + 1);
     row[1] = (int32_t)pos[a0 + a];
     row[2] = (int32_t)pos[a0 + b];
   }

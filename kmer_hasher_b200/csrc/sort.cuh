@@ -30,7 +30,8 @@ namespace kmg {
 struct DigitBin {
   static constexpr bool CHEAP = true;    // two instructions: recomputed wherever the bin is needed
   int shift;
-  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(key >> shift) & (RADIX - 1); }
+  uint32_t mask = RADIX - 1;             // bins - 1 of the pass (8-, 9- or 10-bit digits)
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(key >> shift) & mask; }
 };
 // owner r holds keys in [spl[r-1], spl[r]): bin = number of splitters <= key
 struct OwnerBin {
@@ -56,7 +57,8 @@ struct HashOwnerBin {
 struct HashDigitBin {
   static constexpr bool CHEAP = true;
   int shift;
-  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(mix64(key) >> shift) & (RADIX - 1); }
+  uint32_t mask = RADIX - 1;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(mix64(key) >> shift) & mask; }
 };
 struct NoBin {
   static constexpr bool CHEAP = true;
@@ -98,56 +100,43 @@ struct PassParams {
 // Tuning knobs of one pass (chosen per launch by the host, see api.cu).
 //   RANK 3: ONE shared-memory atomicAdd per record on the warp's bin counter; its return value is the rank.
 //           Needs colliding lanes of one instruction to be applied in ascending lane order, which the library
-//           verifies per device before using it (lane_order_selftest_kernel); the default when that holds;
-//   RANK 0: peers through a per-warp bitmap table (atomicOr the lane bit, read back, leader clears): the
-//           default otherwise;
-//   RANK 1: peers of a record (same bin, same warp step) from 8 ballots, no shared memory; RANK 2: half/half.
+//           verifies per device before using it (lane_order_selftest_kernel) and re-verifies on every index it
+//           builds (rle_kernel checks that positions ascend inside every k-mer); the default when that holds;
+//   RANK 0: peers through a per-warp bitmap table (atomicOr the lane bit, read back, leader clears): assumes
+//           nothing; the default otherwise.
 //   LB    : status words fetched per look-back round trip.
-// Measured and dropped on B200 (profiles/r01_sort_pass_tuning.md): __match_any_sync (20 % slower
-// than ballots), several items per bitmap round trip, two interleaved rank chains, cp.async of the
-// positions, persistent CTAs that claim the next ticket early and prefetch its records into L2 (13 % slower).
-template <int THREADS_, int ITEMS_, int MINBLOCKS_, int RANK_ = 1, int LB_ = 8>
+//   RB    : bits of the digit (bins = 2^RB): 8, 9 or 10.  More bits = fewer passes over the records.
+// Measured and dropped on B200 (profiles/r01_sort_pass_tuning.md): ranking by 8 ballots, __match_any_sync,
+// several items per bitmap round trip, two interleaved rank chains, cp.async of the positions, persistent CTAs
+// that claim the next ticket early and prefetch its records into L2.
+template <int THREADS_, int ITEMS_, int MINBLOCKS_, int RANK_ = 3, int LB_ = 4, int RB_ = RADIX_BITS>
 struct PassCfg {
-  static constexpr int THREADS = THREADS_, ITEMS = ITEMS_, MINBLOCKS = MINBLOCKS_, RANK = RANK_, LB = LB_;
+  static constexpr int THREADS = THREADS_, ITEMS = ITEMS_, MINBLOCKS = MINBLOCKS_, RANK = RANK_, LB = LB_, RB = RB_;
   static constexpr int TILE = THREADS * ITEMS;
+  static constexpr int NB = 1 << RB_;                                    // bins
+  static constexpr int BPT = NB >= THREADS_ ? NB / THREADS_ : 1;         // consecutive bins owned by a thread
+  static_assert(RANK_ == 0 || RANK_ == 3 || RANK_ == 4, "rank variants: 0 bitmap, 3 one atomic, 4 = 3 made unstable on purpose (tests)");
+  static_assert(NB < THREADS_ || NB % THREADS_ == 0, "bins per thread");
+  static_assert(BPT == 1 || BPT == 2 || BPT == 4, "a thread's bins are moved as one vector");
 };
 
 template <class Cfg, bool FROM_SEQ>
 struct PassSmem {
   static constexpr int TILE = Cfg::TILE;
   static constexpr int WARPS = Cfg::THREADS / 32;
+  static constexpr int NB = Cfg::NB;
   using PosT = typename std::conditional<FROM_SEQ, uint16_t, uint32_t>::type;
   uint64_t keys[TILE];
   PosT pos[TILE];
-  uint32_t whist[WARPS][RADIX];                        // per-warp bin counts, later the warp's first slot of the bin
-  uint32_t match[(Cfg::RANK == 0 || Cfg::RANK == 2) ? WARPS * RADIX : 1];  // RANK 0: lane bitmaps of the item being matched (self-clearing)
-  int32_t goff[RADIX];                                 // global index of the bin's first record of this tile - its tile slot
-  uint32_t next[RADIX];
-  uint32_t scratch[8];
+  alignas(16) uint32_t whist[WARPS][NB];                 // per-warp bin counts, later the warp's first slot of the bin
+  uint32_t match[Cfg::RANK == 0 ? WARPS * NB : 1];       // RANK 0: lane bitmaps of the item being matched (self-clearing)
+  int32_t goff[NB];                                      // global index of the bin's first record of this tile - its tile slot
+  uint32_t next[NB];
+  uint32_t scratch[32];
   uint32_t tile;
-  PeerTable peer;                                      // PEER mode only
+  PeerTable peer;                                        // PEER mode only
   TileCodes<FROM_SEQ ? TILE : 16> tc;
 };
-
-// lanes of the warp whose 8-bit bin equals this lane's (restricted to `active`): per bit one predicate,
-// one ballot and one predicated AND (the compiler's own select sequence is two instructions longer)
-__device__ __forceinline__ uint32_t match_bin(uint32_t d, uint32_t active) {
-  uint32_t peers = active;
-#define KMG_MATCH_BIT(B)                                         \
-  asm volatile(                                                  \
-      "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"                   \
-      "and.b32 t, %1, " #B ";\n\t"                               \
-      "setp.ne.u32 p, t, 0;\n\t"                                 \
-      "vote.sync.ballot.b32 t, p, 0xffffffff;\n\t"               \
-      "@p and.b32 %0, %0, t;\n\t"                                \
-      "@!p lop3.b32 %0, %0, t, 0, 0x30;\n\t}"                    \
-      : "+r"(peers) : "r"(d))
-  static_assert(RADIX_BITS == 8, "eight bin bits");
-  KMG_MATCH_BIT(1); KMG_MATCH_BIT(2); KMG_MATCH_BIT(4); KMG_MATCH_BIT(8);
-  KMG_MATCH_BIT(16); KMG_MATCH_BIT(32); KMG_MATCH_BIT(64); KMG_MATCH_BIT(128);
-#undef KMG_MATCH_BIT
-  return peers;
-}
 
 // Do the shared-memory atomics of one warp take effect in (instruction, lane) order, i.e. do colliding lanes of
 // one instruction get their old values in ascending lane order and do back-to-back instructions stay in issue
@@ -194,15 +183,57 @@ __global__ void lane_order_selftest_kernel(uint32_t *bad) {
   if (fails) atomicAdd(bad, fails);
 }
 
+// BPT consecutive 32-bit words as one access
+template <int BPT> struct WordVec;
+template <> struct WordVec<1> { using T = uint32_t; };
+template <> struct WordVec<2> { using T = uint2; };
+template <> struct WordVec<4> { using T = uint4; };
+template <int BPT>
+__device__ __forceinline__ void load_words(const uint32_t *p, uint32_t (&v)[BPT]) {
+  const typename WordVec<BPT>::T t = *reinterpret_cast<const typename WordVec<BPT>::T *>(p);
+  if constexpr (BPT == 1) v[0] = t;
+  else if constexpr (BPT == 2) { v[0] = t.x; v[1] = t.y; }
+  else { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+}
+template <int BPT>
+__device__ __forceinline__ void store_words(uint32_t *p, const uint32_t (&v)[BPT]) {
+  typename WordVec<BPT>::T t;
+  if constexpr (BPT == 1) t = v[0];
+  else if constexpr (BPT == 2) { t.x = v[0]; t.y = v[1]; }
+  else { t.x = v[0]; t.y = v[1]; t.z = v[2]; t.w = v[3]; }
+  *reinterpret_cast<typename WordVec<BPT>::T *>(p) = t;
+}
+// a thread's BPT status words (consecutive bins) of one tile: one 8- or 16-byte access each way where possible
+template <int BPT>
+__device__ __forceinline__ void ld_status(const uint64_t *p, uint64_t (&w)[BPT]) {
+  if constexpr (BPT == 1) w[0] = ld_relaxed_u64(p);
+  else {
+#pragma unroll
+    for (int q = 0; q < BPT; q += 2)
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[q]), "=l"(w[q + 1]) : "l"(p + q) : "memory");
+  }
+}
+template <int BPT>
+__device__ __forceinline__ void st_status(uint64_t *p, const uint64_t (&w)[BPT]) {
+  if constexpr (BPT == 1) st_relaxed_u64(p, w[0]);
+  else {
+#pragma unroll
+    for (int q = 0; q < BPT; q += 2)
+      asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(p + q), "l"(w[q]), "l"(w[q + 1]) : "memory");
+  }
+}
+
 // One tile.  FULL: every slot of the tile holds a valid record (no predicates on the hot path).
 template <class Cfg, bool FROM_SEQ, bool FULL, class BinFn, class NextFn, bool HAS_NEXT, bool PEER>
 __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, PassSmem<Cfg, FROM_SEQ> &sm,
                                           const uint32_t tile, const int64_t q0, const int64_t n_in,
-                                          const uint32_t gbase, const bool special) {
+                                          const uint32_t (&gbase)[Cfg::BPT], const bool special) {
   using S = PassSmem<Cfg, FROM_SEQ>;
-  constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS, ITEMS = Cfg::ITEMS, WARPS = S::WARPS;
+  constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS, ITEMS = Cfg::ITEMS, WARPS = S::WARPS, NB = Cfg::NB, BPT = Cfg::BPT;
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const int t0 = warp * (32 * ITEMS) + lane;
+  const bool owns = NB >= THREADS || tid < NB;           // this thread owns bins [b0, b0 + BPT)
+  const int b0 = tid * BPT;
 #define KMG_STAMP(slot) do { if (P.trace && tid == 0) P.trace[(size_t)tile * 8 + (slot)] = clock64(); } while (0)
   KMG_STAMP(1);
 
@@ -242,13 +273,16 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     for (int i = 0; i < ITEMS; ++i) dpk[i >> 2] |= P.bin(key[i]) << (8 * (i & 3));
   }
 #define KMG_BIN(i) (BinFn::CHEAP ? P.bin(key[i]) : ((dpk[(i) >> 2] >> (8 * ((i) & 3))) & 0xFFu))
-  if constexpr (Cfg::RANK == 3) {
+  if constexpr (Cfg::RANK >= 3) {
     // One shared-memory atomic per record: the value it returns is the record's rank among the warp's
     // earlier records of the bin, PROVIDED the hardware applies the lanes of one instruction that hit the
     // same address in ascending lane order.  PTX does not promise that; the library checks it once per
-    // device (lane_order_selftest_kernel) and never selects this variant unless the check passed.
+    // device (lane_order_selftest_kernel), never selects this variant unless the check passed, and checks every
+    // finished index (rle_kernel: positions ascend inside each k-mer), rebuilding with the bitmap variant if not.
+    // RANK 4 (tests only): the same with the items visited in reverse, which breaks stability on purpose.
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
+    for (int ii = 0; ii < ITEMS; ++ii) {
+      const int i = Cfg::RANK == 4 ? ITEMS - 1 - ii : ii;
       const uint32_t d = KMG_BIN(i);
       const bool ok = FULL || ((valid >> i) & 1u);
       uint32_t r = 0;
@@ -256,55 +290,9 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
       rk[i] = (d << 16) | r;
       if constexpr (!FULL) __syncwarp();                 // keep the steps in order when the guard diverges
     }
-  } else if constexpr (Cfg::RANK >= 1) {
-    // RANK 2: odd items go through the bitmap table instead, so the ALU (ballots) and the
-    // shared-memory pipe (bitmaps) share the ranking work.
-    // phase A: peers of the ballot items (no memory: all steps overlap)
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      if (Cfg::RANK == 2 && (i & 1)) continue;
-      const bool ok = FULL || ((valid >> i) & 1u);
-      const uint32_t peers = match_bin(KMG_BIN(i), FULL ? FULL_MASK_ : __ballot_sync(FULL_MASK_, ok));
-      rk[i] = ok ? peers : 0u;
-    }
-    // phase B, in item order: the lowest peer bumps the warp's bin count; G atomics in flight before
-    // their results are read
-    constexpr int G = 4;
-    static_assert(ITEMS % G == 0, "items per thread in groups of G");
-    const uint32_t lanebit = 1u << lane;
-    uint32_t *mrow = sm.match + (Cfg::RANK == 2 ? warp * RADIX : 0);
-#pragma unroll
-    for (int i0 = 0; i0 < ITEMS; i0 += G) {
-      uint32_t old[G];
-#pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const int i = i0 + j;
-        const uint32_t d = KMG_BIN(i);
-        if (Cfg::RANK == 2 && (i & 1)) {
-          const bool ok = FULL || ((valid >> i) & 1u);
-          if (ok) atomicOr(&mrow[d], lanebit);
-          __syncwarp();
-          rk[i] = ok ? mrow[d] : 0u;
-          __syncwarp();                                    // everyone has read before the clear
-        }
-        const uint32_t peers = rk[i];
-        old[j] = 0;
-        if (peers && (peers & lt) == 0) {
-          if (Cfg::RANK == 2 && (i & 1)) mrow[d] = 0;
-          old[j] = atomicAdd(&sm.whist[warp][d], (uint32_t)__popc(peers));
-        }
-        __syncwarp();                                      // steps stay in order even if the branch diverges
-      }
-#pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const uint32_t peers = rk[i0 + j];
-        const uint32_t base = __shfl_sync(FULL_MASK_, old[j], (FULL || peers) ? (__ffs(peers) - 1) : 0);
-        rk[i0 + j] = (KMG_BIN(i0 + j) << 16) | (base + __popc(peers & lt));
-      }
-    }
   } else {
     const uint32_t lanebit = 1u << lane;
-    uint32_t *mrow = sm.match + warp * RADIX;
+    uint32_t *mrow = sm.match + warp * NB;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       const uint32_t d = KMG_BIN(i);
@@ -330,30 +318,47 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
 
   // ---- per-bin totals of the tile; publish them, then turn whist[w][bin] into the first slot
   //      of warp w's records of that bin in the regrouped tile
-  uint32_t cnt = 0, lstart = 0, tile_count;
+  uint32_t cnt[BPT], lstart[BPT], tile_count;
   {
-    uint32_t c[WARPS];
-    if (tid < RADIX) {
+    uint32_t c[WARPS][BPT], mine = 0;
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) { c[w] = sm.whist[w][tid]; cnt += c[w]; }
-      st_relaxed_u64(P.status + (size_t)tile * RADIX + tid, st_pack(tile == 0 ? ST_INCL : ST_AGG, P.epoch, cnt));
+    for (int q = 0; q < BPT; ++q) cnt[q] = 0;
+    if (owns) {
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        load_words<BPT>(&sm.whist[w][b0], c[w]);
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) cnt[q] += c[w][q];
+      }
+      uint64_t sw[BPT];
+#pragma unroll
+      for (int q = 0; q < BPT; ++q) { sw[q] = st_pack(tile == 0 ? ST_INCL : ST_AGG, P.epoch, cnt[q]); mine += cnt[q]; }
+      st_status<BPT>(P.status + (size_t)tile * NB + b0, sw);
     }
-    const uint32_t incl = warp_incl_scan(cnt);
-    if (tid < RADIX && lane == 31) sm.scratch[warp] = incl;
+    const uint32_t incl = warp_incl_scan(mine);
+    if (lane == 31) sm.scratch[warp] = incl;
     __syncthreads();
     uint32_t add = 0, tot = 0;
 #pragma unroll
-    for (int j = 0; j < RADIX / 32; ++j) {
+    for (int j = 0; j < WARPS; ++j) {
       const uint32_t s = sm.scratch[j];
       if (j < (int)warp) add += s;
       tot += s;
     }
     tile_count = tot;
-    lstart = incl - cnt + add;
-    if (tid < RADIX) {
-      uint32_t run = lstart;
+    uint32_t run = incl - mine + add;
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) { sm.whist[w][tid] = run; run += c[w]; }
+    for (int q = 0; q < BPT; ++q) { lstart[q] = run; run += cnt[q]; }
+    if (owns) {
+      uint32_t r2[BPT];
+#pragma unroll
+      for (int q = 0; q < BPT; ++q) r2[q] = lstart[q];
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        store_words<BPT>(&sm.whist[w][b0], r2);
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) r2[q] += c[w][q];
+      }
     }
   }
   __syncthreads();
@@ -379,35 +384,61 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
   }
 
   KMG_STAMP(5);                                          // regrouped in shared memory
-  // ---- look back over earlier tiles (one bin per thread, LB status words per round trip);
+  // ---- look back over earlier tiles (a thread's BPT bins in lockstep, LB tiles per round trip);
   //      predecessors have had the whole regrouping above to publish
-  if (tid < RADIX) {
-    uint64_t excl = 0;
+  if (owns) {
+    uint64_t excl[BPT];
+    bool done[BPT];
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) { excl[q] = 0; done[q] = false; }
     if (tile > 0 && !(P.dbg & 1u)) {
       constexpr int LB = Cfg::LB;
       int64_t t = (int64_t)tile - 1;
-      bool done = false;
-      while (!done) {
-        uint64_t w[LB];
-#pragma unroll
-        for (int j = 0; j < LB; ++j)
-          w[j] = t - j >= 0 ? ld_relaxed_u64(P.status + (size_t)(t - j) * RADIX + tid) : st_pack(ST_INCL, P.epoch, 0);
-        if (st_flag(w[0], P.epoch) == 0) { __nanosleep(40); continue; }   // not published yet: back off, poll again
+      bool all_done = false;
+      while (!all_done) {
+        uint64_t w[LB][BPT];
 #pragma unroll
         for (int j = 0; j < LB; ++j) {
-          if (done) break;
-          const uint64_t f = st_flag(w[j], P.epoch);
-          if (f == 0) break;
-          excl += st_value(w[j]);
-          --t;
-          if (f == ST_INCL) done = true;
+          if (t - j >= 0) ld_status<BPT>(P.status + (size_t)(t - j) * NB + b0, w[j]);
+          else {
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) w[j][q] = st_pack(ST_INCL, P.epoch, 0);
+          }
         }
+        int adv = 0;                                       // tiles consumed this round: all pending bins advance together
+        bool stop = false;
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+          if (stop) break;
+          bool ready = true;
+#pragma unroll
+          for (int q = 0; q < BPT; ++q) ready &= done[q] || st_flag(w[j][q], P.epoch) != 0;
+          if (!ready) { stop = true; break; }              // not published yet: poll this tile again
+          bool pending = false;
+#pragma unroll
+          for (int q = 0; q < BPT; ++q) {
+            if (!done[q]) {
+              excl[q] += st_value(w[j][q]);
+              if (st_flag(w[j][q], P.epoch) == ST_INCL) done[q] = true; else pending = true;
+            }
+          }
+          ++adv;
+          if (!pending) { all_done = true; stop = true; }
+        }
+        t -= adv;
+        if (adv == 0) __nanosleep(40);                     // predecessor not published yet: back off
       }
-      st_relaxed_u64(P.status + (size_t)tile * RADIX + tid, st_pack(ST_INCL, P.epoch, excl + cnt));
+      uint64_t sw[BPT];
+#pragma unroll
+      for (int q = 0; q < BPT; ++q) sw[q] = st_pack(ST_INCL, P.epoch, excl[q] + cnt[q]);
+      st_status<BPT>(P.status + (size_t)tile * NB + b0, sw);
     }
-    int64_t go = (int64_t)gbase + (int64_t)excl - (int64_t)lstart;
-    if constexpr (PEER) go += tid < MAX_PEERS ? sm.peer.delta[tid] : 0;
-    sm.goff[tid] = (int32_t)go;
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) {
+      int64_t go = (int64_t)gbase[q] + (int64_t)excl[q] - (int64_t)lstart[q];
+      if constexpr (PEER) go += b0 + q < MAX_PEERS ? sm.peer.delta[b0 + q] : 0;
+      sm.goff[b0 + q] = (int32_t)go;
+    }
   }
   __syncthreads();
   KMG_STAMP(6);                                          // look-back finished for all bins
@@ -440,9 +471,9 @@ template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bo
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS)
 scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   using S = PassSmem<Cfg, FROM_SEQ>;
-  constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS;
+  constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS, NB = Cfg::NB, BPT = Cfg::BPT;
   static_assert(TILE <= 65536, "tile-local positions are 16 bit");
-  static_assert(THREADS >= RADIX, "one thread per bin");
+  static_assert(!PEER || NB >= MAX_PEERS, "one bin per owner");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S &sm = *reinterpret_cast<S *>(smem_raw);
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -452,19 +483,22 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   {
     uint4 *zw = reinterpret_cast<uint4 *>(sm.whist[warp]);
 #pragma unroll
-    for (int j = 0; j < RADIX / 4 / 32; ++j) zw[j * 32 + lane] = make_uint4(0, 0, 0, 0);
-    if constexpr (Cfg::RANK == 0 || Cfg::RANK == 2) {
-      uint4 *zm = reinterpret_cast<uint4 *>(sm.match + warp * RADIX);
+    for (int j = 0; j < NB / 4; j += 32) if (j + (int)lane < NB / 4) zw[j + lane] = make_uint4(0, 0, 0, 0);
+    if constexpr (Cfg::RANK == 0) {
+      uint4 *zm = reinterpret_cast<uint4 *>(sm.match + warp * NB);
 #pragma unroll
-      for (int j = 0; j < RADIX / 4 / 32; ++j) zm[j * 32 + lane] = make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < NB / 4; j += 32) if (j + (int)lane < NB / 4) zm[j + lane] = make_uint4(0, 0, 0, 0);
     }
   }
-  if (HAS_NEXT && tid < RADIX) sm.next[tid] = 0;
+  if constexpr (HAS_NEXT)
+    for (int b = tid; b < NB; b += THREADS) sm.next[b] = 0;
   if constexpr (PEER) {
     static_assert(sizeof(PeerTable) % 8 == 0, "copied as 64-bit words");
     if (tid < sizeof(PeerTable) / 8) reinterpret_cast<uint64_t *>(&sm.peer)[tid] = reinterpret_cast<const uint64_t *>(P.peer)[tid];
   }
-  const uint32_t gbase = tid < RADIX ? __ldg(P.gbase + tid) : 0;   // 1 KB, L2-resident
+  uint32_t gbase[BPT];                                   // bin bases: a few KB, L2-resident
+#pragma unroll
+  for (int q = 0; q < BPT; ++q) gbase[q] = (NB >= THREADS || tid < NB) ? __ldg(P.gbase + tid * BPT + q) : 0;
   const int64_t n_in = FROM_SEQ ? P.sv.nstarts : (int64_t)*P.n_records;
   __syncthreads();
   const uint32_t tile = sm.tile;
@@ -482,18 +516,19 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
 
   if constexpr (HAS_NEXT) {
     __syncthreads();
-    if (tid < RADIX) {
-      uint32_t c = sm.next[tid];
-      if (c) atomicAdd(P.hist_next + tid, c);
+    for (int b = tid; b < NB; b += THREADS) {
+      const uint32_t c = sm.next[b];
+      if (c) atomicAdd(P.hist_next + b, c);
     }
   }
 }
 
 // ---- bin bases -----------------------------------------------------------------------------------------
-// gbase = exclusive scan of one histogram; *n (if given) = its total.  One block of RADIX threads.
-__global__ void __launch_bounds__(RADIX)
+// gbase = exclusive scan of one histogram of NB bins; *n (if given) = its total.  One block of NB threads.
+template <int NB>
+__global__ void __launch_bounds__(NB)
 scan_hist_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ gbase, uint64_t *n) {
-  __shared__ uint32_t part[RADIX / 32];
+  __shared__ uint32_t part[NB / 32];
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t v = hist[tid];
   const uint32_t incl = warp_incl_scan(v);
@@ -502,7 +537,7 @@ scan_hist_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ gbase
   uint32_t add = 0;
   uint64_t tot = 0;
 #pragma unroll
-  for (int j = 0; j < RADIX / 32; ++j) {
+  for (int j = 0; j < NB / 32; ++j) {
     if (j < (int)warp) add += part[j];
     tot += part[j];
   }
@@ -553,7 +588,7 @@ owner_offsets_kernel(const uint64_t *__restrict__ matrix, int nparts, int rank, 
 // window's digits directly into ind[r].  hist_finish_kernel adds the two.
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)
-hist_all_kernel(const SeqView sv, uint32_t *common /* [RADIX] */, uint32_t *ind /* [R][RADIX] */) {
+hist_all_kernel(const SeqView sv, uint32_t *common /* [RADIX] */, uint32_t *ind /* [R][stride] */, const int stride) {
   constexpr int TILE = THREADS * ITEMS;
   __shared__ TileCodes<TILE> tc;
   __shared__ uint32_t sh_common[RADIX];
@@ -598,25 +633,25 @@ hist_all_kernel(const SeqView sv, uint32_t *common /* [RADIX] */, uint32_t *ind 
   }
   for (int b = tid; b < R * RADIX; b += THREADS) {
     const uint32_t c = (&sh_ind[0][0])[b];
-    if (c) atomicAdd(ind + b, c);
+    if (c) atomicAdd(ind + (size_t)(b / RADIX) * stride + (b % RADIX), c);
   }
 }
 
 // hist[r] = ind[r] + common folded to digit r's width; gbase[r] = its exclusive scan; *n = windows.
 // Launched with R blocks of RADIX threads.
 __global__ void __launch_bounds__(RADIX)
-hist_finish_kernel(int k, const uint32_t *__restrict__ common, uint32_t *hist /* [R][RADIX], holds ind */,
-                   uint32_t *gbase /* [R][RADIX] */, uint64_t *n) {
+hist_finish_kernel(int k, const uint32_t *__restrict__ common, uint32_t *hist /* [R][stride], holds ind */,
+                   uint32_t *gbase /* [R][stride] */, const int stride, uint64_t *n) {
   __shared__ uint32_t part[RADIX / 32];
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const int r = blockIdx.x;
   const int m = min(4, k - 4 * r);                      // bases in digit r
   const int s = 2 * (4 - m);
-  uint32_t v = hist[r * RADIX + tid];
+  uint32_t v = hist[(size_t)r * stride + tid];
   if (tid < (1u << (2 * m))) {
     for (uint32_t c = tid << s; c < ((tid + 1u) << s); ++c) v += common[c];
   }
-  hist[r * RADIX + tid] = v;
+  hist[(size_t)r * stride + tid] = v;
   const uint32_t incl = warp_incl_scan(v);
   if (lane == 31) part[warp] = incl;
   __syncthreads();
@@ -627,7 +662,7 @@ hist_finish_kernel(int k, const uint32_t *__restrict__ common, uint32_t *hist /*
     if (j < (int)warp) add += part[j];
     tot += part[j];
   }
-  gbase[r * RADIX + tid] = incl - v + add;
+  gbase[(size_t)r * stride + tid] = incl - v + add;
   if (r == 0 && tid == 0) *n = tot;
 }
 
@@ -637,9 +672,9 @@ __global__ void __launch_bounds__(THREADS)
 hist_seq_kernel(const SeqView sv, uint32_t *hist, BinFn bin) {
   constexpr int TILE = THREADS * ITEMS;
   __shared__ TileCodes<TILE> tc;
-  __shared__ uint32_t sh[RADIX];
+  __shared__ uint32_t sh[MAX_NB];
   const unsigned tid = threadIdx.x;
-  for (int b = tid; b < RADIX; b += THREADS) sh[b] = 0;
+  for (int b = tid; b < MAX_NB; b += THREADS) sh[b] = 0;
   const int64_t tiles = ceil_div<int64_t>(sv.nstarts, TILE);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t q0 = tile * TILE;
@@ -660,7 +695,7 @@ hist_seq_kernel(const SeqView sv, uint32_t *hist, BinFn bin) {
     }
   }
   __syncthreads();
-  for (int b = tid; b < RADIX; b += THREADS) {
+  for (int b = tid; b < MAX_NB; b += THREADS) {
     uint32_t c = sh[b];
     if (c) atomicAdd(hist + b, c);
   }
@@ -670,14 +705,14 @@ hist_seq_kernel(const SeqView sv, uint32_t *hist, BinFn bin) {
 template <int THREADS, class BinFn>
 __global__ void __launch_bounds__(THREADS)
 hist_rec_kernel(const uint64_t *keys, int64_t n_host, const uint64_t *n_dev, uint32_t *hist, BinFn bin) {
-  __shared__ uint32_t sh[RADIX];
+  __shared__ uint32_t sh[MAX_NB];
   const int64_t n = n_dev ? (int64_t)*n_dev : n_host;   // the count may only exist on the device
-  for (int b = threadIdx.x; b < RADIX; b += THREADS) sh[b] = 0;
+  for (int b = threadIdx.x; b < MAX_NB; b += THREADS) sh[b] = 0;
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS)
     atomicAdd(&sh[bin(ld_stream_u64(keys + i))], 1u);
   __syncthreads();
-  for (int b = threadIdx.x; b < RADIX; b += THREADS) {
+  for (int b = threadIdx.x; b < MAX_NB; b += THREADS) {
     uint32_t c = sh[b];
     if (c) atomicAdd(hist + b, c);
   }

@@ -107,6 +107,24 @@ def pairs_join(a: dict, b: dict) -> np.ndarray:
     return (np.concatenate(out) if out else np.empty((0, 2), np.int32)).astype(np.int32).ravel()
 
 
+
+class _RefDig(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("sum", C.c_uint64), ("wsum", C.c_uint64)]
+
+    def tuple(self):
+        return (int(self.n), int(self.sum), int(self.wsum))
+
+
+def digest(values) -> tuple:
+    """(n, sum v_t, sum v_t * (2t + 1)) mod 2^64 of a flattened integer stream: the digest ref_driver.c's
+    ref_digest_canonical / ref_query_digest record for the full-size golden fixtures (numpy restatement)."""
+    v = np.ascontiguousarray(values).ravel()
+    v = v.astype(np.int64).view(np.uint64) if v.dtype != np.uint64 else v
+    t = np.arange(v.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return (int(v.size), int(v.sum(dtype=np.uint64)), int((v * (np.uint64(2) * t + np.uint64(1))).sum(dtype=np.uint64)))
+
+
 class Oracle:
     def __init__(self):
         if not os.path.exists(ORACLE_SO):
@@ -197,6 +215,26 @@ class ReferenceIndex:
             self._lib.ref_query_free(rows)
         return out if want_rows else n
 
+    def digest(self, flag: int = 2 | 8) -> dict:
+        """Digests (see `digest`) of the canonical keys / count / pos / pair.pos streams, generated from the
+        reference's tables without materialising them (ref_digest_canonical)."""
+        d = {n: _RefDig() for n in ("keys", "count", "pos", "pair_pos")}
+        bind = (C.c_uint64 * 2)()
+        self._lib.ref_digest_canonical(self._h, C.byref(d["keys"]), C.byref(d["count"]) if flag & 8 else None,
+                                       C.byref(d["pos"]) if flag & 2 else None, C.byref(d["pair_pos"]) if flag & 4 else None, bind)
+        out = {n: v.tuple() for n, v in d.items() if n == "keys" or (n == "count" and flag & 8) or (n == "pos" and flag & 2)
+               or (n == "pair_pos" and flag & 4)}
+        out["bind"] = (int(bind[0]), int(bind[1]))    # order-independent: sum key*count, sum key*pos (mod 2^64)
+        return out
+
+    def query_digest(self, seq, k: int):
+        """(rows, digest of the interleaved (i,j) stream) of seq_kmer_positions."""
+        b = _as_bytes(seq)
+        d, sec = _RefDig(), C.c_double(0)
+        n = self._lib.ref_query_digest(self._h, b, k, C.byref(d), C.byref(sec))
+        self.query_seconds = sec.value
+        return int(n), d.tuple()
+
     def pairs_join(self, other: "ReferenceIndex") -> np.ndarray:
         """kmer.pairs(self, other) on the reference's own hash tables (ref_pairs_join): rows (a, b) flattened."""
         rows = _i32p()
@@ -238,6 +276,10 @@ class Reference:
         lib.ref_free_buf.argtypes = [C.c_void_p]
         lib.ref_pairs_join.restype = C.c_int64
         lib.ref_pairs_join.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_i32p)]
+        lib.ref_digest_canonical.restype = None
+        lib.ref_digest_canonical.argtypes = [C.c_void_p] + [C.POINTER(_RefDig)] * 4 + [_u64p]
+        lib.ref_query_digest.restype = C.c_int64
+        lib.ref_query_digest.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(_RefDig), _dblp]
         self.lib = lib
 
     @staticmethod

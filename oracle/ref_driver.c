@@ -176,6 +176,60 @@ void ref_extract_canonical(const ref_index *ri, uint64_t *keys, char *kmers, int
   free(ord);
 }
 
+/* ---- order-sensitive digests of the canonical outputs (full-size golden fixtures) -----------------
+ * The BASELINE-size outputs (2N ints of pos at 250 Mbp, 3P ints of pair.pos at P > 10^9) are too large to
+ * commit, so tests/golden/make_fullsize.py records digests of them instead: for the flattened value stream
+ * v_0, v_1, ... : n, sum v_t and sum v_t * (2t + 1), all mod 2^64.  tests/ recompute the same three numbers
+ * from the CUDA path's output (on the device).  Nothing is materialised here: the streams are generated
+ * straight from the reference's own tables. */
+typedef struct { uint64_t n, sum, wsum; } ref_dig;
+static inline void dig_add(ref_dig *d, uint64_t v) { d->sum += v; d->wsum += v * (2 * d->n + 1); d->n++; }
+
+/* bind[0] = sum key * count, bind[1] = sum key * pos over all (k-mer, position) pairs, mod 2^64: ORDER-INDEPENDENT sums
+ * that tie counts and positions to their k-mer.  A sharded index (k-mers spread over several GPUs in no global order)
+ * is checked against them together with the n / sum parts of the digests above (bench.py --gpus N, tests). */
+void ref_digest_canonical(const ref_index *ri, ref_dig *keys, ref_dig *counts, ref_dig *pos, ref_dig *pairs, uint64_t *bind) {
+  khash_t(kmer_h) *h = ri->hp.hash;
+  size_t U = kh_size(h);
+  key_slot *ord = malloc((U ? U : 1) * sizeof(key_slot));
+  size_t u = 0;
+  for (khiter_t it = kh_begin(h); it != kh_end(h); ++it)
+    if (kh_exist(h, it)) { ord[u].key = kh_val(h, it).kmer; ord[u].slot = (uint32_t)it; ++u; }
+  qsort(ord, U, sizeof(key_slot), cmp_key_slot);
+  if (keys) memset(keys, 0, sizeof *keys);
+  if (counts) memset(counts, 0, sizeof *counts);
+  if (pos) memset(pos, 0, sizeof *pos);
+  if (pairs) memset(pairs, 0, sizeof *pairs);
+  if (bind) bind[0] = bind[1] = 0;
+  for (u = 0; u < U; ++u) {
+    const kmer_pos_t *kv = &kh_val(h, ord[u].slot);
+    const uint64_t i = u + 1;                       /* canonical 1-based k-mer number */
+    if (keys) dig_add(keys, kv->kmer);
+    if (counts) dig_add(counts, (uint64_t)kv->v.n);
+    if (bind) bind[0] += kv->kmer * (uint64_t)kv->v.n;
+    for (size_t a = 0; a < kv->v.n; ++a) {          /* same loops as kmer_hash.c:1108-1120 */
+      if (bind) bind[1] += kv->kmer * (uint64_t)(int64_t)kv->v.a[a];
+      if (pos) { dig_add(pos, i); dig_add(pos, (uint64_t)(int64_t)kv->v.a[a]); }
+      if (pairs)
+        for (size_t b = a + 1; b < kv->v.n; ++b) {
+          dig_add(pairs, i); dig_add(pairs, (uint64_t)(int64_t)kv->v.a[a]); dig_add(pairs, (uint64_t)(int64_t)kv->v.a[b]);
+        }
+    }
+  }
+  free(ord);
+}
+
+/* digest of the rows seq_kmer_positions (kmer_pos.c:110-136) returns, in its own order */
+int64_t ref_query_digest(const ref_index *ri, const char *seq, int k, ref_dig *rows, double *seconds) {
+  double t0 = now_s();
+  kmer_ppos pp = seq_kmer_positions(ri->hp.hash, seq, k);
+  if (seconds) *seconds = now_s() - t0;
+  memset(rows, 0, sizeof *rows);
+  for (size_t t = 0; t < pp.n; ++t) dig_add(rows, (uint64_t)(int64_t)pp.a[t]);
+  free(pp.a);
+  return (int64_t)(pp.n / 2);
+}
+
 /* seq_kmer_positions (kmer_pos.c:110-136) called as is; rows are (i,j)
  * interleaved, already in a deterministic order.  The result is malloc'd by the
  * reference's kvec; ref_query_free releases it. */

@@ -122,3 +122,34 @@ def test_pairs_join_restatement_matches_reference_tables(oracle, reference):
     # shared: ACGT (a@1,5 ; b@3), TACG (a@4 ; b@2); keys ascending: ACGT = 0b00011011 = 27... order by key
     assert sorted(map(tuple, rows.tolist())) == [(1, 3), (4, 2), (5, 3)]
     ra.close(); rb.close()
+
+
+def test_digest_implementations_agree(reference):
+    """The three statements of the full-size digest -- C over the reference's tables (oracle/ref_driver.c), numpy
+    (oracle.digest) and torch (tests/test_fullsize_gpu.DevDigest, run on the device by the GPU test) -- give the same
+    numbers, including the piecewise and scattered accumulation the GPU test uses."""
+    import torch
+    from kmer_hasher_b200 import synth
+    from oracle import digest
+    from test_fullsize_gpu import DevDigest
+    seq = synth.config_c3(150_000, tail_k=12)
+    r = reference.build(seq, 12)
+    e, d = r.extract(15), r.digest(15)
+    for name in ("keys", "count", "pos", "pair_pos"):
+        assert d[name] == digest(e[name])
+        x = torch.from_numpy(e[name].view(np.int64) if e[name].dtype == np.uint64 else e[name])
+        assert tuple(DevDigest(torch).add(x[:1000]).add(x[1000:], chunk=4096).tuple()) == d[name]
+    pos = torch.from_numpy(e["pos"]).to(torch.int64)
+    perm = torch.randperm(pos.numel())
+    dd = DevDigest(torch)
+    dd.add_at(pos[perm], perm)
+    assert tuple(dd.tuple()) == d["pos"]
+    keys, cnt = e["keys"], e["count"].astype(np.uint64)
+    rows = e["pos"].reshape(-1, 2)
+    with np.errstate(over="ignore"):
+        assert d["bind"] == (int((keys * cnt).sum(dtype=np.uint64)),
+                             int((keys[rows[:, 0] - 1] * rows[:, 1].astype(np.uint64)).sum(dtype=np.uint64)))
+    q = synth.config_c4_query(seq, 40_000)
+    n, dq = r.query_digest(q, 12)
+    assert dq == digest(r.query(q, 12)) and n == dq[0] // 2
+    r.close()

@@ -509,11 +509,12 @@ def test_reverse_complement_probe(kh, oracle, k):
     index_of_rc.free()
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 5, 6])
-def test_every_sort_pass_variant_is_exact(kh, oracle, cfg):
-    """The pass variants selectable with KMG_SORT_CFG / kmg_tune (bitmap, ballot, mixed, one-atomic rank, other
-    tile shapes) all give the reference's index; the one-atomic variant is only the default where the
-    lane-order self-test passes, which is asserted here for this GPU."""
+@pytest.mark.parametrize("rank,shape,rb", [(0, 0, 8), (3, 0, 8), (0, 0, 9), (3, 0, 9), (3, 1, 8), (3, 1, 9), (0, 1, 9),
+                                           (3, 2, 8), (0, 2, 8), (3, 0, 10), (0, 0, 10)])
+def test_every_sort_pass_variant_is_exact(kh, oracle, rank, shape, rb):
+    """The pass variants selectable with kmg_tune -- rank by one atomic per record or by bitmap match, the tile
+    shapes, digits of 8, 9 and 10 bits -- all give the reference's index; the one-atomic variant is only the default
+    where the lane-order self-test passes, which is asserted here for this GPU."""
     import ctypes as C
     from kmer_hasher_b200 import synth, _lib
     L = _lib.load()
@@ -525,7 +526,9 @@ def test_every_sort_pass_variant_is_exact(kh, oracle, cfg):
     seq[5000:9000] = np.frombuffer(b"CA" * 2000, np.uint8)
     seq[20000:20040] = ord("N")
     try:
-        _lib.check(L.kmg_tune(b"sort_cfg", cfg))
+        _lib.check(L.kmg_tune(b"sort_cfg", rank))
+        _lib.check(L.kmg_tune(b"sort_shape", shape))
+        _lib.check(L.kmg_tune(b"hash_rb", rb))
         for k in (32, 21, 9):
             ix = kh.make_kmer_hash(seq, k)
             got = kh.kmer_pos(ix, 2 | 8, canonical=True)
@@ -534,11 +537,52 @@ def test_every_sort_pass_variant_is_exact(kh, oracle, cfg):
             assert np.array_equal(got["count"], want["count"])
             assert np.array_equal(got["pos"].ravel(), want["pos"])
             ix.free()
+        assert L.kmg_tune_get(b"unstable_rebuilds", 0) == 0
     finally:
-        _lib.check(L.kmg_tune(b"sort_cfg", 3))
+        _lib.check(L.kmg_tune(b"sort_cfg", -1))
+        _lib.check(L.kmg_tune(b"sort_shape", 0))
+        _lib.check(L.kmg_tune(b"hash_rb", 0))
 
 
-@pytest.mark.parametrize("bits", [16, 24, 40])
+def test_unstable_sort_is_caught_and_rebuilt(kh, oracle):
+    """The always-on guard (rle_kernel checks that positions ascend inside every k-mer): a sort pass that is unstable on
+    purpose (rank variant 4 visits a thread's records in reverse) is noticed, the device is switched to the bitmap
+    variant for good and the index is rebuilt, so the caller still gets the reference's result."""
+    import ctypes as C
+    from kmer_hasher_b200 import synth, _lib
+    L = _lib.load()
+    seq = synth.config_c2(300_000)
+    seq[1000:3000] = ord("A")
+    seq[5000:9000] = np.frombuffer(b"CA" * 2000, np.uint8)
+    before = L.kmg_tune_get(b"unstable_rebuilds", 0)
+    try:
+        for k, order in ((32, False), (12, True)):          # grouped and sorted builds
+            _lib.check(L.kmg_tune(b"reset_rank", 0))
+            _lib.check(L.kmg_tune(b"sort_cfg", 4))
+            ix = kh.make_kmer_hash(seq, k, do_sort=order)
+            assert L.kmg_tune_get(b"rank_variant", 0) == 0     # demoted to the bitmap variant, override dropped
+            got = kh.kmer_pos(ix, 2 | 8, canonical=True)
+            want = oracle.build(seq, k).extract(2 | 8)
+            assert np.array_equal(got["count"], want["count"]) and np.array_equal(got["pos"].ravel(), want["pos"])
+            ix.free()
+        assert L.kmg_tune_get(b"unstable_rebuilds", 0) == before + 2
+        # builds from records report it instead (the caller's arrays are consumed): KMG_ERR_UNSTABLE
+        import torch
+        okeys, opos = oracle.windows(seq, 32)
+        keys = torch.from_numpy(okeys.view(np.int64)).cuda()
+        pos = torch.from_numpy(opos).cuda()
+        _lib.check(L.kmg_tune(b"reset_rank", 0))
+        _lib.check(L.kmg_tune(b"sort_cfg", 4))
+        h = C.c_void_p()
+        rc = L.kmg_build_records(keys.data_ptr(), pos.data_ptr(), len(okeys), 32, C.byref(h))
+        assert rc == -7 and L.kmg_tune_get(b"rank_variant", 0) == 0
+    finally:
+        _lib.check(L.kmg_tune(b"sort_cfg", -1))
+        _lib.check(L.kmg_tune(b"reset_rank", 0))              # the self-test decides again
+    assert L.kmg_tune_get(b"rank_variant", 0) == 3
+
+
+@pytest.mark.parametrize("bits", [16, 24, 27, 40])
 def test_grouped_build_with_forced_collisions(kh, oracle, bits):
     """KMG_ORDER_GROUPED sorts on `bits` bits of a mix of the key and partitions the groups in which several
     k-mers share those bits.  Few bits force such groups everywhere: 8 bits -> every group is long (the
@@ -574,7 +618,7 @@ def test_grouped_build_with_forced_collisions(kh, oracle, bits):
             assert np.array_equal(kh.kmer_keys(srt), want["keys"])
             ix.free(); srt.free()
     finally:
-        _lib.check(L.kmg_tune(b"hash_bits", 40))
+        _lib.check(L.kmg_tune(b"hash_bits", 0))
 
 
 def test_grouped_build_falls_back_when_the_task_list_overflows(kh, oracle):
@@ -613,5 +657,5 @@ def test_grouped_build_falls_back_when_the_task_list_overflows(kh, oracle):
         assert e.value.code == -3
         eng.shard_close(h)
     finally:
-        _lib.check(L.kmg_tune(b"hash_bits", 40))
+        _lib.check(L.kmg_tune(b"hash_bits", 0))
         _lib.check(L.kmg_tune(b"fix_cap", 0))

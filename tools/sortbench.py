@@ -1,10 +1,10 @@
-"""Tuning run: per-kernel CUDA-event times of make.kmer.hash for each sort-pass configuration.
-usage: python tools/sortbench.py [L] [k] [cfg,cfg,...]"""
+"""Tuning run: per-kernel CUDA-event times of make.kmer.hash for sort-pass configurations.
+usage: python tools/sortbench.py [L] [k] [rank:shape:rb:bits,...] [workload c2|c3]
+  rank 0 bitmap / 3 one atomic; shape 0 256x24x2, 1 256x28x2, 2 256x20x3 (8-bit only); rb digit bits; bits = hash bits (0 = auto)"""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 
 import kmer_hasher_b200 as kh
@@ -12,15 +12,16 @@ from kmer_hasher_b200 import _lib, synth
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 40_000_000
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-cfgs = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(12))
-dbgs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
-if os.environ.get("KMG_HASH_BITS"):
-    _lib.check(_lib.load().kmg_tune(b"hash_bits", int(os.environ["KMG_HASH_BITS"])))
+specs = sys.argv[3].split(",") if len(sys.argv) > 3 else ["3:0:8:32", "3:0:8:40", "3:0:9:36", "3:0:10:40", "3:1:8:32", "3:1:9:36", "3:2:8:32", "0:0:8:32", "0:0:9:36"]
+wl = sys.argv[4] if len(sys.argv) > 4 else "c2"
 lib = _lib.load()
-seq = torch.from_numpy(synth.config_c2(L)).cuda()
-for cfg, dbg in [(c, d) for c in cfgs for d in dbgs]:
-    _lib.check(lib.kmg_tune(b"sort_cfg", cfg))
-    _lib.check(lib.kmg_tune(b"sort_dbg", dbg))
+seq = torch.from_numpy(synth.config_c2(L) if wl == "c2" else synth.config_c3(L)).cuda()
+for spec in specs:
+    rank, shape, rb, bits = (int(x) for x in spec.split(":"))
+    _lib.check(lib.kmg_tune(b"sort_cfg", rank))
+    _lib.check(lib.kmg_tune(b"sort_shape", shape))
+    _lib.check(lib.kmg_tune(b"hash_rb", rb))
+    _lib.check(lib.kmg_tune(b"hash_bits", bits))
     for _ in range(2):
         kh.make_kmer_hash(seq, k).free()
     kh.profile(enable=True, reset=True)
@@ -36,10 +37,10 @@ for cfg, dbg in [(c, d) for c in cfgs for d in dbgs]:
     prof = kh.profile(enable=False)
     kh.profile(reset=True)
     sp = prof.get("sort_pass", (0, 1, 0))
-    line = f"cfg {cfg:2d} dbg {dbg} build {a.elapsed_time(b) / reps:7.3f} ms | sort_pass {sp[0] / max(sp[1], 1) * 1e3:7.1f} us {sp[2] / max(sp[0], 1e-9) / 1e6:7.0f} GB/s"
+    line = f"rank {rank} shape {shape} rb {rb} bits {bits:2d} build {a.elapsed_time(b) / reps:7.3f} ms | sort_pass {sp[0] / max(sp[1], 1) * 1e3:7.1f} us {sp[2] / max(sp[0], 1e-9) / 1e6:7.0f} GB/s"
     sph = prof.get("sort_pass_hist")
     if sph:
-        line += f" | sort_pass_hist {sph[0] / max(sph[1], 1) * 1e3:6.1f}us x{sph[1] // reps}"
+        line += f" | sort_pass_hist {sph[0] / max(sph[1], 1) * 1e3:6.1f}us x{sph[1] // reps} {sph[2] / max(sph[0], 1e-9) / 1e6:5.0f} GB/s"
     for name in ("sort_pass_seq", "hist_all", "hist_seq", "group_detect", "small_fix", "big_fix", "rle", "stats"):
         if name in prof:
             v = prof[name]

@@ -16,7 +16,7 @@ tile = int(sys.argv[3]) if len(sys.argv) > 3 else 6144
 lib = _lib.load()
 raw = C.CDLL(_lib.LIB_PATH)
 seq = torch.from_numpy(synth.config_c2(L)).cuda()
-_lib.check(lib.kmg_tune(b"sort_cfg", cfg))
+_lib.check(lib.kmg_tune(b"sort_cfg", 3 if cfg else 0))
 for _ in range(2):
     kh.make_kmer_hash(seq, 32).free()
 ntr = (L + 2047) // 2048
