@@ -211,6 +211,25 @@ int kmg_ipc_free(void *dptr);
 int kmg_ipc_open(const void *handle, void **dptr);
 int kmg_ipc_close(void *dptr);
 
+/* ---- count.kmers (per-source k-mer counts) and spectra ---------------------------------------------------
+ * kmg_count_add replaces  seq_to_counts / kmer_count_insert   src/kmer_hash.c:185-252
+ * as called from          count_kmers                         src/kmer_hash.c:548-591  (count.kmers, kmer_hash.R:43-46).
+ * The reference keeps source_n counters per distinct k-mer in the same hash type as the position index and bumps
+ * column `source` once per window; the table is read back with kmer.pos (rows (i, count of source s)).  Here the
+ * k-mers of a table are ordered by ascending key.  Spectra: spec[min(count, max_count)] += 1 per k-mer, as doubles
+ * (count_spectrum, src/kmer_tree.c:85-99, the shape kmer_spectrum_* return, src/kmer_hash.c:975-1038). */
+typedef struct kmg_counter kmg_counter;
+int kmg_count_new(int k, int source_n, kmg_counter **out);
+int kmg_count_add(kmg_counter *c, const char *seq, int64_t len, int source);
+int kmg_count_sizes(const kmg_counter *c, uint64_t *U, int *source_n, int *k, uint64_t *new_total);
+int kmg_count_kmers_u64(const kmg_counter *c, uint64_t *keys /* U */);
+int kmg_count_kmers_ascii(const kmg_counter *c, char *buf /* U*(k+1) */);
+int kmg_count_matrix(const kmg_counter *c, int32_t *out /* U*source_n, one row per k-mer */);
+int kmg_count_positions(const kmg_counter *c, int32_t *out /* 2*U*source_n: rows (i, count) as kmer.pos(ptr, 2) gives */);
+int kmg_count_spectrum(const kmg_counter *c, int source /* < 0: summed over sources */, uint32_t max_count, double *spec /* max_count+1 */);
+int kmg_index_spectrum(const kmg_index *idx, uint32_t max_count, double *spec /* max_count+1 */);
+int kmg_count_free(kmg_counter *c);
+
 /* ---- instrumentation (bench.py / profiles) ------------------------------------------------------ */
 int kmg_profile_enable(int on);          /* bracket every kernel with CUDA events               */
 int kmg_profile_reset(void);

@@ -20,7 +20,8 @@ import numpy as np
 from . import _lib
 from ._lib import KmgError, check
 
-__all__ = ["KmerHash", "make_kmer_hash", "kmer_pos", "seq_kmer_pos", "kmer_pairs", "pinned_empty", "KmgError",
+__all__ = ["KmerHash", "KmerCounts", "make_kmer_hash", "kmer_pos", "seq_kmer_pos", "kmer_pairs", "count_kmers", "kmer_spectrum",
+           "pinned_empty", "KmgError",
            "OPT_KMER", "OPT_POS", "OPT_PAIRS", "OPT_COUNT"]
 
 # opt.flag bits, src/kmer_hash.c:17 (pos_opt_flags) in the reference
@@ -112,6 +113,34 @@ class KmerHash:
             pass
 
 
+class KmerCounts(KmerHash):
+    """What count.kmers returns: the same kind of external pointer (same tag) holding per-source counts instead of
+    positions (count_kmers, src/kmer_hash.c:548-591)."""
+
+    def __init__(self, handle: int, k: int, source_n: int):
+        super().__init__(handle, k)
+        self.source_n = source_n
+
+    @property
+    def sizes(self):
+        U, nt = C.c_uint64(), C.c_uint64()
+        check(_L.kmg_count_sizes(self._handle(), C.byref(U), None, None, C.byref(nt)))
+        sn = self.source_n
+        return U.value, U.value * sn, U.value * sn * (sn - 1) // 2
+
+    @property
+    def kmer_count(self):
+        """khash_ptr.kmer_count: k-mers that were new when added, summed over the calls"""
+        nt = C.c_uint64()
+        check(_L.kmg_count_sizes(self._handle(), None, None, None, C.byref(nt)))
+        return nt.value
+
+    def free(self):
+        if self._h:
+            _L.kmg_count_free(self._h)
+            self._h = None
+
+
 def _extract(ex_ptr) -> KmerHash:
     # extract_khash_ptr, src/kmer_hash.c:491-503
     if not isinstance(ex_ptr, KmerHash):
@@ -119,6 +148,13 @@ def _extract(ex_ptr) -> KmerHash:
     if ex_ptr.tag != KMER_HASH_TAG:
         raise ValueError("External pointer has incorrect tag")
     return ex_ptr
+
+
+def _extract_index(ex_ptr) -> KmerHash:
+    ix = _extract(ex_ptr)
+    if isinstance(ix, KmerCounts):
+        raise ValueError("this external pointer holds k-mer counts (count.kmers), not a position index")
+    return ix
 
 
 def make_kmer_hash(seq, k, do_sort=False) -> KmerHash:
@@ -181,6 +217,8 @@ def kmer_pos(ex_ptr, opt_flag, out: dict | None = None, canonical: bool = False)
     """
     ix = _extract(ex_ptr)
     opt_flag = int(opt_flag)
+    if isinstance(ix, KmerCounts):
+        return _count_table_pos(ix, opt_flag)
     out = out or {}
     U, N, P = ix.sizes
     h = ix._handle()
@@ -227,12 +265,101 @@ def kmer_pos(ex_ptr, opt_flag, out: dict | None = None, canonical: bool = False)
     return res
 
 
+def count_kmers(seq, params, hash_ptr: "KmerCounts | None" = None) -> KmerCounts:
+    """count.kmers (kmer_hash.R:43-46 -> count_kmers, src/kmer_hash.c:548-591).
+
+    params = (k, source, source_n).  Every sequence of `seq` (a string or a list of strings) that is longer than k
+    adds one to column `source` of its k-mers' counters, window rule as in make.kmer.hash; `hash_ptr=None` makes a
+    new table.  Read the table with kmer_pos(ptr, 1 + 2 + 8) as the reference does (test.R:340-347): "pos" holds
+    rows (i, count of source 0), (i, count of source 1), ...; "count" is source_n for every k-mer.  k-mers come in
+    ascending key order (the reference's is its hash table's)."""
+    params = [int(p) for p in params]
+    if len(params) != 3:
+        raise ValueError("k_r must be an integer vector of length 3")
+    k, source, source_n = params
+    if k < 1 or k > MAX_K:
+        raise ValueError("k must be a positive integer less than 1+MAX_K")
+    if source_n < 1 or source >= source_n or source < 0:
+        raise ValueError("source_n must be larger than 1 and larger than source")
+    if isinstance(seq, (str, bytes, bytearray, np.ndarray)) or hasattr(seq, "data_ptr"):
+        seq = [seq]
+    if len(seq) < 1:
+        raise ValueError("seq_r should be a character vector of length at least one")
+    if hash_ptr is None:
+        h = C.c_void_p()
+        check(_L.kmg_count_new(k, source_n, C.byref(h)))
+        hash_ptr = KmerCounts(h.value, k, source_n)
+    else:
+        if not isinstance(hash_ptr, KmerCounts):
+            raise ValueError("failed to extract kmer_hash from external pointer")
+        if hash_ptr.k != k:
+            raise ValueError("mismatch between specified k and that given in the external pointer")
+        if hash_ptr.source_n != source_n:
+            raise ValueError("mismatch between specified source_n and that of the external pointer")
+    for s in seq:
+        ptr, n, keep = _seq_buffer(s)
+        if n <= k:
+            continue
+        check(_L.kmg_count_add(hash_ptr._handle(), ptr, n, source))
+        del keep
+    return hash_ptr
+
+
+def _count_table_pos(ct: KmerCounts, opt_flag: int) -> dict:
+    U = ct.sizes[0]
+    sn, h = ct.source_n, ct._handle()
+    res = {"kmer": None, "pos": None, "pair.pos": None, "count": None}
+    if opt_flag & OPT_KMER:
+        buf = np.empty(U * (ct.k + 1), np.uint8)
+        check(_L.kmg_count_kmers_ascii(h, _out_ptr(buf)))
+        res["kmer"] = np.ascontiguousarray(buf.reshape(U, ct.k + 1)[:, :ct.k]).view(f"S{ct.k}").ravel()
+    if opt_flag & OPT_POS:
+        if U * sn > INT_MAX:
+            raise OverflowError("pos matrix extent exceeds int")
+        a = np.empty((U * sn, 2), np.int32)
+        check(_L.kmg_count_positions(h, _out_ptr(a)))
+        res["pos"] = a
+    if opt_flag & OPT_PAIRS:
+        m = np.empty((U, sn), np.int32)
+        check(_L.kmg_count_matrix(h, _out_ptr(m)))
+        ia, ib = np.triu_indices(sn, 1)
+        rows = np.empty((U, len(ia), 3), np.int32)
+        rows[:, :, 0] = np.arange(1, U + 1, dtype=np.int32)[:, None]
+        rows[:, :, 1] = m[:, ia]
+        rows[:, :, 2] = m[:, ib]
+        res["pair.pos"] = rows.reshape(-1, 3)
+    if opt_flag & OPT_COUNT:
+        res["count"] = np.full(U, sn, np.int32)
+    return res
+
+
+def kmer_spectrum(ptr, max_count: int, source: "int | None" = None) -> np.ndarray:
+    """k-mer count spectrum: spec[c] = number of k-mers seen c times, counts >= max_count pooled in spec[max_count];
+    doubles, like the reference's kmer.spec.* (count_spectrum, src/kmer_tree.c:85-99; src/kmer_hash.c:975-1038).
+    `ptr` is a count table (count_kmers; `source` picks a column, None sums them) or a position index
+    (make_kmer_hash; a k-mer's count is the length of its position list)."""
+    ix = _extract(ptr)
+    max_count = int(max_count)
+    if max_count < 1 or max_count > (1 << 30):
+        raise ValueError("Unsuitable value of max_count")
+    spec = np.zeros(max_count + 1, np.float64)
+    sp = spec.ctypes.data_as(C.POINTER(C.c_double))
+    if isinstance(ix, KmerCounts):
+        check(_L.kmg_count_spectrum(ix._handle(), -1 if source is None else int(source), max_count, sp))
+    else:
+        check(_L.kmg_index_spectrum(ix._handle(), max_count, sp))
+    return spec
+
+
 def kmer_keys(ex_ptr, canonical: bool = False) -> np.ndarray:
     """The distinct k-mers as uint64 keys in the index's order, or ascending with canonical=True (not part of
     the R API; used by tests)."""
     ix = _extract(ex_ptr)
     U, _, _ = ix.sizes
     a = np.empty(U, np.uint64)
+    if isinstance(ix, KmerCounts):
+        check(_L.kmg_count_kmers_u64(ix._handle(), _out_ptr(a)))
+        return a
     check(_L.kmg_kmers_u64(ix._handle(), _out_ptr(a)))
     return np.sort(a) if canonical else a
 
@@ -247,7 +374,7 @@ def seq_kmer_pos(ex_ptr, seq, k, *, allow_k32: bool = False, out: np.ndarray | N
     `reverse_complement=True` probes reverseComplement(seq) instead, made on the device: the second half
     of every dot plot in the reference's notebook (test.R:43-52,73); i then refers to that string.
     """
-    ix = _extract(ex_ptr)
+    ix = _extract_index(ex_ptr)
     if isinstance(seq, (list, tuple)):
         if len(seq) != 1:
             raise ValueError("seq_r should be a single sequence")
@@ -278,7 +405,7 @@ def kmer_pairs(ptr_a, ptr_b, *, out: np.ndarray | None = None) -> np.ndarray:
     inner), k-mers of `ptr_a` in ascending key order.  (The reference's own routine crashes on its
     bucket walk, test.R:330-331; this is its evident intent.)
     """
-    a, b = _extract(ptr_a), _extract(ptr_b)
+    a, b = _extract_index(ptr_a), _extract_index(ptr_b)
     st, M = C.c_void_p(), C.c_uint64()
     check(_L.kmg_join_begin(a._handle(), b._handle(), C.byref(st), C.byref(M)))
     try:

@@ -73,6 +73,16 @@ SIGNATURES = {
     "kmg_launch_count": (C.c_uint64, []),
     "kmg_selftest_lane_order": (C.c_int, [C.POINTER(C.c_uint32)]),
     "kmg_tune": (C.c_int, [C.c_char_p, C.c_int]),
+    "kmg_count_new": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
+    "kmg_count_add": (C.c_int, [vp, vp, C.c_int64, C.c_int]),
+    "kmg_count_sizes": (C.c_int, [vp, u64p, C.POINTER(C.c_int), C.POINTER(C.c_int), u64p]),
+    "kmg_count_kmers_u64": (C.c_int, [vp, vp]),
+    "kmg_count_kmers_ascii": (C.c_int, [vp, vp]),
+    "kmg_count_matrix": (C.c_int, [vp, vp]),
+    "kmg_count_positions": (C.c_int, [vp, vp]),
+    "kmg_count_spectrum": (C.c_int, [vp, C.c_int, C.c_uint32, C.POINTER(C.c_double)]),
+    "kmg_index_spectrum": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_double)]),
+    "kmg_count_free": (C.c_int, [vp]),
     "kmg_tune_get": (C.c_int64, [C.c_char_p, C.c_int64]),
     "kmg_trim": (C.c_int, []),
     "kmg_cached_bytes": (C.c_uint64, []),

@@ -355,7 +355,8 @@ struct kmg_index {
   // made on first use
   std::mutex mu;
   uint4 *hash = nullptr;        // key table of the probe (probe.cuh), made on the first query
-  uint64_t hash_bmask = 0;
+  uint64_t hash_nb = 0;         // buckets of the key table
+  int hash_hbits = 0;           // 0: bucket = hash & (nb-1); else the monotone bucket function of a grouped index (probe.cuh)
   uint32_t *multi_u = nullptr;
   uint64_t *pair_off = nullptr;
 };
@@ -421,6 +422,7 @@ struct SortPlan { int rb, passes; int bits() const { return rb * passes; } };
 // fixed up afterwards; b >= log2(N) + 5 keeps that below N/64: 32 bits (4 x 8) up to 2^27 records, 36 bits (4 x 9) beyond.
 static int g_hash_bits = 0;
 static int g_hash_rb = 0;      // kmg_tune "hash_rb": force the digit width (tuning runs)
+static int g_hash_cas = 0;     // kmg_tune "hash_cas": 1 = always build the probe's key table by CAS (tests, tuning)
 static int g_fix_cap = 0;      // kmg_tune "fix_cap": capacity of the short-group task list (0 = max(2^20, N/8)); tests shrink it
 static SortPlan grouped_plan(int64_t n_upper) {
   if (g_hash_bits > 0) {
@@ -454,6 +456,7 @@ extern "C" int kmg_tune(const char *key, int value) {
   }
   if (key && !strcmp(key, "sort_dbg")) { g_sort_dbg = (uint32_t)value; return KMG_OK; }
   if (key && !strcmp(key, "fix_cap")) { g_fix_cap = value > 0 ? value : 0; return KMG_OK; }
+  if (key && !strcmp(key, "hash_cas")) { g_hash_cas = value != 0; return KMG_OK; }
   if (key && !strcmp(key, "hash_bits")) {
     if (value != 0 && (value < 8 || value > 56 || (value % 8 && value % 9 && value % 10))) return fail(KMG_ERR_ARG, "hash_bits must be 0 (auto) or a multiple of 8, 9 or 10 in [8,56]");
     g_hash_bits = value;
@@ -1058,15 +1061,51 @@ static int ensure_hash(kmg_index *ix) {
   std::lock_guard<std::mutex> g(ix->mu);
   if (ix->hash || ix->U == 0) return KMG_OK;
   cudaStream_t s = g_ctx.stream();
+  const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(ix->U, 256), (uint64_t)g_ctx.sms * 32);
+  uint4 *slots = nullptr;
+  // grouped index: the k-mers are in ascending order of the sorted bits of their mix, which a monotone bucket function
+  // turns into ascending bucket order: the table is streamed out (one bucket per k-mer on average = load 0.5)
+  const bool stream = ix->grouped && ix->hbits >= 8 && ix->hbits <= 56 && !g_hash_cas && (ix->hbits >= 40 || ix->U <= (uint64_t(1) << ix->hbits));
+  if (stream) {
+    const uint64_t nb = std::max<uint64_t>(ix->U, 4);
+    const uint32_t ov_cap = (uint32_t)std::min<uint64_t>(ix->U / 4 + 1024, UINT32_MAX);
+    uint32_t *ov = nullptr;
+    TRY(dalloc(&slots, nb * BUCKET_SLOTS, s));
+    int rc = dalloc(&ov, (size_t)ov_cap + 1, s);
+    if (rc != KMG_OK) { dfree(slots, s); return rc; }
+    uint32_t h_ov = 0;
+    auto body = [&]() -> int {
+      CU(cudaMemsetAsync(ov + ov_cap, 0, 4, s));
+      KeyHash kt{slots, nb, ix->hbits};
+      LAUNCH("hash_stream", s, hash_stream_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, kt, ov, ov + ov_cap, ov_cap));
+      CU(cudaMemcpyAsync(&h_ov, ov + ov_cap, 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      if (h_ov > ov_cap) return KMG_OK;                  // too many crowded buckets (never seen): the CAS build below
+      if (h_ov) {
+        const unsigned g2 = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(h_ov, 256), (uint64_t)g_ctx.sms * 32);
+        LAUNCH("hash_insert", s, hash_insert_kernel<<<g2, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, kt, ov, ov + ov_cap));
+        CU(cudaStreamSynchronize(s));
+      }
+      return KMG_OK;
+    };
+    rc = body();
+    dfree(ov, s);
+    if (rc != KMG_OK) { dfree(slots, s); return rc; }
+    if (h_ov <= ov_cap) {
+      ix->hash = slots; ix->hash_nb = nb; ix->hash_hbits = ix->hbits;
+      prof_bytes("hash_stream", 12.0 * ix->U + 16.0 * BUCKET_SLOTS * nb);
+      prof_bytes("hash_insert", 28.0 * h_ov);
+      return KMG_OK;
+    }
+    dfree(slots, s);
+  }
   uint64_t cap = 4 * BUCKET_SLOTS;
   while (cap < 2 * ix->U) cap <<= 1;                          // load <= 0.5
-  uint4 *slots = nullptr;
   TRY(dalloc(&slots, cap, s));
   CU(cudaMemsetAsync(slots, 0, cap * sizeof(uint4), s));
-  const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(ix->U, 256), (uint64_t)g_ctx.sms * 32);
-  LAUNCH("hash_insert", s, hash_insert_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, KeyHash{slots, cap / BUCKET_SLOTS - 1}));
+  LAUNCH("hash_insert", s, hash_insert_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, KeyHash{slots, cap / BUCKET_SLOTS, 0}, nullptr, nullptr));
   CU(cudaStreamSynchronize(s));
-  ix->hash = slots; ix->hash_bmask = cap / BUCKET_SLOTS - 1;
+  ix->hash = slots; ix->hash_nb = cap / BUCKET_SLOTS; ix->hash_hbits = 0;
   prof_bytes("hash_insert", 12.0 * ix->U + 16.0 * ix->U);
   return KMG_OK;
 }
@@ -1097,7 +1136,7 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
     CU(cudaMemsetAsync(qs, 0, sizeof(QueryStats), s));
     CU(cudaMemsetAsync(status, 0, tiles * sizeof(Pair64), s));
     CU(cudaMemsetAsync(ticket, 0, 4, s));
-    KeyHash kt{ix->hash, ix->hash_bmask};
+    KeyHash kt{ix->hash, ix->hash_nb, ix->hash_hbits};
     TRY(dalloc(&found, (size_t)total, s));
     const unsigned ltiles = (unsigned)ceil_div<uint64_t>((uint64_t)total, PROBE_TILE);
     if (from_seq) {
@@ -1281,7 +1320,7 @@ extern "C" int kmg_join_begin(const kmg_index *a, const kmg_index *cb, kmg_join 
     CU(cudaMemsetAsync(qs, 0, sizeof(QueryStats), s));
     CU(cudaMemsetAsync(status, 0, tiles * sizeof(Pair64), s));
     CU(cudaMemsetAsync(ticket, 0, 4, s));
-    KeyHash kt{b->hash, b->hash_bmask};
+    KeyHash kt{b->hash, b->hash_nb, b->hash_hbits};
     SeqView sv{};
     LAUNCH("probe_lookup_rec", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
                                       sv, a->ukeys, (int64_t)U, nullptr, kt, found));
@@ -1867,4 +1906,250 @@ extern "C" int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L
   if (rc != KMG_OK) { kmg_shard_close(sh); return rc; }
   *out = sh;
   return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// count.kmers: per-source k-mer counts in one table
+// ------------------------------------------------------------------------------------------------
+// Replaces seq_to_counts / kmer_count_insert (src/kmer_hash.c:185-252) as called from count_kmers (:548-591): the
+// reference keeps, per distinct k-mer, an array of source_n ints in the SAME khash (kmer_pos_t.v reused as counters) and
+// bumps column `source` for every window of every sequence handed to count.kmers(seq, c(k, source, source_n), ptr).
+// Here a sequence's counts are the list lengths of its (sorted) position index -- the same windows, the same build --
+// and the table is a sorted array of distinct keys with a U x source_n count matrix; a new batch is merged in by one
+// stable sort of the concatenated key lists (table entries first) and a row-wise copy/add.
+struct kmg_counter {
+  int device = 0, k = 0, source_n = 0;
+  uint64_t U = 0, new_total = 0;     // distinct k-mers; sum over calls of the k-mers that were new (khash_ptr.kmer_count)
+  uint64_t *keys = nullptr;          // [U] ascending 2-bit keys
+  int32_t *counts = nullptr;         // [U][source_n]
+};
+
+__global__ void count_first_kernel(const uint32_t *__restrict__ ustart, uint64_t U, int source_n, int source, int32_t *__restrict__ counts) {
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x)
+    counts[u * source_n + source] = (int32_t)(ustart[u + 1] - ustart[u]);
+}
+__global__ void iota_kernel(uint32_t *p, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+// merged index over (table keys ++ batch keys): every distinct key has one or two payloads, the table's first
+__global__ void count_merge_kernel(const uint32_t *__restrict__ mstart, const uint32_t *__restrict__ mpay, uint64_t Um, uint64_t Ut,
+                                   const int32_t *__restrict__ old_counts, const uint32_t *__restrict__ bstart, int source_n, int source,
+                                   int32_t *__restrict__ counts) {
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < Um; u += (uint64_t)gridDim.x * blockDim.x) {
+    int32_t add = 0;
+    const int32_t *row = nullptr;
+    for (uint32_t j = mstart[u]; j < mstart[u + 1]; ++j) {
+      const uint32_t p = mpay[j];
+      if (p < Ut) row = old_counts + (uint64_t)p * source_n;
+      else add += (int32_t)(bstart[p - Ut + 1] - bstart[p - Ut]);
+    }
+    for (int s = 0; s < source_n; ++s) counts[u * source_n + s] = (row ? row[s] : 0) + (s == source ? add : 0);
+  }
+}
+// rows (i, count of source s) for s = 0..source_n-1: what kmer.pos(ptr, 2) returns for a count table (the reference's
+// kmer_positions walks v.a[0..v.n), src/kmer_hash.c:1108-1112, and v holds the counters)
+__global__ void count_rows_kernel(const int32_t *__restrict__ counts, uint64_t cells, int source_n, int2 *__restrict__ out) {
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (uint64_t)gridDim.x * blockDim.x)
+    out[c] = make_int2((int)(c / source_n + 1), counts[c]);
+}
+// spectrum[min(count, max_count)] += 1 over the k-mers (count_spectrum, src/kmer_tree.c:85-99); source < 0: summed over sources
+__global__ void spectrum_counts_kernel(const int32_t *__restrict__ counts, uint64_t U, int source_n, int source, uint32_t max_count,
+                                       unsigned long long *__restrict__ spec) {
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t c = 0;
+    if (source >= 0) c = (uint64_t)counts[u * source_n + source];
+    else for (int s = 0; s < source_n; ++s) c += (uint64_t)counts[u * source_n + s];
+    atomicAdd(spec + (c >= max_count ? max_count : c), 1ull);
+  }
+}
+__global__ void spectrum_index_kernel(const uint32_t *__restrict__ ustart, uint64_t U, uint32_t max_count, unsigned long long *__restrict__ spec) {
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = ustart[u + 1] - ustart[u];
+    atomicAdd(spec + (c >= max_count ? max_count : c), 1ull);
+  }
+}
+
+extern "C" int kmg_count_new(int k, int source_n, kmg_counter **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be a positive integer less than 1+MAX_K");
+  if (source_n < 1) return fail(KMG_ERR_ARG, "source_n must be larger than 1 and larger than source");
+  TRY(ctx_init());
+  kmg_counter *c = new (std::nothrow) kmg_counter();
+  if (!c) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  c->device = g_ctx.device; c->k = k; c->source_n = source_n;
+  *out = c;
+  return KMG_OK;
+}
+extern "C" int kmg_count_free(kmg_counter *c) {
+  if (!c) return KMG_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  const bool mine = g_ctx.ready && g_ctx.device == c->device;
+  if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
+  g_arena[c->device & 63].put(c->keys, nullptr, true);
+  g_arena[c->device & 63].put(c->counts, nullptr, true);
+  cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
+  delete c;
+  return KMG_OK;
+}
+static int use_counter(const kmg_counter *c) {
+  if (!c) return fail(KMG_ERR_ARG, "counter is NULL");
+  TRY(ctx_init());
+  if (c->device != g_ctx.device) return fail(KMG_ERR_ARG, "the count table lives on device %d but this thread works on device %d", c->device, g_ctx.device);
+  return KMG_OK;
+}
+
+// seq_to_counts(seq, k, hash, source, source_n) for one sequence (src/kmer_hash.c:220-252)
+extern "C" int kmg_count_add(kmg_counter *c, const char *seq, int64_t len, int source) {
+  TRY(use_counter(c));
+  if (source < 0 || source >= c->source_n) return fail(KMG_ERR_ARG, "source_n must be larger than 1 and larger than source");
+  if (len < 0 || (len > 0 && !seq)) return fail(KMG_ERR_ARG, "bad sequence pointer/length");
+  kmg_index *b = nullptr;
+  TRY(kmg_build_ordered(seq, len, c->k, KMG_ORDER_SORTED, &b));
+  if (b->U == 0) { kmg_free(b); return KMG_OK; }
+  cudaStream_t s = g_ctx.stream();
+  const int sn = c->source_n;
+  const unsigned grid_of_b = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(b->U, 256), (uint64_t)g_ctx.sms * 16);
+  uint64_t *cat_keys = nullptr;
+  uint32_t *cat_pay = nullptr;
+  int32_t *ncounts = nullptr;
+  kmg_index *m = nullptr;
+  auto body = [&]() -> int {
+    if (c->U == 0) {                                         // first batch: the table is the batch
+      TRY(dalloc(&ncounts, (size_t)b->U * sn, s));
+      CU(cudaMemsetAsync(ncounts, 0, (size_t)b->U * sn * sizeof(int32_t), s));
+      LAUNCH("count_first", s, count_first_kernel<<<grid_of_b, 256, 0, s>>>(b->ustart, b->U, sn, source, ncounts));
+      CU(cudaStreamSynchronize(s));
+      c->keys = b->ukeys; b->ukeys = nullptr;                // the batch's key array becomes the table's
+      c->counts = ncounts; ncounts = nullptr;
+      c->U = b->U; c->new_total += b->U;
+      return KMG_OK;
+    }
+    const uint64_t Ut = c->U, n = Ut + b->U;
+    if (n > (uint64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "count table would exceed 2^31-1 k-mers");
+    TRY(dalloc(&cat_keys, (size_t)n, s));
+    TRY(dalloc(&cat_pay, (size_t)n, s));
+    CU(cudaMemcpyAsync(cat_keys, c->keys, Ut * 8, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(cat_keys + Ut, b->ukeys, b->U * 8, cudaMemcpyDeviceToDevice, s));
+    LAUNCH("iota", s, iota_kernel<<<(unsigned)std::min<uint64_t>(ceil_div<uint64_t>(n, 256), (uint64_t)g_ctx.sms * 16), 256, 0, s>>>(cat_pay, n));
+    TRY(kmg_build_records(cat_keys, cat_pay, (int64_t)n, c->k, &m));      // stable: a key's table entry precedes its batch entry
+    TRY(dalloc(&ncounts, (size_t)m->U * sn, s));
+    LAUNCH("count_merge", s, count_merge_kernel<<<(unsigned)std::min<uint64_t>(ceil_div<uint64_t>(m->U, 256), (uint64_t)g_ctx.sms * 16), 256, 0, s>>>(
+                                 m->ustart, m->pos, m->U, Ut, c->counts, b->ustart, sn, source, ncounts));
+    CU(cudaStreamSynchronize(s));
+    dfree(c->keys, s); dfree(c->counts, s);
+    c->keys = m->ukeys; m->ukeys = nullptr;
+    c->counts = ncounts; ncounts = nullptr;
+    c->new_total += m->U - Ut;
+    c->U = m->U;
+    return KMG_OK;
+  };
+  const int rc = body();
+  dfree(cat_keys, s); dfree(cat_pay, s); dfree(ncounts, s);
+  if (m) kmg_free(m);
+  kmg_free(b);
+  return rc;
+}
+
+extern "C" int kmg_count_sizes(const kmg_counter *c, uint64_t *U, int *source_n, int *k, uint64_t *new_total) {
+  if (!c) return fail(KMG_ERR_ARG, "counter is NULL");
+  if (U) *U = c->U;
+  if (source_n) *source_n = c->source_n;
+  if (k) *k = c->k;
+  if (new_total) *new_total = c->new_total;
+  return KMG_OK;
+}
+extern "C" int kmg_count_kmers_u64(const kmg_counter *c, uint64_t *keys) {
+  TRY(use_counter(c));
+  if (c->U == 0) return KMG_OK;
+  if (!keys) return fail(KMG_ERR_ARG, "keys is NULL");
+  CU(cudaMemcpyAsync(keys, c->keys, c->U * 8, cudaMemcpyDefault, g_ctx.stream()));
+  CU(cudaStreamSynchronize(g_ctx.stream()));
+  return KMG_OK;
+}
+extern "C" int kmg_count_kmers_ascii(const kmg_counter *c, char *out) {
+  TRY(use_counter(c));
+  if (!out && c->U) return fail(KMG_ERR_ARG, "buf is NULL");
+  const size_t stride = (size_t)c->k + 1;
+  const int k = c->k;
+  const uint64_t *keys = c->keys;
+  const int sms = g_ctx.sms;
+  return stream_rows(c->U, stride, out, CHUNK_BYTES / stride, [=](uint64_t first, uint64_t rows, void *dst, uint64_t *, cudaStream_t s) -> int {
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(rows * stride, 256), (uint64_t)sms * 16);
+    LAUNCH("kmers_ascii", s, kmers_ascii_kernel<<<grid, 256, 0, s>>>(keys + first, rows, k, (char *)dst));
+    return KMG_OK;
+  });
+}
+// the U x source_n matrix, one row per k-mer (ascending key)
+extern "C" int kmg_count_matrix(const kmg_counter *c, int32_t *out) {
+  TRY(use_counter(c));
+  if (c->U == 0) return KMG_OK;
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  CU(cudaMemcpyAsync(out, c->counts, c->U * c->source_n * sizeof(int32_t), cudaMemcpyDefault, g_ctx.stream()));
+  CU(cudaStreamSynchronize(g_ctx.stream()));
+  return KMG_OK;
+}
+// kmer.pos(count.ptr, 2): 2 x (U * source_n) interleaved rows (i, count)
+extern "C" int kmg_count_positions(const kmg_counter *c, int32_t *out) {
+  TRY(use_counter(c));
+  const uint64_t cells = c->U * (uint64_t)c->source_n;
+  if (cells == 0) return KMG_OK;
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  const int32_t *counts = c->counts;
+  const int sn = c->source_n, sms = g_ctx.sms;
+  return stream_rows(cells, 8, out, CHUNK_BYTES / 8, [=](uint64_t first, uint64_t rows, void *dst, uint64_t *, cudaStream_t s) -> int {
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(rows, 256), (uint64_t)sms * 16);
+    // chunks start at a multiple of source_n only if rows do; index from the absolute cell
+    LAUNCH("count_rows", s, count_rows_kernel<<<grid, 256, 0, s>>>(counts, first + rows, sn, (int2 *)dst - first));
+    return KMG_OK;
+  });
+}
+
+static int spectrum_out(unsigned long long *d_spec, uint32_t max_count, double *spec, cudaStream_t s) {
+  std::vector<unsigned long long> h((size_t)max_count + 1);
+  CU(cudaMemcpyAsync(h.data(), d_spec, h.size() * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < h.size(); ++i) spec[i] = (double)h[i];
+  return KMG_OK;
+}
+// kmer spectrum of one source column (source < 0: of the summed counts): spec[min(count, max_count)] += 1 per k-mer,
+// doubles as the reference's spectra are (count_spectrum, src/kmer_tree.c:85-99; kmer_spectrum_*, src/kmer_hash.c:975-1038)
+extern "C" int kmg_count_spectrum(const kmg_counter *c, int source, uint32_t max_count, double *spec) {
+  TRY(use_counter(c));
+  if (!spec) return fail(KMG_ERR_ARG, "spec is NULL");
+  if (max_count < 1 || max_count > (1u << 30)) return fail(KMG_ERR_ARG, "Unsuitable value of max_count");
+  if (source >= c->source_n) return fail(KMG_ERR_ARG, "source out of range");
+  cudaStream_t s = g_ctx.stream();
+  unsigned long long *d = nullptr;
+  TRY(dalloc(&d, (size_t)max_count + 1, s));
+  int rc = KMG_OK;
+  if (cudaMemsetAsync(d, 0, ((size_t)max_count + 1) * 8, s) != cudaSuccess) rc = fail(KMG_ERR_CUDA, "memset failed");
+  if (rc == KMG_OK && c->U) {
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(c->U, 256), (uint64_t)g_ctx.sms * 16);
+    spectrum_counts_kernel<<<grid, 256, 0, s>>>(c->counts, c->U, c->source_n, source, max_count, d);
+  }
+  if (rc == KMG_OK) rc = spectrum_out(d, max_count, spec, s);
+  dfree(d, s);
+  return rc;
+}
+// the same for a position index: the count of a k-mer is the length of its position list
+extern "C" int kmg_index_spectrum(const kmg_index *ix, uint32_t max_count, double *spec) {
+  TRY(use_index(ix));
+  if (!spec) return fail(KMG_ERR_ARG, "spec is NULL");
+  if (max_count < 1 || max_count > (1u << 30)) return fail(KMG_ERR_ARG, "Unsuitable value of max_count");
+  cudaStream_t s = g_ctx.stream();
+  unsigned long long *d = nullptr;
+  TRY(dalloc(&d, (size_t)max_count + 1, s));
+  int rc = KMG_OK;
+  if (cudaMemsetAsync(d, 0, ((size_t)max_count + 1) * 8, s) != cudaSuccess) rc = fail(KMG_ERR_CUDA, "memset failed");
+  if (rc == KMG_OK && ix->U) {
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(ix->U, 256), (uint64_t)g_ctx.sms * 16);
+    spectrum_index_kernel<<<grid, 256, 0, s>>>(ix->ustart, ix->U, max_count, d);
+  }
+  if (rc == KMG_OK) rc = spectrum_out(d, max_count, spec, s);
+  dfree(d, s);
+  return rc;
 }

@@ -28,10 +28,6 @@ struct QueryStats {
 // size and the rate is bound by requests, 46 G/s for 32-byte requests = HBM peak in lines; an overflow
 // bucket is in the same line three times out of four and then comes from L2.
 constexpr int BUCKET_SLOTS = 2;
-struct KeyHash {
-  uint4 *slots;
-  uint64_t bmask;   // buckets - 1 (a power of two; 2 * buckets >= 2 U)
-};
 
 __device__ __forceinline__ uint64_t hash64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
@@ -39,6 +35,20 @@ __device__ __forceinline__ uint64_t hash64(uint64_t x) {
   x ^= x >> 33;
   return x;
 }
+
+// Home bucket of a key.  hbits == 0: hash64(key) & (nb - 1), nb a power of two (table of an index in ascending key order,
+// filled by 128-bit CAS).  hbits > 0: floor(low hbits bits of mix64(key) / 2^hbits * nb), any nb: MONOTONE in the order of a
+// grouped index (records sorted on those bits), so its table is written front to back by a streaming kernel.
+struct KeyHash {
+  uint4 *slots;
+  uint64_t nb;      // buckets
+  int hbits;
+  __device__ __forceinline__ uint64_t bucket(uint64_t key) const {
+    const uint64_t h = hash64(key);                        // == mix64(key)
+    return hbits ? __umul64hi(h << (64 - hbits), nb) : (h & (nb - 1));
+  }
+  __device__ __forceinline__ uint64_t next(uint64_t b) const { return b + 1 == nb ? 0 : b + 1; }
+};
 
 // compare a 16-byte slot with all-zero and swap `desired` in (one 128-bit CAS, sm_90+); true if it was empty
 __device__ __forceinline__ bool claim_slot(uint4 *slot, uint4 desired) {
@@ -54,20 +64,59 @@ __device__ __forceinline__ bool claim_slot(uint4 *slot, uint4 desired) {
   return olo == 0 && ohi == 0;
 }
 
+__device__ __forceinline__ void cas_insert(const KeyHash &kh, uint64_t key, uint32_t start, uint32_t count) {
+  const uint4 rec = make_uint4((uint32_t)key, (uint32_t)(key >> 32), start, count);
+  uint64_t b = kh.bucket(key);
+  bool placed = false;
+  while (!placed) {
+#pragma unroll
+    for (int j = 0; j < BUCKET_SLOTS; ++j)
+      if (!placed) placed = claim_slot(kh.slots + b * BUCKET_SLOTS + j, rec);
+    b = kh.next(b);
+  }
+}
+
 // Distinct keys only: one 128-bit CAS claims a slot and fills it (a stored slot is never all-zero: count >= 1).
-__global__ void hash_insert_kernel(const uint64_t *__restrict__ ukeys, const uint32_t *__restrict__ ustart, uint64_t U, KeyHash kh) {
+// `list` (optional): insert only the k-mers it names (the overflow of hash_stream_kernel).
+__global__ void hash_insert_kernel(const uint64_t *__restrict__ ukeys, const uint32_t *__restrict__ ustart, uint64_t U, KeyHash kh,
+                                   const uint32_t *__restrict__ list, const uint32_t *__restrict__ n_list) {
+  const uint64_t n = list ? (uint64_t)*n_list : U;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t u = list ? list[i] : i;
+    const uint32_t start = ustart[u];
+    cas_insert(kh, ukeys[u], start, ustart[u + 1] - start);
+  }
+}
+
+// Table of a grouped index, written front to back (no memset, no atomics): the k-mers come in ascending home-bucket order,
+// so the first k-mer of a bucket (its leader) writes the whole 32-byte bucket -- itself, the next k-mer if it shares the
+// bucket, else an empty slot -- and zero-fills the empty buckets before it; a bucket's third and later k-mers (~10 % at
+// one k-mer per bucket on average) go to `overflow` and are CAS-inserted afterwards by hash_insert_kernel, which places
+// each in the first bucket after its home that has room: exactly the table the all-CAS build gives up to slot order.
+__global__ void hash_stream_kernel(const uint64_t *__restrict__ ukeys, const uint32_t *__restrict__ ustart, uint64_t U, KeyHash kh,
+                                   uint32_t *__restrict__ overflow, uint32_t *n_overflow, uint32_t ov_cap) {
+  const uint4 zero = make_uint4(0, 0, 0, 0);
   for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t key = ukeys[u];
-    const uint32_t start = ustart[u], count = ustart[u + 1] - start;
-    const uint4 rec = make_uint4((uint32_t)key, (uint32_t)(key >> 32), start, count);
-    uint64_t b = hash64(key) & kh.bmask;
-    bool placed = false;
-    while (!placed) {
-#pragma unroll
-      for (int j = 0; j < BUCKET_SLOTS; ++j)
-        if (!placed) placed = claim_slot(kh.slots + b * BUCKET_SLOTS + j, rec);
-      b = (b + 1) & kh.bmask;
+    const uint64_t b = kh.bucket(key);
+    const int64_t bp1 = u > 0 ? (int64_t)kh.bucket(ukeys[u - 1]) : -1;
+    const int64_t bp2 = u > 1 ? (int64_t)kh.bucket(ukeys[u - 2]) : -1;
+    if (bp1 != (int64_t)b) {                               // leader of bucket b
+      const uint32_t s0 = ustart[u], s1 = ustart[u + 1];
+      uint4 second = zero;
+      if (u + 1 < U) {
+        const uint64_t kn = ukeys[u + 1];
+        if (kh.bucket(kn) == b) second = make_uint4((uint32_t)kn, (uint32_t)(kn >> 32), s1, ustart[u + 2] - s1);
+      }
+      kh.slots[b * BUCKET_SLOTS] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), s0, s1 - s0);
+      kh.slots[b * BUCKET_SLOTS + 1] = second;
+      for (int64_t g = bp1 + 1; g < (int64_t)b; ++g) { kh.slots[g * BUCKET_SLOTS] = zero; kh.slots[g * BUCKET_SLOTS + 1] = zero; }
+    } else if (bp2 == (int64_t)b) {                         // third or later k-mer of its bucket
+      const uint32_t i = atomicAdd(n_overflow, 1u);
+      if (i < ov_cap) overflow[i] = (uint32_t)u;
     }
+    if (u + 1 == U)                                         // the empty buckets after the last k-mer's
+      for (uint64_t g = b + 1; g < kh.nb; ++g) { kh.slots[g * BUCKET_SLOTS] = zero; kh.slots[g * BUCKET_SLOTS + 1] = zero; }
   }
 }
 
@@ -78,7 +127,7 @@ __device__ __forceinline__ uint2 resolve_key(const KeyHash &kh, uint64_t key, ui
     if (s0.w != 0 && s0.x == klo && s0.y == khi) return make_uint2(s0.z, s0.w);
     if (s1.w != 0 && s1.x == klo && s1.y == khi) return make_uint2(s1.z, s1.w);
     if (s0.w == 0 || s1.w == 0) return make_uint2(0u, 0u);
-    b = (b + 1) & kh.bmask;
+    b = kh.next(b);
     ld_stream_sector(kh.slots + b * BUCKET_SLOTS, s0, s1);
   }
 }
@@ -127,7 +176,7 @@ probe_lookup_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, int6
         if (mixed) key = unmix64(key);                      // records of a grouped sharded index carry mix64(key)
       }
       kk[j] = key;
-      home[j] = hash64(key) & kh.bmask;
+      home[j] = kh.bucket(key);
       if (ok[j]) ld_stream_sector(kh.slots + home[j] * BUCKET_SLOTS, s0[j], s1[j]);
     }
     uint2 r[BATCH];

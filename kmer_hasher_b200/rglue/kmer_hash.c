@@ -10,6 +10,7 @@
  *   kmer_positions(ptr, opt.flag)           replaces src/kmer_hash.c:1054-1147
  *   sequence_kmer_positions(ptr, seq, k)    replaces src/kmer_hash.c:1151-1172
  *   kmer_pair_pos(ptr.a, ptr.b)             replaces src/kmer_hash.c:1174-1203 (which crashes: test.R:330-331)
+ *   count_kmers(ptr, params, seq)           replaces src/kmer_hash.c:548-591 (count.kmers: per-source counts)
  *   R_init_kmer_hash                        replaces src/kmer_hash.c:1221-1224
  *
  * Differences a user can observe: k-mers come out in the order of a mix of their 2-bit key (ascending key
@@ -36,7 +37,8 @@ static const char *const field_names[4] = {"kmer", "pos", "pair.pos", "count"}; 
 
 /* what the external pointer addresses (the reference's khash_ptr, src/kmer_pos.h:43-48) */
 typedef struct {
-  kmg_index *index;
+  kmg_index *index;     /* make.kmer.hash: positions */
+  kmg_counter *counter; /* count.kmers: per-source counts (the reference keeps both kinds in the same khash type) */
   int k;
 } kmer_handle;
 
@@ -58,7 +60,12 @@ static kmer_handle *handle_or_error(SEXP ptr) {
       error("External pointer has incorrect tag");
     error("external pointer is NULL");
   }
-  if (!h->index) error("the k-mer index has been released");
+  if (!h->index && !h->counter) error("the k-mer index has been released");
+  return h;
+}
+static kmer_handle *index_handle_or_error(SEXP ptr) {
+  kmer_handle *h = handle_or_error(ptr);
+  if (!h->index) error("this external pointer holds k-mer counts (count.kmers), not a position index");
   return h;
 }
 
@@ -70,6 +77,10 @@ static void finalise_handle(SEXP ptr) {
   if (h->index) {
     kmg_free(h->index);
     h->index = NULL;
+  }
+  if (h->counter) {
+    kmg_count_free(h->counter);
+    h->counter = NULL;
   }
   free(h);
   R_ClearExternalPtr(ptr);
@@ -104,10 +115,113 @@ SEXP make_kmer_h_index(SEXP seq_r, SEXP k_r, SEXP sort_pos_r) {
   return ptr;
 }
 
+/* kmer.pos() of a count table: the reference's kmer_positions walks v.a[0..v.n) of every k-mer, and count.kmers
+ * keeps the source_n counters there (src/kmer_hash.c:196-205), so "pos" = rows (i, count of source 0), (i, count of
+ * source 1), ..., "count" = source_n for every k-mer, "pair.pos" = rows (i, c_a, c_b) for a < b, "kmer" as usual. */
+static SEXP count_table_positions(kmer_handle *h, unsigned flag) {
+  uint64_t U = 0;
+  int sn = 0;
+  if (kmg_count_sizes(h->counter, &U, &sn, NULL, NULL) != KMG_OK) error("kmer.pos failed: %s", kmg_last_error());
+  const uint64_t N = U * (uint64_t)sn, P = U * (uint64_t)sn * (uint64_t)(sn - 1) / 2;
+  if ((flag & (F_KMER | F_COUNT)) && U > (uint64_t)INT_MAX) error("%llu distinct k-mers do not fit an R vector", (unsigned long long)U);
+  if ((flag & F_POS) && N > (uint64_t)INT_MAX) error("%llu rows do not fit an R matrix", (unsigned long long)N);
+  if ((flag & F_PAIRS) && P > (uint64_t)INT_MAX) error("pair.pos would have %llu rows, more than an R matrix can hold (2^31-1)", (unsigned long long)P);
+  SEXP ret = PROTECT(allocVector(VECSXP, 4));
+  SEXP names = PROTECT(allocVector(STRSXP, 4));
+  for (int i = 0; i < 4; ++i) SET_STRING_ELT(names, i, mkChar(field_names[i]));
+  setAttrib(ret, R_NamesSymbol, names);
+  UNPROTECT(1);
+  const char *failed = NULL;
+  if (flag & F_KMER) {
+    const size_t stride = (size_t)h->k + 1;
+    char *buf = R_alloc(U ? U : 1, (int)stride);
+    if (kmg_count_kmers_ascii(h->counter, buf) != KMG_OK) failed = "kmer";
+    else {
+      SEXP kmers = allocVector(STRSXP, (R_xlen_t)U);
+      SET_VECTOR_ELT(ret, 0, kmers);
+      for (uint64_t u = 0; u < U; ++u) SET_STRING_ELT(kmers, (R_xlen_t)u, mkCharLen(buf + u * stride, h->k));
+    }
+  }
+  if (!failed && (flag & F_POS)) {
+    SEXP m = allocMatrix(INTSXP, 2, (int)N);
+    SET_VECTOR_ELT(ret, 1, m);
+    if (kmg_count_positions(h->counter, INTEGER(m)) != KMG_OK) failed = "pos";
+  }
+  if (!failed && (flag & F_PAIRS)) {
+    SEXP m = allocMatrix(INTSXP, 3, (int)P);
+    SET_VECTOR_ELT(ret, 2, m);
+    int *mat = (int *)R_alloc(N ? N : 1, sizeof(int));
+    if (kmg_count_matrix(h->counter, mat) != KMG_OK) failed = "pair.pos";
+    else {
+      int *o = INTEGER(m);
+      for (uint64_t u = 0; u < U; ++u)
+        for (int a = 0; a < sn; ++a)
+          for (int b = a + 1; b < sn; ++b) { *o++ = (int)(u + 1); *o++ = mat[u * sn + a]; *o++ = mat[u * sn + b]; }
+    }
+  }
+  if (!failed && (flag & F_COUNT)) {
+    SEXP v = allocVector(INTSXP, (R_xlen_t)U);
+    SET_VECTOR_ELT(ret, 3, v);
+    int *o = INTEGER(v);
+    for (uint64_t u = 0; u < U; ++u) o[u] = sn;
+  }
+  UNPROTECT(1);
+  if (failed) error("kmer.pos failed while extracting %s: %s", failed, kmg_last_error());
+  return ret;
+}
+
+/* count.kmers(seq, c(k, source, source_n), hash.ptr) -> .Call("count_kmers", hash.ptr, params, seq), kmer_hash.R:43-46;
+ * replaces src/kmer_hash.c:548-591 (and seq_to_counts / kmer_count_insert, :185-252): every sequence longer than k adds
+ * its windows to column `source` of the table; a NULL pointer makes a new table. */
+SEXP count_kmers(SEXP hash_ptr_r, SEXP params_r, SEXP seq_r) {
+  if (TYPEOF(seq_r) != STRSXP || length(seq_r) < 1) error("seq_r should be a character vector of length at least one");
+  if (TYPEOF(params_r) != INTSXP || length(params_r) != 3) error("k_r must be an integer vector of length 3");
+  const int *params = INTEGER(params_r);
+  const int k = params[0], source = params[1], source_n = params[2];
+  if (k < 1 || k > KMG_MAX_K) error("k must be a positive integer less than 1+MAX_K");
+  if (source_n < 1 || source >= source_n || source < 0) error("source_n must be larger than 1 and larger than source");
+  SEXP ptr_r = hash_ptr_r;
+  kmer_handle *h = NULL;
+  int protect_n = 0;
+  if (ptr_r == R_NilValue) {
+    h = (kmer_handle *)calloc(1, sizeof *h);
+    if (!h) error("out of memory");
+    h->k = k;
+    if (kmg_count_new(k, source_n, &h->counter) != KMG_OK) {
+      free(h);
+      error("count.kmers failed: %s", kmg_last_error());
+    }
+    SEXP tag = PROTECT(allocVector(STRSXP, 1));
+    SET_STRING_ELT(tag, 0, mkChar(KMER_HASH_TAG));
+    ptr_r = PROTECT(R_MakeExternalPtr(h, tag, R_NilValue));
+    R_RegisterCFinalizerEx(ptr_r, finalise_handle, TRUE);
+    protect_n = 2;
+  } else {
+    h = handle_or_null(hash_ptr_r);
+  }
+  if (!h) error("failed to extract kmer_hash from external pointer");
+  if (!h->counter) { UNPROTECT(protect_n); error("the external pointer holds a position index, not k-mer counts"); }
+  if (h->k != k) { UNPROTECT(protect_n); error("mismatch between specified k and that given in the external pointer"); }
+  int sn = 0;
+  kmg_count_sizes(h->counter, NULL, &sn, NULL, NULL);
+  if (sn != source_n) { UNPROTECT(protect_n); error("mismatch between specified source_n and that of the external pointer"); }
+  for (int i = 0; i < length(seq_r); ++i) {
+    SEXP s = STRING_ELT(seq_r, i);
+    if (length(s) <= k) continue;                              /* as the reference: too short to hold a k-mer */
+    if (kmg_count_add(h->counter, CHAR(s), (int64_t)length(s), source) != KMG_OK) {
+      UNPROTECT(protect_n);
+      error("count.kmers failed: %s", kmg_last_error());
+    }
+  }
+  UNPROTECT(protect_n);
+  return ptr_r;
+}
+
 SEXP kmer_positions(SEXP ptr_r, SEXP opt_flag_r) {
   kmer_handle *h = handle_or_error(ptr_r);
   if (TYPEOF(opt_flag_r) != INTSXP || length(opt_flag_r) != 1) error("opt_flag_r should be an integer vector of length 1");
   const unsigned flag = (unsigned)asInteger(opt_flag_r);
+  if (h->counter) return count_table_positions(h, flag);
 
   uint64_t U = 0, N = 0, P = 0;
   if (kmg_sizes(h->index, &U, &N, &P) != KMG_OK) error("kmer.pos failed: %s", kmg_last_error());
@@ -155,7 +269,7 @@ SEXP kmer_positions(SEXP ptr_r, SEXP opt_flag_r) {
 }
 
 SEXP sequence_kmer_positions(SEXP ptr_r, SEXP seq_r, SEXP k_r) {
-  kmer_handle *h = handle_or_error(ptr_r);
+  kmer_handle *h = index_handle_or_error(ptr_r);
   if (TYPEOF(seq_r) != STRSXP || length(seq_r) != 1) error("seq_r should be a single sequence");
   if (TYPEOF(k_r) != INTSXP || length(k_r) != 1) error("k should be an integer of length 1");
   const int k = INTEGER(k_r)[0];
@@ -182,8 +296,8 @@ SEXP sequence_kmer_positions(SEXP ptr_r, SEXP seq_r, SEXP k_r) {
 /* kmer.pairs(ptr.a, ptr.b) -> .Call("kmer_pair_pos", ...), kmer_hash.R:30-34; replaces src/kmer_hash.c:1174-1203:
  * rows (a, b) for every k-mer the two indexes share; kmer.pairs() names and transposes. */
 SEXP kmer_pair_pos(SEXP ptr_a, SEXP ptr_b) {
-  kmer_handle *a = handle_or_error(ptr_a);
-  kmer_handle *b = handle_or_error(ptr_b);
+  kmer_handle *a = index_handle_or_error(ptr_a);
+  kmer_handle *b = index_handle_or_error(ptr_b);
   kmg_join *j = NULL;
   uint64_t M = 0;
   if (kmg_join_begin(a->index, b->index, &j, &M) != KMG_OK) error("kmer.pairs failed: %s", kmg_last_error());
@@ -204,6 +318,7 @@ static const R_CallMethodDef call_methods[] = {
     {"kmer_positions", (DL_FUNC)&kmer_positions, 2},
     {"sequence_kmer_positions", (DL_FUNC)&sequence_kmer_positions, 3},
     {"kmer_pair_pos", (DL_FUNC)&kmer_pair_pos, 2},
+    {"count_kmers", (DL_FUNC)&count_kmers, 3},
     {NULL, NULL, 0}};
 
 void R_init_kmer_hash(DllInfo *info) { R_registerRoutines(info, NULL, call_methods, NULL, NULL); }

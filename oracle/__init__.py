@@ -276,11 +276,36 @@ class Reference:
         lib.ref_free_buf.argtypes = [C.c_void_p]
         lib.ref_pairs_join.restype = C.c_int64
         lib.ref_pairs_join.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_i32p)]
+        lib.ref_count_new.restype = C.c_void_p
+        lib.ref_count_new.argtypes = [C.c_int]
+        lib.ref_count_add.restype = C.c_int
+        lib.ref_count_add.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         lib.ref_digest_canonical.restype = None
         lib.ref_digest_canonical.argtypes = [C.c_void_p] + [C.POINTER(_RefDig)] * 4 + [_u64p]
         lib.ref_query_digest.restype = C.c_int64
         lib.ref_query_digest.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(_RefDig), _dblp]
         self.lib = lib
+
+    def count_kmers(self, seqs, k: int, source: int, source_n: int, table: "ReferenceIndex | None" = None) -> "ReferenceIndex":
+        """count.kmers(seq, c(k, source, source_n), hash.ptr) (kmer_hash.R:43-46 -> count_kmers, src/kmer_hash.c:548-591):
+        restated seq_to_counts on the reference's own khash (ref_count_add).  Read the table with extract():
+        'pos' rows are (i, count of source 0), (i, count of source 1), ... and 'count' is source_n everywhere."""
+        if k < 1 or k > 32:
+            raise ValueError("k must be a positive integer less than 1+MAX_K")
+        if source_n < 1 or source >= source_n:
+            raise ValueError("source_n must be larger than 1 and larger than source")
+        if table is None:
+            table = ReferenceIndex(self.lib, self.lib.ref_count_new(k), k, 0.0)
+        elif table.k != k:
+            raise ValueError("mismatch between specified k and that given in the external pointer")
+        if isinstance(seqs, (str, bytes, np.ndarray)):
+            seqs = [seqs]
+        for sq in seqs:
+            self.lib.ref_count_add(table._h, _as_bytes(sq), source, source_n)
+        U, N, P, B, W = (C.c_uint64() for _ in range(5))
+        self.lib.ref_sizes(table._h, C.byref(U), C.byref(N), C.byref(P), C.byref(B), C.byref(W))
+        table.U, table.N, table.P, table.buckets, table.new_kmers = U.value, N.value, P.value, B.value, W.value
+        return table
 
     @staticmethod
     def available() -> bool:

@@ -26,6 +26,7 @@
 #include <string.h>
 #include <time.h>
 #include "kmer_pos.h"   /* from -I/root/reference/src */
+#include "kmer_util.h"
 
 typedef struct {
   khash_ptr hp;          /* the reference's own handle struct (kmer_pos.h:43-48) */
@@ -273,6 +274,69 @@ int64_t ref_pairs_join(const ref_index *ra, const ref_index *rb, int **rows_out)
   }
   free(ord);
   return n;
+}
+
+/* ---- count.kmers ---------------------------------------------------------------
+ * seq_to_counts / kmer_count_insert live in the R glue file (kmer_hash.c:185-252, which needs R.h for its
+ * warning()), so they are RESTATED here, on the reference's own khash type and with the reference's own
+ * init_kmer / UPDATE_OFFSET / LC (kmer_util.h, kmer_util.c: called, not restated): per distinct k-mer an array
+ * of source_n ints in kmer_pos_t.v (kmer_hash.c:196-203), column `source` bumped once per window (:205), the
+ * window loop that of seq_to_hash (:236-250).  Pinned by tests/test_oracle.py: with one source the counts must
+ * equal the list lengths of the index the UNMODIFIED seq_to_hash builds from the same sequence.
+ * The result is read back through ref_extract_canonical, exactly as R's kmer.pos reads a count table (it walks
+ * v.a[0..v.n), which now holds the counters). */
+static int ref_count_insert(uint64_t kmer, khash_t(kmer_h) *hash, size_t source, size_t source_n) {
+  if (source >= source_n) return -1;
+  int ret = 0, new_kmer = 0;
+  khiter_t it = kh_get(kmer_h, hash, kmer);
+  if (it == kh_end(hash)) {
+    it = kh_put(kmer_h, hash, kmer, &ret);
+    if (it == kh_end(hash)) return -1;
+    kv_init(kh_val(hash, it).v);
+    kh_val(hash, it).kmer = kmer;
+    kh_val(hash, it).v.a = calloc(source_n, sizeof(int));
+    kh_val(hash, it).v.m = source_n;
+    kh_val(hash, it).v.n = source_n;
+    new_kmer = 1;
+  }
+  kh_val(hash, it).v.a[source]++;
+  return new_kmer;
+}
+
+ref_index *ref_count_new(int k) {
+  ref_index *ri = calloc(1, sizeof(ref_index));
+  ri->hp.k = k;
+  ri->hp.hash = kh_init(kmer_h);
+  return ri;
+}
+
+/* one sequence of count_kmers' loop (kmer_hash.c:580-587): sequences with length <= k are skipped there */
+int ref_count_add(ref_index *ri, const char *seq, int source, int source_n) {
+  const int k = ri->hp.k;
+  if ((int64_t)strlen(seq) <= (int64_t)k) return 0;
+  khash_t(kmer_h) *hash = ri->hp.hash;
+  size_t i = 0;
+  uint64_t offset = 0;
+  int word_count = 0;
+  const uint64_t mask = k < 32 ? (((uint64_t)1) << (2 * k)) - 1 : ~(uint64_t)0;
+  while (seq[i]) {
+    i = init_kmer(seq, i, &offset, k);
+    if (!seq[i]) break;
+    int r = ref_count_insert(offset & mask, hash, (size_t)source, (size_t)source_n);
+    if (r < 0) return r;
+    word_count += r;
+    while (seq[i] && LC(seq[i]) != 'n') {
+      offset = UPDATE_OFFSET(offset, seq[i]);
+      ++i;
+      r = ref_count_insert(offset & mask, hash, (size_t)source, (size_t)source_n);
+      if (r < 0) return r;
+      word_count += r;
+    }
+  }
+  if (word_count > 0) ri->hp.kmer_count += (size_t)word_count;
+  ri->n_pos = (uint64_t)kh_size(hash) * (uint64_t)source_n;                       /* rows kmer.pos(ptr, 2) returns */
+  ri->n_pairs = (uint64_t)kh_size(hash) * (uint64_t)source_n * (uint64_t)(source_n - 1) / 2;
+  return word_count;
 }
 
 /* The insertion stream of seq_to_hash, observed without touching the reference:

@@ -153,3 +153,36 @@ def test_digest_implementations_agree(reference):
     n, dq = r.query_digest(q, 12)
     assert dq == digest(r.query(q, 12)) and n == dq[0] // 2
     r.close()
+
+
+def test_restated_count_kmers_is_pinned_to_seq_to_hash(reference):
+    """seq_to_counts lives in the R glue file (needs R.h) and is restated in oracle/ref_driver.c.  Pin: with one
+    source, the count of every k-mer equals the length of its position list in the index the UNMODIFIED seq_to_hash
+    builds from the same sequence (same window rule, same keys); with several sources and calls the columns add up."""
+    from kmer_hasher_b200 import synth
+    a = synth.config_c3(80_000, tail_k=9)
+    b = synth.config_c2(60_000)
+    for k in (4, 9, 21, 32):
+        ix = reference.build(a, k)
+        lists = ix.extract(8)
+        ct = reference.count_kmers(a, k, 0, 1)
+        e = ct.extract(2 | 8)
+        assert np.array_equal(e["keys"], lists["keys"])
+        assert np.array_equal(e["pos"].reshape(-1, 2)[:, 1], lists["count"])      # (i, count) rows
+        assert (e["count"] == 1).all() and ct.new_kmers == ix.U
+        ct.close()
+        # two sources, three calls: column sums equal per-sequence list lengths
+        ct = reference.count_kmers([a, "ACGT"], k, 0, 2)                           # "ACGT" (length <= k for k >= 4) is skipped
+        ct = reference.count_kmers(b, k, 1, 2, ct)
+        ct = reference.count_kmers(b[:20_000], k, 0, 2, ct)
+        e = ct.extract(2)
+        m = dict(zip(e["keys"].tolist(), e["pos"].reshape(-1, 2, 2)[:, :, 1].tolist()))
+        ib, ib2 = reference.build(b, k), reference.build(b[:20_000], k)
+        la, lb, lb2 = (dict(zip(x["keys"].tolist(), x["count"].tolist())) for x in (lists, ib.extract(8), ib2.extract(8)))
+        assert set(m) == set(la) | set(lb)
+        for key, (c0, c1) in m.items():
+            assert c0 == la.get(key, 0) + lb2.get(key, 0) and c1 == lb.get(key, 0)
+        for x in (ix, ib, ib2, ct):
+            x.close()
+    with pytest.raises(ValueError):
+        reference.count_kmers(a, 21, 2, 2)

@@ -18,7 +18,9 @@ def test_registered_routines(R):
     with pytest.raises(RError, match="Incorrect number of arguments"):
         R.call("kmer_pair_pos", R.integer(1))
     with pytest.raises(RError, match="not in load table"):
-        R.call("count_kmers", R.integer(1), R.integer(1), R.integer(1))
+        R.call("count_kmers_fastq", R.integer(1), R.integer(1), R.integer(1))      # read counting: out of scope
+    with pytest.raises(RError, match="Incorrect number of arguments"):
+        R.call("count_kmers", R.integer(1), R.integer(1))
     with pytest.raises(RError, match="Incorrect number of arguments"):
         R.call("make_kmer_h_index", R.character("ACGT"), R.integer(2))
     with pytest.raises(RError, match="Incorrect number of arguments"):
