@@ -205,6 +205,16 @@ int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, con
 int kmg_query_received(const kmg_index *idx, const uint64_t *d_keys, const int32_t *d_i,
                        uint64_t capacity, const uint64_t *d_info, int mixed, kmg_query **st,
                        uint64_t *M);
+/* Region exchange (grouped order, k >= 21): owners are nparts EQUAL ranges of the mixed key -- uniform whatever the
+ * sequence, so nothing is sampled, counted or exchanged before the scatter.  Every source rank has its own region of
+ * region_cap slots in every owner's arrays (region r starts at r * region_cap); the scatter's last tile stores the number
+ * of records this rank sent to owner b in peer_counts[b][rank].  The owner then builds from / probes its regions. */
+int kmg_shard_scatter_ranges(const kmg_shard *sh, int nparts, int rank, void *const *peer_keys, void *const *peer_pos,
+                             void *const *peer_counts, uint64_t region_cap, int32_t pos_add);
+int kmg_build_regions(uint64_t *d_keys, uint32_t *d_pos, uint64_t region_cap, int nparts, const uint64_t *d_counts, int k,
+                      kmg_index **out);
+int kmg_query_regions(const kmg_index *idx, const uint64_t *d_keys, const int32_t *d_i, uint64_t region_cap, int nparts,
+                      const uint64_t *d_counts, kmg_query **st, uint64_t *M);
 /* device buffers other processes of the node can map (CUDA IPC); handle is 64 bytes */
 int kmg_ipc_alloc(size_t bytes, void **dptr, void *handle);
 int kmg_ipc_free(void *dptr);

@@ -62,6 +62,9 @@ SIGNATURES = {
     "kmg_shard_scatter": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_uint64, vp, C.c_int32, vp]),
     "kmg_build_received": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.POINTER(vp)]),
     "kmg_query_received": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_int, C.POINTER(vp), u64p]),
+    "kmg_shard_scatter_ranges": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_uint64, C.c_int32]),
+    "kmg_build_regions": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp, C.c_int, C.POINTER(vp)]),
+    "kmg_query_regions": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, vp, C.POINTER(vp), u64p]),
     "kmg_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), vp]),
     "kmg_ipc_free": (C.c_int, [vp]),
     "kmg_ipc_open": (C.c_int, [vp, C.POINTER(vp)]),

@@ -7,6 +7,9 @@
 #include <ctime>
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <thread>
 #include <map>
 #include <mutex>
 #include <string>
@@ -62,7 +65,7 @@ struct Ctx {
   cudaStream_t own = nullptr, copy = nullptr;   // compute stream, second stream for overlapped copies
   cudaStream_t user = nullptr;
   bool use_user = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [0..1] kernel done, [2..3] copy done, [4..6] staging slot done
   int sms = 148;
   cudaStream_t stream() const { return use_user ? user : own; }
 };
@@ -285,6 +288,7 @@ static Arena g_arena[64];
 
 // Give the cached device blocks of this thread's device back to the driver (live indexes are untouched).  An R
 // session calls it (or sets KMERGPU_CACHE_MB=0) when it wants the memory of freed indexes returned at once.
+static void stage_release();
 extern "C" int kmg_trim(void) {
   TRY(ctx_init());
   cudaStreamSynchronize(g_ctx.stream());
@@ -292,6 +296,7 @@ extern "C" int kmg_trim(void) {
   std::lock_guard<std::mutex> g(a.mu);
   for (auto &kv : a.cache) if (!kv.second.synced && kv.second.last && kv.second.last != g_ctx.stream()) cudaStreamSynchronize(kv.second.last);
   a.trim_locked();
+  stage_release();
   return KMG_OK;
 }
 extern "C" uint64_t kmg_cached_bytes(void) {
@@ -309,6 +314,110 @@ template <typename T>
 static void dfree(T *&p, cudaStream_t s) {
   if (p) g_arena[g_ctx.device & 63].put((void *)p, s, false);
   p = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pageable host buffers at PCIe speed: pinned staging + host copy threads
+// ------------------------------------------------------------------------------------------------
+// R hands the glue ordinary (pageable) memory: CHAR(STRING_ELT()) for the sequence, INTEGER(allocMatrix()) for the
+// results (src/kmer_hash.c:1127-1140 of the reference memcpy's into the same kind).  A cudaMemcpy to or from pageable
+// memory is staged by the driver in small pieces at a fraction of the link rate, so large transfers go through three
+// pinned slots instead: the DMA fills (drains) one slot while a few host threads memcpy another to (from) the caller's
+// buffer.  Worker threads touch caller memory only between entry and return of the library call that started them.
+class CopyPool {
+  struct Task { char *dst; const char *src; size_t n; int group; };
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<Task> q;
+  int pending[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<std::thread> th;
+  bool stop = false;
+  void run() {
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> l(mu);
+        cv_work.wait(l, [&] { return stop || !q.empty(); });
+        if (q.empty()) return;
+        t = q.front();
+        q.pop_front();
+      }
+      memcpy(t.dst, t.src, t.n);
+      {
+        std::lock_guard<std::mutex> l(mu);
+        if (--pending[t.group & 7] == 0) cv_done.notify_all();
+      }
+    }
+  }
+ public:
+  int threads() {
+    std::lock_guard<std::mutex> l(mu);
+    if (th.empty()) {
+      const char *e = getenv("KMERGPU_COPY_THREADS");
+      int n = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+      n = std::max(1, std::min(n, 8));
+      for (int i = 0; i < n; ++i) th.emplace_back([this] { run(); });
+    }
+    return (int)th.size();
+  }
+  void submit(int group, void *dst, const void *src, size_t n) {       // split into one piece per thread
+    const int parts = threads();
+    const size_t piece = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
+    std::lock_guard<std::mutex> l(mu);
+    for (size_t off = 0; off < n; off += piece) {
+      q.push_back(Task{(char *)dst + off, (const char *)src + off, std::min(piece, n - off), group});
+      ++pending[group & 7];
+    }
+    cv_work.notify_all();
+  }
+  void wait(int group) {
+    std::unique_lock<std::mutex> l(mu);
+    cv_done.wait(l, [&] { return pending[group & 7] == 0; });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> l(mu); stop = true; }
+    cv_work.notify_all();
+    for (auto &t : th) t.join();
+  }
+};
+static CopyPool g_pool;
+constexpr size_t STAGE_BYTES = size_t(64) << 20;
+constexpr int STAGE_SLOTS = 3;
+struct Staging {
+  std::mutex mu;                       // one staged transfer at a time per process
+  char *slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
+  int ensure() {
+    for (auto &p : slot)
+      if (!p && cudaMallocHost((void **)&p, STAGE_BYTES) != cudaSuccess) { cudaGetLastError(); return fail(KMG_ERR_NOMEM, "pinned staging allocation failed"); }
+    return KMG_OK;
+  }
+  void release() { for (auto &p : slot) { if (p) cudaFreeHost(p); p = nullptr; } }
+};
+static Staging g_stage;
+static void stage_release() { std::lock_guard<std::mutex> gs(g_stage.mu); g_stage.release(); }
+static bool staged_transfers() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("KMERGPU_STAGING"); on = !(e && e[0] == '0'); }
+  return on == 1;
+}
+
+// host (pageable) -> device through the slots: memcpy of piece c+1 overlaps the DMA of piece c
+static int staged_upload(void *d_dst, const void *h_src, size_t bytes, cudaStream_t s) {
+  std::lock_guard<std::mutex> g(g_stage.mu);
+  TRY(g_stage.ensure());
+  cudaEvent_t *ev = g_ctx.ev + 4;
+  int c = 0;
+  for (size_t off = 0; off < bytes; off += STAGE_BYTES, ++c) {
+    const int sl = c % STAGE_SLOTS;
+    const size_t n = std::min(STAGE_BYTES, bytes - off);
+    if (c >= STAGE_SLOTS) CU(cudaEventSynchronize(ev[sl]));          // the DMA that last read this slot is done
+    g_pool.submit(c, g_stage.slot[sl], (const char *)h_src + off, n);
+    g_pool.wait(c);
+    CU(cudaMemcpyAsync((char *)d_dst + off, g_stage.slot[sl], n, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(ev[sl], s));
+  }
+  CU(cudaStreamSynchronize(s));                                        // the slots are reusable by the next call
+  return KMG_OK;
 }
 
 enum PtrKind { PK_HOST_PAGEABLE, PK_HOST_PINNED, PK_DEVICE };
@@ -334,6 +443,7 @@ static int upload_seq(const void *src, int64_t len, cudaStream_t s, DevSeq *out)
   out->len = len;
   CU(cudaMemsetAsync(out->buf, 0, 16, s));
   CU(cudaMemsetAsync(out->buf + cap - 32, 0, 32, s));
+  if (len > (int64_t)(8 << 20) && staged_transfers() && ptr_kind(src) == PK_HOST_PAGEABLE) return staged_upload(out->base, src, (size_t)len, s);
   if (len > 0) CU(cudaMemcpyAsync(out->base, src, (size_t)len, cudaMemcpyDefault, s));
   return KMG_OK;
 }
@@ -369,7 +479,7 @@ struct kmg_query {
 };
 
 constexpr int HIST_THREADS = 512, HIST_ITEMS = 16, HIST_TILE = HIST_THREADS * HIST_ITEMS;
-constexpr int RLE_THREADS = 256, RLE_ITEMS = 32, RLE_TILE = RLE_THREADS * RLE_ITEMS;
+constexpr int RLE_THREADS = 256, RLE_ITEMS = 16, RLE_TILE = RLE_THREADS * RLE_ITEMS;
 constexpr int PROBE_THREADS = 256, PROBE_ITEMS = 8, PROBE_TILE = PROBE_THREADS * PROBE_ITEMS;
 constexpr int COMPACT_ITEMS = 8, COMPACT_TILE = PROBE_THREADS * COMPACT_ITEMS;
 constexpr int EMIT_THREADS = 256, EMIT_TILE = EMIT_THREADS * 8;
@@ -419,9 +529,10 @@ static void demote_rank_variant() {
 struct SortPlan { int rb, passes; int bits() const { return rb * passes; } };
 // Bits of mix64(key) the grouped build sorts on (kmg_tune "hash_bits": 0 = chosen from the record count, else a multiple
 // of 8 or 9; tests lower it to force collisions).  With b bits ~N^2 / 2^(b+1) pairs of distinct k-mers collide and are
-// fixed up afterwards; b >= log2(N) + 5 keeps that below N/64: 32 bits (4 x 8) up to 2^27 records, 36 bits (4 x 9) beyond.
+// fixed up afterwards: 36 bits (4 passes of 9) up to 2^26 records, 40 bits (5 passes of 8) beyond.
 static int g_hash_bits = 0;
 static int g_hash_rb = 0;      // kmg_tune "hash_rb": force the digit width (tuning runs)
+static int g_scatter_bitmap = 0; // kmg_tune "scatter_bitmap": 1 = region scatter ranks by bitmap match even where the one-atomic variant is valid
 static int g_hash_cas = 0;     // kmg_tune "hash_cas": 1 = always build the probe's key table by CAS (tests, tuning)
 static int g_fix_cap = 0;      // kmg_tune "fix_cap": capacity of the short-group task list (0 = max(2^20, N/8)); tests shrink it
 static SortPlan grouped_plan(int64_t n_upper) {
@@ -429,12 +540,16 @@ static SortPlan grouped_plan(int64_t n_upper) {
     const int rb = g_hash_rb > 0 && g_hash_bits % g_hash_rb == 0 ? g_hash_rb : (g_hash_bits % 8 == 0 ? 8 : 9);
     return SortPlan{rb, g_hash_bits / rb};
   }
-  if (g_hash_rb > 0) return SortPlan{g_hash_rb, n_upper <= (int64_t(1) << 27) ? (32 + g_hash_rb - 1) / g_hash_rb : (36 + g_hash_rb - 1) / g_hash_rb};
-  return n_upper <= (int64_t(1) << 27) ? SortPlan{8, 4} : SortPlan{9, 4};
+  if (g_hash_rb > 0) return SortPlan{g_hash_rb, (36 + g_hash_rb - 1) / g_hash_rb};
+  // measured on B200 (profiles/r02_sortbench_*.log): a 9-bit pass costs 1.18x an 8-bit one and 36 bits leave ~16x the colliding
+  // groups of 40, so 4 x 9 wins up to ~64 M records (2.11 vs 2.17 ms at 40 M) and 5 x 8 beyond (11.7 vs 12.1 ms at 250 M);
+  // 4 x 8 = 32 bits loses everywhere to the fix-up of its collisions, 10-bit digits cost 1.66x
+  return n_upper <= (int64_t(1) << 26) ? SortPlan{9, 4} : SortPlan{8, 5};
 }
-// is the grouped build used for this k, requested order and size?  (it has to save at least two 8-bit passes)
-static bool grouped_for(int k, int order, int64_t n_upper) {
-  return order == KMG_ORDER_GROUPED && num_passes(k) > grouped_plan(n_upper).passes + 1;
+// is the grouped build used for this k and requested order?  From k = 21 on (keys of more than 40 bits: a sort by key would
+// need 6+ passes): independent of the size, so that every rank of a sharded build decides alike.
+static bool grouped_for(int k, int order, int64_t /*n_upper*/) {
+  return order == KMG_ORDER_GROUPED && 2 * k > 40;
 }
 
 static unsigned long long *g_trace = nullptr;
@@ -457,6 +572,7 @@ extern "C" int kmg_tune(const char *key, int value) {
   if (key && !strcmp(key, "sort_dbg")) { g_sort_dbg = (uint32_t)value; return KMG_OK; }
   if (key && !strcmp(key, "fix_cap")) { g_fix_cap = value > 0 ? value : 0; return KMG_OK; }
   if (key && !strcmp(key, "hash_cas")) { g_hash_cas = value != 0; return KMG_OK; }
+  if (key && !strcmp(key, "scatter_bitmap")) { g_scatter_bitmap = value != 0; return KMG_OK; }
   if (key && !strcmp(key, "hash_bits")) {
     if (value != 0 && (value < 8 || value > 56 || (value % 8 && value % 9 && value % 10))) return fail(KMG_ERR_ARG, "hash_bits must be 0 (auto) or a multiple of 8, 9 or 10 in [8,56]");
     g_hash_bits = value;
@@ -625,7 +741,7 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
 // final_pos (optional): the last pass writes its positions there instead of into the ping-pong buffer
 // (the array the index keeps), so `pa` is meaningless afterwards.
 static int sort_tail(SortScratch &sc, SortPlan plan, int first_pass, bool has_next, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
-                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr) {
+                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr, const SegMap *seg0 = nullptr) {
   const int R = plan.passes, rb = plan.rb;
   const uint32_t mask = (1u << rb) - 1;
   for (int r = first_pass; r < R; ++r) {
@@ -634,6 +750,7 @@ static int sort_tail(SortScratch &sc, SortPlan plan, int first_pass, bool has_ne
     P.gbase = sc.gbase(r); P.hist_next = sc.hist(r + 1);
     P.status = sc.status; P.ticket = sc.ticket(r); P.epoch = (uint32_t)(r + 1);
     P.n_records = &sc.stats()->n;
+    P.seg = r == first_pass ? seg0 : nullptr;               // records in regions (owner side of a region-mode scatter)
     P.bin = DigitBin{r * rb, mask}; P.next = DigitBin{(r + 1) * rb, mask};
     P.dbg = g_sort_dbg;
     P.trace = (r == 2 && g_trace && ceil_div<int64_t>(n_upper, SORT_TILE_MIN) <= g_trace_tiles) ? g_trace : nullptr;   // trace the third pass
@@ -891,6 +1008,57 @@ static int use_index(const kmg_index *ix) {
 // Run `emit(first, rows, d_dst)` over [0,total) rows of `row_bytes` each and land them at `out`.
 // Device destinations are written in place; host destinations go through two device chunks so the
 // copy of chunk c overlaps the kernel of chunk c+1.
+// stream_rows for a large pageable destination: device chunk -> pinned slot (DMA) -> caller's buffer (host threads), the
+// three stages of consecutive chunks overlapping.
+template <class Emit>
+static int stream_rows_staged(uint64_t total, size_t row_bytes, void *out, Emit emit) {
+  std::lock_guard<std::mutex> g(g_stage.mu);
+  TRY(g_stage.ensure());
+  cudaStream_t s = g_ctx.stream(), cs = g_ctx.copy;
+  const uint64_t chunk_rows = std::max<uint64_t>(1, STAGE_BYTES / row_bytes);
+  const int64_t nchunks = (int64_t)ceil_div<uint64_t>(total, chunk_rows);
+  uint64_t *blk = nullptr;
+  char *buf[2] = {nullptr, nullptr};
+  TRY(dalloc(&blk, (size_t)ceil_div<uint64_t>(chunk_rows, EMIT_TILE), s));
+  int rc = dalloc(&buf[0], chunk_rows * row_bytes, s);
+  if (rc == KMG_OK && nchunks > 1) rc = dalloc(&buf[1], chunk_rows * row_bytes, s);
+  cudaEvent_t *ev = g_ctx.ev;                          // ev[0..1] kernel done, ev[4..6] slot filled (= device buffer free again)
+  int64_t issued = 0, retired = 0;
+  while (rc == KMG_OK && retired < nchunks) {
+    while (rc == KMG_OK && issued < nchunks && issued - retired < 2) {
+      const int64_t c = issued;
+      const int b = (int)(c & 1), sl = (int)(c % STAGE_SLOTS);
+      const uint64_t first = (uint64_t)c * chunk_rows, rows = std::min<uint64_t>(chunk_rows, total - first);
+      if (c >= STAGE_SLOTS) g_pool.wait((int)(c - STAGE_SLOTS));       // the slot's previous contents have reached the caller
+      if (c >= 2) cudaStreamWaitEvent(s, ev[4 + (int)((c - 2) % STAGE_SLOTS)], 0);   // device buffer b has been drained
+      rc = emit(first, rows, (void *)buf[b], blk, s);
+      if (rc != KMG_OK) break;
+      cudaEventRecord(ev[b], s);
+      cudaStreamWaitEvent(cs, ev[b], 0);
+      if (cudaMemcpyAsync(g_stage.slot[sl], buf[b], rows * row_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+        rc = fail(KMG_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      cudaEventRecord(ev[4 + sl], cs);
+      ++issued;
+    }
+    if (rc != KMG_OK) break;
+    const int64_t c = retired;
+    const int sl = (int)(c % STAGE_SLOTS);
+    const uint64_t first = (uint64_t)c * chunk_rows, rows = std::min<uint64_t>(chunk_rows, total - first);
+    if (cudaEventSynchronize(ev[4 + sl]) != cudaSuccess) { rc = fail(KMG_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    g_pool.submit((int)c, (char *)out + first * row_bytes, g_stage.slot[sl], rows * row_bytes);
+    ++retired;
+  }
+  for (int64_t c = std::max<int64_t>(0, retired - STAGE_SLOTS); c < retired; ++c) g_pool.wait((int)c);
+  cudaStreamSynchronize(cs);
+  cudaStreamSynchronize(s);
+  dfree(buf[0], s); dfree(buf[1], s); dfree(blk, s);
+  if (rc == KMG_OK) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(KMG_ERR_CUDA, "extraction failed: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
+
 template <class Emit>
 static int stream_rows(uint64_t total, size_t row_bytes, void *out, uint64_t chunk_rows, Emit emit) {
   if (total == 0) return KMG_OK;
@@ -904,6 +1072,10 @@ static int stream_rows(uint64_t total, size_t row_bytes, void *out, uint64_t chu
     if (rc == KMG_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(KMG_ERR_CUDA, "extraction failed: %s", cudaGetErrorString(cudaGetLastError()));
     dfree(blk, s);
     return rc;
+  }
+  if (staged_transfers() && total * row_bytes > (uint64_t)(8 << 20) && ptr_kind(out) == PK_HOST_PAGEABLE) {
+    dfree(blk, s);
+    return stream_rows_staged(total, row_bytes, out, emit);
   }
   char *buf[2] = {nullptr, nullptr};
   int rc = dalloc(&buf[0], chunk_rows * row_bytes, s);
@@ -1635,12 +1807,12 @@ __global__ void set_n_kernel(const uint64_t *info, uint64_t cap, uint64_t *n) { 
 
 // Index from the records peers scattered into (d_keys, d_pos): their number is on the device (d_info[0]).
 // Everything is sized by `capacity`; the one host synchronisation is the read of the finished index's stats.
-extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, const uint64_t *d_info, int k, int order,
-                                  kmg_index **out) {
-  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
-  *out = nullptr;
-  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
-  if (capacity == 0 || capacity > (uint64_t)INT32_MAX || !d_keys || !d_pos || !d_info) return fail(KMG_ERR_ARG, "bad record arrays");
+// Owner-side build from records that peers scattered into (d_keys, d_pos).  Two layouts:
+//   dense   (d_counts == nullptr): records 0 .. d_info[0]-1, d_info[1] != 0 if an owner overflowed (kmg_shard_scatter);
+//   regions (d_counts != nullptr): source r's records start at r * region_cap, d_counts[r] of them (kmg_shard_scatter_ranges).
+// Everything is sized by `capacity`; the one host synchronisation is the read of the finished index's stats.
+static int owner_build(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, const uint64_t *d_info, int nsegs, uint64_t region_cap,
+                       const uint64_t *d_counts, int k, int order, kmg_index **out) {
   TRY(ctx_init());
   cudaStream_t s = g_ctx.stream();
   kmg_index *ix = new (std::nothrow) kmg_index();
@@ -1651,25 +1823,34 @@ extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t ca
   SortScratch sc;
   uint64_t *ka = d_keys, *kb = nullptr;
   uint32_t *pa = d_pos, *pb = nullptr, *pfinal = nullptr;
+  SegMap *seg = nullptr;
   uint64_t h_info[2] = {0, 0};
+  SegMap h_seg{};
   const bool grouped = grouped_for(k, order, n);
   const SortPlan gp = grouped_plan(n);
   auto body = [&]() -> int {
     TRY(scratch_alloc(sc, n, s, grouped ? gp.rb : RADIX_BITS));
     TRY(dalloc(&kb, (size_t)n, s));
     TRY(dalloc(&pb, (size_t)n, s));
-    LAUNCH("set_n", s, set_n_kernel<<<1, 1, 0, s>>>(d_info, capacity, &sc.stats()->n));
     const unsigned hgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256 * 16), (int64_t)g_ctx.sms * 8);
     const int rb0 = grouped ? gp.rb : RADIX_BITS;
-    LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, &sc.stats()->n, sc.hist(0), DigitBin{0, (1u << rb0) - 1}));
+    if (d_counts) {
+      TRY(dalloc(&seg, 1, s));
+      LAUNCH("seg_prefix", s, seg_prefix_kernel<<<1, 32, 0, s>>>(d_counts, nsegs, region_cap, seg, &sc.stats()->n));
+      LAUNCH("hist_rec", s, hist_seg_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, seg, sc.hist(0), DigitBin{0, (1u << rb0) - 1}));
+      CU(cudaMemcpyAsync(&h_seg, seg, sizeof h_seg, cudaMemcpyDeviceToHost, s));
+    } else {
+      LAUNCH("set_n", s, set_n_kernel<<<1, 1, 0, s>>>(d_info, capacity, &sc.stats()->n));
+      LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, &sc.stats()->n, sc.hist(0), DigitBin{0, (1u << rb0) - 1}));
+      CU(cudaMemcpyAsync(h_info, d_info, sizeof h_info, cudaMemcpyDeviceToHost, s));
+    }
     TRY(launch_scan_hist(rb0, s, sc.hist(0), sc.gbase(0), (uint64_t *)nullptr));
     TRY(dalloc(&pfinal, (size_t)n, s));
-    CU(cudaMemcpyAsync(h_info, d_info, sizeof h_info, cudaMemcpyDeviceToHost, s));
     if (grouped) {
       // records carry mix64(key): sort on its low bits, then partition the groups in which k-mers share them.
       // The passes ping-pong (caller's arrays <-> ours); the fix-up needs the result and a scratch pair, so the
       // last pass may not divert into pfinal: copy the positions at the end instead.
-      TRY(sort_tail(sc, gp, 0, true, ka, pa, kb, pb, n, s, nullptr));
+      TRY(sort_tail(sc, gp, 0, true, ka, pa, kb, pb, n, s, nullptr, seg));
       uint32_t h_cnt[4] = {0, 0, 0, 0};
       uint32_t *fixmem = nullptr;
       int rc = fix_groups(sc, gp.bits(), ka, pa, kb, pb, n, s, h_cnt, &fixmem);
@@ -1690,7 +1871,7 @@ extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t ca
       ix->grouped = true;
       ix->hbits = gp.bits();
     } else {
-      TRY(sort_tail(sc, SortPlan{RADIX_BITS, num_passes(k)}, 0, true, ka, pa, kb, pb, n, s, pfinal));
+      TRY(sort_tail(sc, SortPlan{RADIX_BITS, num_passes(k)}, 0, true, ka, pa, kb, pb, n, s, pfinal, seg));
       TRY(finish_index(ix, sc, ka, pfinal, n, s));            // synchronises
     }
     pfinal = nullptr;
@@ -1708,11 +1889,126 @@ extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t ca
   if (pa && pa != d_pos) dfree(pa, s);
   if (pb != d_pos) dfree(pb, s);
   dfree(pfinal, s);
+  dfree(seg, s);
   scratch_free(sc, s);
-  if (rc == KMG_OK && h_info[1]) rc = fail(KMG_ERR_RANGE, "an owner received more than the exchange capacity of %llu records", (unsigned long long)capacity);
+  if (rc == KMG_OK && (h_info[1] || h_seg.overflow))
+    rc = fail(KMG_ERR_RANGE, "an owner received more than the exchange capacity of %llu records", (unsigned long long)(d_counts ? region_cap : capacity));
   if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_free(ix); return rc; }
   *out = ix;
   return KMG_OK;
+}
+
+// Index from the records peers scattered into (d_keys, d_pos): their number is on the device (d_info[0]).
+extern "C" int kmg_build_received(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, const uint64_t *d_info, int k, int order,
+                                  kmg_index **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (capacity == 0 || capacity > (uint64_t)INT32_MAX || !d_keys || !d_pos || !d_info) return fail(KMG_ERR_ARG, "bad record arrays");
+  return owner_build(d_keys, d_pos, capacity, d_info, 0, 0, nullptr, k, order, out);
+}
+// The same for a region-mode scatter (kmg_shard_scatter_ranges): nparts regions of region_cap slots, d_counts[r] records in region r.
+extern "C" int kmg_build_regions(uint64_t *d_keys, uint32_t *d_pos, uint64_t region_cap, int nparts, const uint64_t *d_counts, int k,
+                                 kmg_index **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
+  if (nparts < 1 || nparts > MAX_PEERS || region_cap == 0 || region_cap * (uint64_t)nparts > (uint64_t)INT32_MAX || !d_keys || !d_pos || !d_counts)
+    return fail(KMG_ERR_ARG, "bad record arrays");
+  if (!grouped_for(k, KMG_ORDER_GROUPED, (int64_t)(region_cap * nparts))) return fail(KMG_ERR_ARG, "region exchange carries mixed keys: k must be large enough for the grouped build");
+  return owner_build(d_keys, d_pos, region_cap * (uint64_t)nparts, nullptr, nparts, region_cap, d_counts, k, KMG_ORDER_GROUPED, out);
+}
+
+// ---- region-mode scatter: nothing is counted or exchanged beforehand ----------------------------------------------------
+__global__ void region_table_kernel(PeerPtrs pp, PeerPtrs counts /* keys[] reused as count arrays */, int nparts, int rank, uint64_t region_cap,
+                                    PeerTable *tab, uint32_t *gbase, bool announce_zero) {
+  const int b = threadIdx.x;
+  for (int o = b; o < MAX_NB; o += blockDim.x) gbase[o] = 0;
+  if (b < MAX_PEERS) {
+    tab->keys[b] = b < nparts ? pp.keys[b] : nullptr;
+    tab->pos[b] = b < nparts ? pp.pos[b] : nullptr;
+    tab->delta[b] = (int64_t)rank * (int64_t)region_cap;
+    tab->counts[b] = b < nparts ? counts.keys[b] : nullptr;
+    if (announce_zero && b < nparts) counts.keys[b][rank] = 0;    // a shard without windows still tells every owner so
+  }
+  if (b == 0) { tab->cap = region_cap; tab->rank = (uint32_t)rank; tab->region = 1; }
+}
+
+// Encode the shard, group its records by owner = one of nparts equal ranges of the mixed key, and write each group straight
+// into this rank's region of the owner's arrays (own or NVLink-mapped); the last tile stores the per-owner totals in the
+// owners' count arrays.  pos_add as in kmg_shard_scatter.
+extern "C" int kmg_shard_scatter_ranges(const kmg_shard *sh, int nparts, int rank, void *const *peer_keys, void *const *peer_pos,
+                                        void *const *peer_counts, uint64_t region_cap, int32_t pos_add) {
+  if (!sh || !peer_keys || !peer_pos || !peer_counts) return fail(KMG_ERR_ARG, "NULL argument");
+  if (nparts < 1 || nparts > MAX_PEERS || rank < 0 || rank >= nparts) return fail(KMG_ERR_ARG, "bad nparts/rank");
+  if (region_cap == 0 || region_cap * (uint64_t)nparts > (uint64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "capacity exceeds int coordinates");
+  if (!sh->hashed) return fail(KMG_ERR_ARG, "region exchange needs a shard of mixed keys (grouped order, k large enough)");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  SortScratch sc;
+  PeerTable *tab = nullptr;
+  auto body = [&]() -> int {
+    TRY(scratch_alloc(sc, sh->sv.nstarts, s, 4));
+    TRY(dalloc(&tab, 1, s));
+    PeerPtrs pp{}, pc{};
+    for (int i = 0; i < nparts; ++i) { pp.keys[i] = (uint64_t *)peer_keys[i]; pp.pos[i] = (uint32_t *)peer_pos[i]; pc.keys[i] = (uint64_t *)peer_counts[i]; }
+    LAUNCH("region_table", s, region_table_kernel<<<1, 256, 0, s>>>(pp, pc, nparts, rank, region_cap, tab, sc.gbase(0), sh->sv.nstarts == 0));
+    if (sh->sv.nstarts == 0) return KMG_OK;
+    PassParams<RangeBin, NoBin> P{};
+    P.sv = sh->sv;
+    P.gbase = sc.gbase(0); P.hist_next = nullptr;
+    P.status = sc.status; P.ticket = sc.ticket(0); P.epoch = 1;
+    P.pos_add = (uint32_t)pos_add;
+    P.hashed = 1;
+    P.peer = tab;
+    P.bin = RangeBin{(uint32_t)nparts};
+    if (rank_variant() >= 3 && !g_scatter_bitmap)
+      TRY((launch_pass_cfg<PassCfg<256, 24, 2, 3, 4, 4>, true, RangeBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
+    else
+      TRY((launch_pass_cfg<PassCfg<256, 24, 2, 0, 8, 4>, true, RangeBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
+    prof_bytes("scatter_peer", (double)sh->sv.avail + 12.0 * (double)sh->sv.nstarts);
+    return KMG_OK;
+  };
+  int rc = body();
+  dfree(tab, s);
+  scratch_free(sc, s);
+  return rc;
+}
+
+// match the (mixed key, i) records of a region-mode scatter: compacted into dense arrays, then as kmg_query_received
+extern "C" int kmg_query_regions(const kmg_index *ix, const uint64_t *d_keys, const int32_t *d_i, uint64_t region_cap, int nparts,
+                                 const uint64_t *d_counts, kmg_query **st, uint64_t *M) {
+  if (!st) return fail(KMG_ERR_ARG, "st is NULL");
+  *st = nullptr;
+  if (nparts < 1 || nparts > MAX_PEERS || region_cap == 0 || region_cap * (uint64_t)nparts > (uint64_t)INT32_MAX || !d_keys || !d_i || !d_counts)
+    return fail(KMG_ERR_ARG, "bad record arrays");
+  TRY(use_index(ix));
+  cudaStream_t s = g_ctx.stream();
+  const uint64_t capacity = region_cap * (uint64_t)nparts;
+  SegMap *seg = nullptr;
+  uint64_t *dk = nullptr, *dn = nullptr;
+  uint32_t *di = nullptr;
+  SegMap h_seg{};
+  auto body = [&]() -> int {
+    TRY(dalloc(&seg, 1, s));
+    TRY(dalloc(&dn, 1, s));
+    TRY(dalloc(&dk, (size_t)capacity, s));
+    TRY(dalloc(&di, (size_t)capacity, s));
+    LAUNCH("seg_prefix", s, seg_prefix_kernel<<<1, 32, 0, s>>>(d_counts, nparts, region_cap, seg, dn));
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(region_cap, 256), (uint64_t)g_ctx.sms * 8);
+    LAUNCH("seg_compact", s, seg_compact_kernel<<<grid, 256, 0, s>>>(d_keys, (const uint32_t *)d_i, seg, dk, di));
+    CU(cudaMemcpyAsync(&h_seg, seg, sizeof h_seg, cudaMemcpyDeviceToHost, s));
+    SeqView sv{};
+    return query_common(ix, false, sv, dk, (const int32_t *)di, (int64_t)capacity, st, M, dn, true);   // synchronises
+  };
+  int rc = body();
+  dfree(seg, s); dfree(dn, s); dfree(dk, s); dfree(di, s);
+  if (rc == KMG_OK && h_seg.overflow) {
+    kmg_query_free(*st);
+    *st = nullptr;
+    return fail(KMG_ERR_RANGE, "an owner received more than the exchange capacity of %llu records", (unsigned long long)region_cap);
+  }
+  return rc;
 }
 
 // ---- exchange buffers that other processes on the node can map (CUDA IPC over NVLink) ---------------------
@@ -1869,7 +2165,7 @@ extern "C" int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L
   if (!out) return fail(KMG_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (k < 1 || k > KMG_MAX_K) return fail(KMG_ERR_K, "k must be in [1,32]");
-  if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || !d_allpack || (world > 1 && !d_splitters))
+  if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || !d_allpack)      // d_splitters may be NULL: fixed owner ranges
     return fail(KMG_ERR_ARG, "bad world/rank/pack arguments");
   const int64_t per = (L + world - 1) / world;
   const int64_t s0 = std::min<int64_t>((int64_t)rank * per, L), s1 = std::min<int64_t>((int64_t)(rank + 1) * per, L);
@@ -1897,7 +2193,7 @@ extern "C" int kmg_shard_open_packed(const void *d_own, int64_t n_own, int64_t L
     int64_t nstarts = std::min<int64_t>(s1, L - k + 1) - s0;
     sh->sv.base = sh->ds.base; sh->sv.nstarts = nstarts > 0 ? nstarts : 0; sh->sv.avail = avail; sh->sv.s0 = s0; sh->sv.L = L; sh->sv.k = k;
     if (s0 + sh->sv.nstarts > (int64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "positions exceed int");
-    if (world > 1)
+    if (world > 1 && d_splitters)
       LAUNCH("select_splitters", s, select_splitters_kernel<<<ceil_div(n_samples * world, 256), 256, 0, s>>>(
                                         (const uint8_t *)d_allpack, pack_bytes, n_samples, world, d_splitters));
     return KMG_OK;

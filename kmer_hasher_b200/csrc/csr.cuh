@@ -40,28 +40,41 @@ rle_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos, 
   }
   const uint64_t w0 = q0 + (uint64_t)warp * (32 * ITEMS);
   uint64_t key[ITEMS];
+  uint32_t p[ITEMS];
   uint32_t heads = 0, before[ITEMS], running = 0;
   uint64_t carry = 0;                                  // key just before this warp item (lane 0's predecessor)
   uint32_t pcarry = 0;                                 // and its position
   bool bad = false;
+  // all loads first (independent, all in flight), then the shuffle chain
   if (lane == 0 && w0 > 0 && w0 < n) { carry = ld_stream_u64(keys + w0 - 1); pcarry = ld_stream_u32(pos + w0 - 1); }
+  if (q0 + TILE <= n) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) key[i] = ld_stream_u64(keys + w0 + i * 32 + lane);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) p[i] = ld_stream_u32(pos + w0 + i * 32 + lane);
+  } else {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const uint64_t idx = w0 + i * 32 + lane;
+      key[i] = idx < n ? ld_stream_u64(keys + idx) : 0;
+      p[i] = idx < n ? ld_stream_u32(pos + idx) : 0;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint64_t idx = w0 + i * 32 + lane;
     const bool ok = idx < n;
-    key[i] = ok ? ld_stream_u64(keys + idx) : 0;
-    const uint32_t p = ok ? ld_stream_u32(pos + idx) : 0;
     uint64_t prev = __shfl_up_sync(FULL, key[i], 1);
-    uint32_t pprev = __shfl_up_sync(FULL, p, 1);
+    uint32_t pprev = __shfl_up_sync(FULL, p[i], 1);
     if (lane == 0) { prev = carry; pprev = pcarry; }
     const bool head = ok && (idx == 0 || key[i] != prev);
-    bad |= ok && !head && p <= pprev;                  // same k-mer as the record before: its position must be larger
+    bad |= ok && !head && p[i] <= pprev;               // same k-mer as the record before: its position must be larger
     const unsigned bal = __ballot_sync(FULL, head);
     before[i] = running + __popc(bal & lanemask_lt());
     running += __popc(bal);
     if (head) heads |= 1u << i;
     carry = __shfl_sync(FULL, key[i], 31);             // lane 0 uses it next round
-    pcarry = __shfl_sync(FULL, p, 31);
+    pcarry = __shfl_sync(FULL, p[i], 31);
   }
   if (__any_sync(FULL, bad) && lane == 0) st->unstable = 1;
   if (lane == 0) s_wsum[warp] = running;

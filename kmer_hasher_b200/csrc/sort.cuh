@@ -60,6 +60,13 @@ struct HashDigitBin {
   uint32_t mask = RADIX - 1;
   __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(mix64(key) >> shift) & mask; }
 };
+// owner of a record of the grouped sharded build: G equal ranges of the mixed key (records carry mix64(key), which is
+// uniform whatever the sequence's composition: no sampling, no splitters, balanced by construction)
+struct RangeBin {
+  static constexpr bool CHEAP = true;
+  uint32_t nparts;
+  __device__ __forceinline__ uint32_t operator()(uint64_t h) const { return (uint32_t)__umul64hi(h, (uint64_t)nparts); }
+};
 struct NoBin {
   static constexpr bool CHEAP = true;
   __device__ __forceinline__ uint32_t operator()(uint64_t) const { return 0; }
@@ -72,7 +79,18 @@ struct PeerTable {
   uint64_t *keys[MAX_PEERS];
   uint32_t *pos[MAX_PEERS];
   int64_t delta[MAX_PEERS];   // (this rank's first slot in owner b's arrays) - (first index of bin b in this rank's stream)
-  uint64_t cap;               // records each destination array can hold
+  uint64_t cap;               // records each destination array can hold (region mode: each source's region of it)
+  // region mode (kmg_shard_scatter_ranges): every source has its own fixed region of every owner's arrays, so nothing has
+  // to be counted or exchanged before the scatter; the last tile tells owner b how many records it got from this rank
+  uint64_t *counts[MAX_PEERS];  // owner b's received-count array (indexed by source rank), or all null
+  uint32_t rank, region;
+};
+// Record source made of `nsegs` regions of `stride` slots each, region r holding prefix[r+1] - prefix[r] records from its
+// start: what an owner receives from a region-mode scatter.  Logical record q lives at q + r * stride - prefix[r].
+struct SegMap {
+  uint64_t prefix[MAX_PEERS + 1];
+  uint64_t stride;
+  uint32_t nsegs, overflow;     // overflow: some source sent more than a region holds (its excess was dropped)
 };
 
 template <class BinFn, class NextFn>
@@ -91,6 +109,7 @@ struct PassParams {
   uint32_t hashed;            // FROM_SEQ: records carry mix64(key) instead of the key (grouped build)
   uint32_t pos_add;           // FROM_SEQ: added to the 1-based start (k-1 turns it into the 1-based end of a query window)
   const PeerTable *peer;      // PEER: per-bin destination arrays (own or NVLink-mapped peer memory)
+  const SegMap *seg;          // record source in regions (owner side of a region-mode scatter), or nullptr
   unsigned long long *trace;  // tuning runs only: 8 clock64 stamps per tile, or nullptr
   uint32_t dbg;               // tuning runs only (wrong results): 1 no look-back wait, 2 no global stores
   BinFn bin;
@@ -134,6 +153,7 @@ struct PassSmem {
   uint32_t next[NB];
   uint32_t scratch[32];
   uint32_t tile;
+  SegMap seg;                                            // segmented record source only
   PeerTable peer;                                        // PEER mode only
   TileCodes<FROM_SEQ ? TILE : 16> tc;
 };
@@ -223,11 +243,18 @@ __device__ __forceinline__ void st_status(uint64_t *p, const uint64_t (&w)[BPT])
   }
 }
 
+// physical - logical index of logical record q of a segmented source
+__device__ __forceinline__ int64_t seg_shift(const SegMap &sg, int64_t q) {
+  uint32_t r = 0;
+  while (r + 1 < sg.nsegs && (uint64_t)q >= sg.prefix[r + 1]) ++r;
+  return (int64_t)(r * sg.stride) - (int64_t)sg.prefix[r];
+}
+
 // One tile.  FULL: every slot of the tile holds a valid record (no predicates on the hot path).
 template <class Cfg, bool FROM_SEQ, bool FULL, class BinFn, class NextFn, bool HAS_NEXT, bool PEER>
 __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, PassSmem<Cfg, FROM_SEQ> &sm,
                                           const uint32_t tile, const int64_t q0, const int64_t n_in,
-                                          const uint32_t (&gbase)[Cfg::BPT], const bool special) {
+                                          const uint32_t (&gbase)[Cfg::BPT], const bool special, const int64_t src_shift) {
   using S = PassSmem<Cfg, FROM_SEQ>;
   constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS, ITEMS = Cfg::ITEMS, WARPS = S::WARPS, NB = Cfg::NB, BPT = Cfg::BPT;
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -251,13 +278,15 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
         if (tile_valid<TILE>(P.sv, sm.tc, q0, t, special)) valid |= 1u << i;
     }
   } else {
-    const uint64_t *ksrc = P.keys_in + q0 + t0;
+    // src_shift: physical - logical index (0 for a dense source; uniform over a FULL tile of a segmented one)
+    const uint64_t *ksrc = P.keys_in + q0 + t0 + (FULL ? src_shift : 0);
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if constexpr (FULL) key[i] = ld_stream_u64(ksrc + i * 32);
       else {
         key[i] = 0;
-        if (q0 + t0 + i * 32 < n_in) { key[i] = ld_stream_u64(ksrc + i * 32); valid |= 1u << i; }
+        const int64_t q = q0 + t0 + i * 32;
+        if (q < n_in) { key[i] = ld_stream_u64(ksrc + i * 32 + (P.seg ? seg_shift(sm.seg, q) : 0)); valid |= 1u << i; }
       }
     }
   }
@@ -376,8 +405,10 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
   } else {
     uint32_t val[ITEMS];
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i)
-      val[i] = (FULL || ((valid >> i) & 1u)) ? ld_stream_u32(P.pos_in + q0 + t0 + i * 32) : 0;
+    for (int i = 0; i < ITEMS; ++i) {
+      if constexpr (FULL) val[i] = ld_stream_u32(P.pos_in + q0 + t0 + i * 32 + src_shift);
+      else val[i] = ((valid >> i) & 1u) ? ld_stream_u32(P.pos_in + q0 + t0 + i * 32 + (P.seg ? seg_shift(sm.seg, q0 + t0 + i * 32) : 0)) : 0;
+    }
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i)
       if (FULL || ((valid >> i) & 1u)) sm.pos[rk[i]] = val[i];
@@ -435,9 +466,12 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     }
 #pragma unroll
     for (int q = 0; q < BPT; ++q) {
-      int64_t go = (int64_t)gbase[q] + (int64_t)excl[q] - (int64_t)lstart[q];
-      if constexpr (PEER) go += b0 + q < MAX_PEERS ? sm.peer.delta[b0 + q] : 0;
+      const int64_t go = (int64_t)gbase[q] + (int64_t)excl[q] - (int64_t)lstart[q];   // index in this rank's stream of bin b - tile slot
       sm.goff[b0 + q] = (int32_t)go;
+      if constexpr (PEER) {                                // region mode: the last tile reports this rank's total to each owner
+        if (sm.peer.region && q0 + TILE >= n_in && b0 + q < MAX_PEERS && sm.peer.counts[b0 + q])
+          sm.peer.counts[b0 + q][sm.peer.rank] = excl[q] + cnt[q];
+      }
     }
   }
   __syncthreads();
@@ -450,11 +484,16 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     if (FULL || s < (int)tile_count) {
       const uint64_t kk = sm.keys[s];
       const uint32_t b = P.bin(kk);
-      const int dst = sm.goff[b] + s;
+      int64_t dst = sm.goff[b] + s;
       uint64_t *kout = P.keys_out;
       uint32_t *pout = P.pos_out;
       bool room = true;
-      if constexpr (PEER) { kout = sm.peer.keys[b]; pout = sm.peer.pos[b]; room = (uint64_t)dst < sm.peer.cap; }
+      if constexpr (PEER) {
+        kout = sm.peer.keys[b]; pout = sm.peer.pos[b];
+        const int64_t local = dst;
+        dst += sm.peer.delta[b];
+        room = (uint64_t)(sm.peer.region ? local : dst) < sm.peer.cap;
+      }
       if (room && !(P.dbg & 2u)) {
         kout[dst] = kk;
         if constexpr (FROM_SEQ) pout[dst] = (uint32_t)(P.sv.s0 + q0 + 1) + P.pos_add + sm.pos[s];   // 1-based start (+ pos_add)
@@ -493,26 +532,37 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   if constexpr (HAS_NEXT)
     for (int b = tid; b < NB; b += THREADS) sm.next[b] = 0;
   if constexpr (PEER) {
-    static_assert(sizeof(PeerTable) % 8 == 0, "copied as 64-bit words");
+    static_assert(sizeof(PeerTable) % 8 == 0 && sizeof(SegMap) % 8 == 0, "copied as 64-bit words");
     if (tid < sizeof(PeerTable) / 8) reinterpret_cast<uint64_t *>(&sm.peer)[tid] = reinterpret_cast<const uint64_t *>(P.peer)[tid];
   }
   uint32_t gbase[BPT];                                   // bin bases: a few KB, L2-resident
 #pragma unroll
   for (int q = 0; q < BPT; ++q) gbase[q] = (NB >= THREADS || tid < NB) ? __ldg(P.gbase + tid * BPT + q) : 0;
+  if constexpr (!FROM_SEQ) {
+    if (P.seg && tid < sizeof(SegMap) / 8) reinterpret_cast<uint64_t *>(&sm.seg)[tid] = reinterpret_cast<const uint64_t *>(P.seg)[tid];
+  }
   const int64_t n_in = FROM_SEQ ? P.sv.nstarts : (int64_t)*P.n_records;
   __syncthreads();
   const uint32_t tile = sm.tile;
   const int64_t q0 = (int64_t)tile * TILE;
   if (q0 >= n_in) return;
+  int64_t src_shift = 0;
+  bool seg_uniform = true;                               // segmented source: does the whole tile lie in one region?
+  if constexpr (!FROM_SEQ) {
+    if (P.seg) {
+      src_shift = seg_shift(sm.seg, q0);
+      seg_uniform = q0 + TILE <= n_in && seg_shift(sm.seg, q0 + TILE - 1) == src_shift;
+    }
+  }
   if (P.trace && tid == 0) P.trace[(size_t)tile * 8] = (unsigned long long)t_start;
 
   bool special = false;
   if constexpr (FROM_SEQ) special = tile_pack<TILE, THREADS>(P.sv, q0, sm.tc);
   const bool touches_end = FROM_SEQ && (P.sv.s0 + q0 + TILE + P.sv.k > P.sv.L);
-  if (q0 + TILE <= n_in && !special && !touches_end)
-    pass_tile<Cfg, FROM_SEQ, true, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special);
+  if (q0 + TILE <= n_in && !special && !touches_end && seg_uniform)
+    pass_tile<Cfg, FROM_SEQ, true, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special, src_shift);
   else
-    pass_tile<Cfg, FROM_SEQ, false, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special);
+    pass_tile<Cfg, FROM_SEQ, false, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special, 0);
 
   if constexpr (HAS_NEXT) {
     __syncthreads();
@@ -685,13 +735,23 @@ hist_seq_kernel(const SeqView sv, uint32_t *hist, BinFn bin) {
     const int t0 = tid * ITEMS;
     const uint64_t kmask = key_mask(sv.k);
     uint64_t key = tile_key<TILE>(tc, t0, sv.k);
+    // the ITEMS - 1 bases that roll in (tile positions t0 + k .. t0 + k + ITEMS - 2) span at most two packed words: take
+    // them into a register once instead of one shared-memory read per window
+    static_assert(ITEMS <= 17, "incoming bases fit two 16-base words");
+    const int p0 = t0 + sv.k;
+    const uint64_t inc = ((uint64_t(tc.codes[p0 >> 4]) << 32) | tc.codes[(p0 >> 4) + 1]) << (2 * (p0 & 15));
+    if (!special && q0 + TILE <= sv.nstarts && sv.s0 + q0 + TILE + sv.k <= sv.L) {     // every window of the tile is valid
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      if (i > 0) {
-        const int p = t0 + i + sv.k - 1;
-        key = ((key << 2) | ((tc.codes[p >> 4] >> (30 - 2 * (p & 15))) & 3u)) & kmask;
+      for (int i = 0; i < ITEMS; ++i) {
+        if (i > 0) key = ((key << 2) | ((inc >> (64 - 2 * i)) & 3u)) & kmask;
+        atomicAdd(&sh[bin(key)], 1u);
       }
-      if (tile_valid<TILE>(sv, tc, q0, t0 + i, special)) atomicAdd(&sh[bin(key)], 1u);
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        if (i > 0) key = ((key << 2) | ((inc >> (64 - 2 * i)) & 3u)) & kmask;
+        if (tile_valid<TILE>(sv, tc, q0, t0 + i, special)) atomicAdd(&sh[bin(key)], 1u);
+      }
     }
   }
   __syncthreads();
@@ -715,6 +775,55 @@ hist_rec_kernel(const uint64_t *keys, int64_t n_host, const uint64_t *n_dev, uin
   for (int b = threadIdx.x; b < MAX_NB; b += THREADS) {
     uint32_t c = sh[b];
     if (c) atomicAdd(hist + b, c);
+  }
+}
+
+// The same over a segmented record source (see SegMap).
+template <int THREADS, class BinFn>
+__global__ void __launch_bounds__(THREADS)
+hist_seg_kernel(const uint64_t *keys, const SegMap *seg, uint32_t *hist, BinFn bin) {
+  __shared__ uint32_t sh[MAX_NB];
+  for (int b = threadIdx.x; b < MAX_NB; b += THREADS) sh[b] = 0;
+  __syncthreads();
+  const uint32_t nsegs = seg->nsegs;
+  for (uint32_t r = 0; r < nsegs; ++r) {
+    const int64_t n = (int64_t)(seg->prefix[r + 1] - seg->prefix[r]);
+    const uint64_t *src = keys + (uint64_t)r * seg->stride;
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS)
+      atomicAdd(&sh[bin(ld_stream_u64(src + i))], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < MAX_NB; b += THREADS) {
+    uint32_t c = sh[b];
+    if (c) atomicAdd(hist + b, c);
+  }
+}
+
+// counts (per source) -> SegMap; *n = records held; counts above the region size are clamped and flagged
+__global__ void seg_prefix_kernel(const uint64_t *__restrict__ counts, int nsegs, uint64_t stride, SegMap *seg, uint64_t *n) {
+  if (threadIdx.x == 0) {
+    uint64_t run = 0;
+    uint32_t over = 0;
+    for (int r = 0; r < MAX_PEERS; ++r) {
+      seg->prefix[r] = run;
+      if (r < nsegs) { uint64_t c = counts[r]; if (c > stride) { c = stride; over = 1; } run += c; }
+    }
+    seg->prefix[MAX_PEERS] = run;
+    seg->stride = stride; seg->nsegs = (uint32_t)nsegs; seg->overflow = over;
+    *n = run;
+  }
+}
+// dense copy of a segmented (key, payload) source
+__global__ void seg_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay, const SegMap *seg,
+                                   uint64_t *__restrict__ okeys, uint32_t *__restrict__ opay) {
+  const uint32_t nsegs = seg->nsegs;
+  for (uint32_t r = 0; r < nsegs; ++r) {
+    const int64_t n = (int64_t)(seg->prefix[r + 1] - seg->prefix[r]);
+    const uint64_t src = (uint64_t)r * seg->stride, dst = seg->prefix[r];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      okeys[dst + i] = ld_stream_u64(keys + src + i);
+      opay[dst + i] = ld_stream_u32(pay + src + i);
+    }
   }
 }
 

@@ -82,12 +82,12 @@ class CudaEngine:
         self._lib.check(self.L.kmg_shard_pack(own.data_ptr(), own.numel(), k, n_samples, order, pack.data_ptr()))
         return pack
 
-    def shard_open_packed(self, own, L, world, rank, k, n_samples, allpack, order=0):
+    def shard_open_packed(self, own, L, world, rank, k, n_samples, allpack, order=0, splitters=True):
         h = C.c_void_p()
-        spl = torch.empty(max(world - 1, 1), dtype=torch.int64, device=self.device)
+        spl = torch.empty(max(world - 1, 1), dtype=torch.int64, device=self.device) if splitters else None
         self._lib.check(self.L.kmg_shard_open_packed(own.data_ptr(), own.numel(), L, world, rank, k, n_samples, order,
-                                                     allpack.data_ptr(), C.byref(h), spl.data_ptr()))
-        return h, spl[:world - 1]
+                                                     allpack.data_ptr(), C.byref(h), spl.data_ptr() if splitters else None))
+        return h, (spl[:world - 1] if splitters else None)
 
     def shard_close(self, h):
         self.L.kmg_shard_close(h)
@@ -128,6 +128,34 @@ class CudaEngine:
             self.L.kmg_query_free(st)
         return rows
 
+    # ---- region exchange: owners = equal ranges of the mixed key, nothing counted or exchanged before the scatter ----
+    def shard_scatter_ranges(self, h, nparts, rank, slot, region_cap, pos_add):
+        self._lib.check(self.L.kmg_shard_scatter_ranges(h, nparts, rank, slot.peer_keys, slot.peer_pos, slot.peer_counts,
+                                                        region_cap, pos_add))
+
+    def build_regions(self, slot, region_cap, nparts, k):
+        from . import KmerHash
+        h = C.c_void_p()
+        self._lib.check(self.L.kmg_build_regions(slot.keys, slot.pos, region_cap, nparts, slot.counts, k, C.byref(h)))
+        return KmerHash(h.value, k)
+
+    def query_regions(self, index, slot, region_cap, nparts, count_only=False):
+        st, M = C.c_void_p(), C.c_uint64()
+        self._lib.check(self.L.kmg_query_regions(index._handle(), slot.keys, slot.pos, region_cap, nparts, slot.counts,
+                                                 C.byref(st), C.byref(M)))
+        if count_only:
+            self.L.kmg_query_free(st)
+            return int(M.value)
+        rows = torch.empty((M.value, 2), dtype=torch.int32, device=self.device)
+        try:
+            self._lib.check(self.L.kmg_query_emit(st, rows.data_ptr()))
+        finally:
+            self.L.kmg_query_free(st)
+        return rows
+
+    def positions_base(self, index, i_base, out):
+        self._lib.check(self.L.kmg_positions_base(index._handle(), i_base, out.data_ptr()))
+
     def query_records(self, index, keys, coords, n):
         st, M = C.c_void_p(), C.c_uint64()
         self._lib.check(self.L.kmg_query_records(index._handle(), keys.data_ptr(), coords.data_ptr(), n,
@@ -149,7 +177,7 @@ class PeerUnavailable(RuntimeError):
 
 class _Slot:
     """One set of receive arrays: this rank's (keys, pos) and every rank's, as the scatter sees them."""
-    __slots__ = ("keys", "pos", "peer_keys", "peer_pos")
+    __slots__ = ("keys", "pos", "counts", "peer_keys", "peer_pos", "peer_counts")
 
 
 class PeerExchange:
@@ -164,25 +192,29 @@ class PeerExchange:
         L, lib = engine.L, engine._lib
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         self._own, self._opened = [], []
-        handles = torch.zeros(4 * 64, dtype=torch.uint8)
+        # region exchange: every source rank has its own region of region_cap slots in every owner's arrays
+        self.region_cap = self.capacity // max(world, 1)
+        NB = 6                                               # per slot: keys, pos, received counts
+        sizes = [self.capacity * 8, self.capacity * 4, 16 * 8] * 2
+        handles = torch.zeros(NB * 64, dtype=torch.uint8)
         ok = True
         try:
-            for i in range(4):                               # slot0 keys, slot0 pos, slot1 keys, slot1 pos
+            for i in range(NB):                              # slot0 keys, pos, counts, slot1 keys, pos, counts
                 p, hbuf = C.c_void_p(), (C.c_ubyte * 64)()
-                lib.check(L.kmg_ipc_alloc(self.capacity * (8 if i % 2 == 0 else 4), C.byref(p), hbuf))
+                lib.check(L.kmg_ipc_alloc(sizes[i], C.byref(p), hbuf))
                 self._own.append(p.value)
                 handles[i * 64:(i + 1) * 64] = torch.frombuffer(bytearray(hbuf), dtype=torch.uint8)
         except lib.KmgError:
             ok = False
         mine = handles.to(engine.device)
-        allh = torch.empty(world * 4 * 64, dtype=torch.uint8, device=engine.device)
+        allh = torch.empty(world * NB * 64, dtype=torch.uint8, device=engine.device)
         dist.all_gather_into_tensor(allh, mine, group=group)
-        allh = allh.cpu().numpy().reshape(world, 4, 64)
-        ptrs = [[0] * 4 for _ in range(world)]
+        allh = allh.cpu().numpy().reshape(world, NB, 64)
+        ptrs = [[0] * NB for _ in range(world)]
         if ok:
             try:
                 for r in range(world):
-                    for i in range(4):
+                    for i in range(NB):
                         if r == rank:
                             ptrs[r][i] = self._own[i]
                         else:
@@ -206,9 +238,10 @@ class PeerExchange:
         self.slots = []
         for sidx in range(2):
             sl = _Slot()
-            sl.keys, sl.pos = self._own[2 * sidx], self._own[2 * sidx + 1]
-            sl.peer_keys = (C.c_void_p * world)(*[ptrs[r][2 * sidx] for r in range(world)])
-            sl.peer_pos = (C.c_void_p * world)(*[ptrs[r][2 * sidx + 1] for r in range(world)])
+            sl.keys, sl.pos, sl.counts = self._own[3 * sidx], self._own[3 * sidx + 1], self._own[3 * sidx + 2]
+            sl.peer_keys = (C.c_void_p * world)(*[ptrs[r][3 * sidx] for r in range(world)])
+            sl.peer_pos = (C.c_void_p * world)(*[ptrs[r][3 * sidx + 1] for r in range(world)])
+            sl.peer_counts = (C.c_void_p * world)(*[ptrs[r][3 * sidx + 2] for r in range(world)])
             self.slots.append(sl)
         self._turn = 0
         self._token = torch.zeros(1, dtype=torch.int32, device=engine.device)
@@ -220,6 +253,12 @@ class PeerExchange:
     def barrier(self):
         """Device-side: every rank's scatter has finished before any rank reads what it received."""
         dist.all_reduce(self._token, group=self.group)
+
+    def agree(self, status: int) -> int:
+        """The worst status any rank reports (a collective): what to do next is decided together, never by one rank alone."""
+        t = torch.tensor([int(status)], dtype=torch.int32, device=self.engine.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
 
     def close(self):
         torch.cuda.synchronize()
@@ -333,6 +372,31 @@ class ShardedIndex:
         return int(sum(self.U_all[:self.rank]))
 
     @property
+    def row_offset(self):                                 # first row of this owner's slice of the global pos matrix
+        return int(sum(self.N_all[:self.rank]))
+
+    def kmer_pos(self, flag: int = 2 | 8, out: dict | None = None) -> dict:
+        """kmer.pos of the sharded index, this owner's slice (SURVEY.md 8e "Extraction"): the k-mer number i is GLOBAL
+        (owners in rank order: i = local number + distinct k-mers of the owners before), so the owners' slices written at
+        `row_offset` / `i_offset` into one matrix are the index's kmer.pos.  Collective on first use (sizes are gathered).
+        out: optional preallocated {"pos": (N_local, 2) int32, "count": (U_local,) int32} (device or host)."""
+        import kmer_hasher_b200 as kh
+        U, N, _ = self.local.sizes
+        i_base = self.i_offset
+        out = out or {}
+        res = {"pos": None, "count": None, "i_offset": i_base, "row_offset": self.row_offset}
+        if flag & 2:
+            a = out.get("pos")
+            if a is None:
+                a = torch.empty((max(N, 1), 2), dtype=torch.int32, device=self.engine.device)
+            ptr = a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
+            self.engine._lib.check(self.engine.L.kmg_positions_base(self.local._handle(), i_base, ptr))
+            res["pos"] = a[:N]
+        if flag & 8:
+            res["count"] = kh.kmer_pos(self.local, 8, out={"count": out["count"]} if "count" in out else None)["count"]
+        return res
+
+    @property
     def U_total(self):
         return int(sum(self.U_all))
 
@@ -430,21 +494,93 @@ def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerE
         xchg.barrier()
         ev("barrier")
         from ._lib import KmgError
+        status = 0
         try:
             local = engine.build_received(slot, xchg.capacity, info, k, order)
         except KmgError as e:
-            if e.code != -3:
+            if e.code not in (-3, -7):
                 raise
-            local = None
+            local, status = None, -e.code
     finally:
         engine.shard_close(sh)
     ev("built")
-    if local is None:          # an owner overflowed; every rank saw the same flag (it is computed from the shared
-        return sharded_build(own, L, k, engine, group)       # count matrix), so all take the general path together
+    # -3: an owner overflowed or its fix-up lists did (the latter is local to one rank); -7: the position-order check
+    # failed on one device.  The ranks agree on the worst status and act together: a rank must never enter the general
+    # path's collectives alone.
+    worst = xchg.agree(status)
+    if worst:
+        if local is not None:
+            local.free()
+        if worst == 7:                                      # that device now ranks by bitmap match: same path again
+            return sharded_build_p2p(own, L, k, engine, xchg, group, n_samples, order)
+        return sharded_build(own, L, k, engine, group)
     ix = ShardedIndex(local, k, rank, world, None, None, None, engine, splitters_dev=spl, group=group)
     ix.mixed = engine.L.kmg_index_order(local._handle()) == 0   # owner ranges are those of the mixed key
     ix.order = order
     return ix
+
+
+def ranges_supported(k: int, order: int = 0) -> bool:
+    """Region exchange carries mixed keys: the grouped build's domain (make.kmer.hash default order, k >= 21)."""
+    return order == 0 and k >= 21
+
+
+def sharded_build_ranges(own_bytes, L: int, k: int, engine, xchg, group=None) -> ShardedIndex:
+    """The sharded build for the grouped order (k >= 21): owners are `world` EQUAL ranges of the mixed key, which is uniform
+    whatever the sequence's composition, so nothing is sampled, counted or exchanged before the records move.  Per build:
+    ONE small all-gather (halo bytes), the fused encode + partition + scatter over NVLink into this rank's own region of
+    every owner's arrays (kmg_shard_scatter_ranges; its last tile leaves the per-owner counts with the owners), a
+    one-word all-reduce as the barrier, the owner build straight from the regions (kmg_build_regions), and one status
+    all-reduce so that every rank takes the same path if any owner's region overflowed."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    own = own_bytes if isinstance(own_bytes, torch.Tensor) else engine.upload(np.asarray(own_bytes, np.uint8))
+    pack = engine.shard_pack(own, k, 2, 0)                     # halo bytes (the two sample keys are not used)
+    allpack = torch.empty(world * pack.numel(), dtype=torch.uint8, device=engine.device)
+    dist.all_gather_into_tensor(allpack, pack, group=group)
+    sh, _ = engine.shard_open_packed(own, L, world, rank, k, 2, allpack, 0, splitters=False)
+    from ._lib import KmgError
+    status, local = 0, None
+    try:
+        slot = xchg.next_slot()
+        engine.shard_scatter_ranges(sh, world, rank, slot, xchg.region_cap, 0)
+        xchg.barrier()
+        try:
+            local = engine.build_regions(slot, xchg.region_cap, world, k)
+        except KmgError as e:
+            if e.code not in (-3, -7):
+                raise
+            status = -e.code
+    finally:
+        engine.shard_close(sh)
+    worst = xchg.agree(status)
+    if worst:
+        if local is not None:
+            local.free()
+        if worst == 7:                                         # a device switched to the bitmap rank variant: once more
+            return sharded_build_ranges(own, L, k, engine, xchg, group)
+        return sharded_build(own, L, k, engine, group)         # a region overflowed (a huge repeat): the exact-size path
+    ix = ShardedIndex(local, k, rank, world, None, None, None, engine, group=group)
+    ix.mixed, ix.ranges, ix.order = True, True, 0
+    return ix
+
+
+def sharded_query_ranges(index: ShardedIndex, own_query_bytes, Lq: int, k: int, xchg, group=None, count_only: bool = False):
+    """seq.kmer.pos against an index built by sharded_build_ranges: query (mixed key, i) records go to the key's owner
+    through the same region scatter; each owner returns its (i,j) rows ordered by i then j."""
+    engine = index.engine
+    world, rank = index.world, index.rank
+    own = own_query_bytes if isinstance(own_query_bytes, torch.Tensor) else engine.upload(np.asarray(own_query_bytes, np.uint8))
+    pack = engine.shard_pack(own, k, 2, 0)
+    allpack = torch.empty(world * pack.numel(), dtype=torch.uint8, device=engine.device)
+    dist.all_gather_into_tensor(allpack, pack, group=group)
+    sh, _ = engine.shard_open_packed(own, Lq, world, rank, k, 2, allpack, 0, splitters=False)
+    try:
+        slot = xchg.next_slot()
+        engine.shard_scatter_ranges(sh, world, rank, slot, xchg.region_cap, k - 1)     # 1-based END (src/kmer_pos.c:127)
+        xchg.barrier()
+        return engine.query_regions(index.local, slot, xchg.region_cap, world, count_only)
+    finally:
+        engine.shard_close(sh)
 
 
 def sharded_query_p2p(index: ShardedIndex, own_query_bytes, Lq: int, k: int, xchg: PeerExchange, group=None,
@@ -509,31 +645,101 @@ def sharded_query(index: ShardedIndex, own_query_bytes, Lq: int, k: int, group=N
 # ---------------------------------------------------------------------------------------------------------
 # bench.py's N>1 leg
 # ---------------------------------------------------------------------------------------------------------
+MASK64 = (1 << 64) - 1
+
+
+def _allreduce_u64(vals, dev):
+    """Sum of 64-bit values over the ranks, mod 2^64 (halves summed separately: no reliance on overflow behaviour)."""
+    halves = []
+    for v in vals:
+        halves += [v & 0xFFFFFFFF, (v >> 32) & 0xFFFFFFFF]
+    t = torch.tensor(halves, dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    h = t.cpu().tolist()
+    return [((h[2 * i + 1] << 32) + h[2 * i]) & MASK64 for i in range(len(vals))]
+
+
+def sharded_parity_sums(ix: ShardedIndex):
+    """Order-independent sums of a sharded index over all owners (a collective): U, N, sum of keys, sum key * count,
+    sum key * pos (mod 2^64) -- the numbers tests/golden/fullsize.json holds for the reference's index of the same
+    sequence ('keys'[1], 'bind') -- plus whether every owner's position lists ascend."""
+    import kmer_hasher_b200 as kh
+    dev = ix.engine.device
+    U, N, _ = ix.local.sizes
+    keys = torch.empty(max(U, 1), dtype=torch.int64, device=dev)
+    ix.engine._lib.check(ix.engine.L.kmg_kmers_u64(ix.local._handle(), keys.data_ptr()))
+    keys = keys[:U]
+    cnt = torch.empty(max(U, 1), dtype=torch.int32, device=dev)
+    pos = torch.empty((max(N, 1), 2), dtype=torch.int32, device=dev)
+    kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos, "count": cnt})
+    cnt, pos = cnt[:U].to(torch.int64), pos[:N]
+    ksum = int(keys.sum().item()) & MASK64
+    b0 = int((keys * cnt).sum().item()) & MASK64
+    b1 = 0
+    ordered = True
+    step = 1 << 26
+    for a in range(0, N, step):
+        rows = pos[a:a + step + 1]
+        b1 = (b1 + int((keys[rows[:step, 0].to(torch.int64) - 1] * rows[:step, 1].to(torch.int64)).sum().item())) & MASK64
+        same = rows[1:, 0] == rows[:-1, 0]
+        ordered &= bool((rows[1:, 1][same] > rows[:-1, 1][same]).all()) and bool((rows[1:, 0] >= rows[:-1, 0]).all())
+    tot = _allreduce_u64([U, N, ksum, b0, b1, 0 if ordered else 1], dev)
+    return {"U": tot[0], "N": tot[1], "keys_sum": tot[2], "bind": [tot[3], tot[4]], "lists_ascending": tot[5] == 0}
+
+
 def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
+    import json
+    import os
     import kmer_hasher_b200 as kh
     from . import synth
+    from bench import ClockSampler, config_of, METRIC
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = torch.device("cuda", torch.cuda.current_device())
     engine = CudaEngine(dev)
-    # weak scaling: every rank owns L bases of an (N x L)-base sequence; shards are independent draws
-    Ltot = L * world
+    strong = args.scaling == "strong"
+    Ltot = L if strong else L * world
     if Ltot > 2**31 - 2:
         raise SystemExit("global sequence exceeds the reference's int coordinates")
-    own_pin = kh.pinned_empty(L, np.uint8)
-    synth.generate(L, 0xC2 + 7919 * rank, repeat=0.30, tandem=0.10, homo=0.05, lower=0.20, out=own_pin)
-    own_host = torch.from_numpy(own_pin)                   # page-locked by kmg_host_alloc: async DMA source
+    s0, s1, _, _ = shard_bounds(Ltot, world, rank, k)
+    n_own = s1 - s0
+    own_pin = kh.pinned_empty(max(n_own, 1), np.uint8)
+    seq_all = None
+    if strong:                                              # ONE sequence, cut `world` ways: every rank generates it and keeps its slice
+        seq_all = synth.config_c2(L) if w["gen"] == "c2" else synth.config_c3(L)
+        own_pin[:n_own] = seq_all[s0:s1]
+    else:                                                   # weak: every rank draws its own L bases of an (N x L)-base sequence
+        (synth.config_c2 if w["gen"] == "c2" else synth.config_c3)(n_own, out=own_pin, seed=(0xC2 if w["gen"] == "c2" else 0xC3) + 7919 * rank)
+    own_host = torch.from_numpy(own_pin)[:n_own]            # page-locked by kmg_host_alloc: async DMA source
     own_dev = own_host.to(dev)
 
+    per = (Ltot + world - 1) // world
+    region_cap = int(per / world * 1.3) + 65536
     try:
-        xchg = PeerExchange(engine, int(L * 1.25) + 4096)  # receive arrays mapped into every rank (NVLink P2P)
+        xchg = PeerExchange(engine, region_cap * world)    # receive arrays mapped into every rank (NVLink P2P)
     except PeerUnavailable:
         xchg = None                                        # every rank lands here together: NCCL all-to-all path
+    use_ranges = xchg is not None and ranges_supported(k)
 
     def build(own):
+        if use_ranges:
+            return sharded_build_ranges(own, Ltot, k, engine, xchg)
         return sharded_build_p2p(own, Ltot, k, engine, xchg) if xchg is not None else sharded_build(own, Ltot, k, engine)
     ix = build(own_dev)
     U, N, _ = ix.local.sizes
     ntot = ix.N_total
+    used_ranges = bool(ix.ranges)
+    # ---- parity of the sharded index against the reference's digests of the same sequence (strong scaling only) ----
+    parity = None
+    gpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fullsize.json")
+    if strong and os.path.exists(gpath):
+        gold = json.load(open(gpath)).get(w.get("golden", ""), None)
+        if gold and gold.get("bases") == L and "bind" in gold:
+            got = sharded_parity_sums(ix)
+            parity = {"ok": bool(got["U"] == gold["U"] and got["N"] == gold["N"] and got["keys_sum"] == gold["keys"][1]
+                                 and got["bind"] == list(gold["bind"]) and got["lists_ascending"]),
+                      "what": "U, N, sum of keys, sum key*count, sum key*pos (mod 2^64) over all owners == the reference engine's "
+                              "(tests/golden/fullsize.json, made by tests/golden/make_fullsize.py); every owner's position lists ascend",
+                      "got": got, "want": {"U": gold["U"], "N": gold["N"], "keys_sum": gold["keys"][1], "bind": list(gold["bind"])}}
     ix.free()
     pos_dev = torch.empty((max(N, 1), 2), dtype=torch.int32, device=dev)
     cnt_dev = torch.empty(max(U, 1), dtype=torch.int32, device=dev)
@@ -541,12 +747,12 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
 
     def step_device():
         ix = build(own_dev)
-        kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos_dev, "count": cnt_dev})
+        ix.kmer_pos(2 | 8, out={"pos": pos_dev, "count": cnt_dev})      # this owner's slice, global k-mer numbers
         ix.free()
 
     def step_e2e():
         ix = build(own_host.to(dev, non_blocking=True))
-        kh.kmer_pos(ix.local, 2 | 8, out={"pos": pos_pin, "count": cnt_pin})
+        ix.kmer_pos(2 | 8, out={"pos": pos_pin, "count": cnt_pin})
         ix.free()
 
     def timed(fn, n):
@@ -566,7 +772,6 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     kh.profile(enable=True, reset=True)
     kh.profile(reset=True)
     l0 = kh.launch_count()
-    from bench import ClockSampler
     with ClockSampler(dev.index or 0) as clk:
         ms = timed(step_device, steps)
     launches = kh.launch_count() - l0
@@ -576,32 +781,30 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
         step_e2e()
     ms_e2e = timed(step_e2e, steps)
 
-    # ---- probe leg (seq.kmer.pos, weak scaling): every rank holds 10 Mbp of the query; windows are routed to the
-    #      k-mer's owner by the same fused scatter, matched there (lookups + compaction + row count, as at N=1)
+    # ---- probe leg (BASELINE config 4, strong scaling): the query is cut `world` ways, windows are routed to the k-mer's
+    #      owner by the same fused scatter, matched there, and the (i,j) rows are emitted on the owners
     probe = None
-    if xchg is not None and not getattr(args, "no_probe", False):
-        Lq = min(10_000_000, L // 4)
-        q = synth.generate(Lq, 0xC4 + 31 * rank)
-        rng = np.random.default_rng(4 + rank)
-        src = np.asarray(own_pin)
-        for _ in range(Lq // 50_000):                          # sprinkle 2 kb copies of this rank's index sequence
-            a, b = int(rng.integers(0, L - 2000)), int(rng.integers(0, Lq - 2000))
-            q[b:b + 2000] = src[a:a + 2000]
-        q_dev = torch.from_numpy(q).to(dev)
+    if use_ranges and strong and not getattr(args, "no_probe", False):
+        Lq = w["Lq"]
+        q_all = synth.config_c4_query(seq_all, Lq)
+        q0, q1, _, _ = shard_bounds(Lq, world, rank, k)
+        q_dev = torch.from_numpy(np.ascontiguousarray(q_all[q0:q1])).to(dev)
         ixq = build(own_dev)
-        rows = [0]
+        rows = [None]
 
         def probe_step():
-            rows[0] = sharded_query_p2p(ixq, q_dev, Lq * world, k, xchg, count_only=True)
+            rows[0] = sharded_query_ranges(ixq, q_dev, Lq, k, xchg)
         for _ in range(3):
             probe_step()
         ms_q = timed(probe_step, max(3, steps // 3))
-        tot_rows = torch.tensor([rows[0]], dtype=torch.int64, device=dev)
+        tot_rows = torch.tensor([rows[0].shape[0]], dtype=torch.int64, device=dev)
         dist.all_reduce(tot_rows)
-        probe = {"metric": "kmers_queried_per_s", "value": world * (Lq - k + 1) / (ms_q * 1e-3), "unit": "k-mers/s",
-                 "query_bases": Lq * world, "rows": int(tot_rows.item()), "ms": ms_q,
-                 "what": "sharded seq.kmer.pos: halo, owner counts, fused scatter over NVLink, lookups + compaction + row count on the owners"}
+        probe = {"metric": "kmers_queried_per_s", "value": (Lq - k + 1) / (ms_q * 1e-3), "unit": "k-mers/s",
+                 "query_bases": Lq, "rows": int(tot_rows.item()), "ms": ms_q,
+                 "what": "sharded seq.kmer.pos (c4 query cut N ways): halo, fused scatter of (mixed key, i) records over NVLink, "
+                         "lookups + compaction + scan + row emission on the owners (rows stay on the owners' devices)"}
         ixq.free()
+        del q_all
     sizes = torch.tensor([N, U], dtype=torch.int64, device=dev)
     all_sizes = [torch.empty_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
@@ -618,19 +821,28 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
                 "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src, "launches": int(sp[1]),
                 "avg_launch_ms": sp[0] / max(sp[1], 1), "algo_bytes_per_launch": sp[2] / max(sp[1], 1)}
     kernels = {n: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for n, v in sorted(prof.items())}
-    exchanged = 12.0 * ntot / world * (world - 1) / world     # bytes leaving each GPU per step (uniform keys)
-    return {"metric": "kmers_indexed_per_s", "value": ntot / (ms * 1e-3), "unit": "k-mers/s", "n_gpus": world,
-            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    exchanged = 12.0 * ntot / world * (world - 1) / world     # bytes leaving each GPU per step (uniform owners)
+    sc_ms = prof.get("scatter_peer", (0, 0, 0))[0] / steps
+    path = ("written straight into equal mixed-key ranges' owners over NVLink by the partitioning pass (peer memory, per-source regions: "
+            "no counting, no all-to-all)" if used_ranges else
+            "written straight into the key-range owners' arrays over NVLink by the partitioning pass (peer memory, no all-to-all)"
+            if xchg is not None else "routed to key-range owners by one NCCL all-to-all (peer memory unavailable)")
+    return {"metric": METRIC, "value": ntot / (ms * 1e-3), "unit": "k-mers/s", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": w["name"] + f" per GPU; {world} shards of one {Ltot}-base sequence, (key,pos) records "
-                       + ("written straight into the key-range owners' arrays over NVLink by the partitioning pass (peer memory, no all-to-all)"
-                        if xchg is not None else "routed to key-range owners by one NCCL all-to-all (peer memory unavailable)"), "k": k, "bases": Ltot, "kmers": int(ntot),
-                       "per_rank_kmers": all_sizes[:, 0].tolist(), "per_rank_distinct": all_sizes[:, 1].tolist(),
-                       "l2": "inputs_exceed_l2"},
-            "e2e": {"value": ntot / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(L * world),
+            "config": config_of(w, k, L),
+            "detail": {"sharding": (f"ONE {Ltot}-base sequence cut into {world} shards with k-1 bases of overlap" if strong else
+                                    f"{world} shards of {L} bases each of one {Ltot}-base sequence") + "; (key,pos) records " + path,
+                       "bases_total": Ltot, "kmers": int(ntot), "per_rank_kmers": all_sizes[:, 0].tolist(),
+                       "per_rank_distinct": all_sizes[:, 1].tolist(), "l2": "inputs_exceed_l2"},
+            "parity_checked": parity,
+            "e2e": {"value": ntot / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(Ltot),
                     "d2h_bytes_per_step": int((8 * all_sizes[:, 0] + 4 * all_sizes[:, 1]).sum()), "ms_per_step": ms_e2e,
-                    "what": "per rank: pinned host shard -> device, sharded build, kmer_pos(2|8) into pinned host arrays"},
+                    "what": "per rank: pinned host shard -> device, sharded build, kmer_pos(2|8) of the owner's slice into pinned host arrays"},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": None, "probe": probe,
-            "exchange": {"bytes_per_gpu_per_step": exchanged, "what": "12-byte records leaving each GPU over NVLink (estimate, uniform owners)",
-                         "kernel": "scatter_peer", "ms_per_step": (prof.get("scatter_peer", (0, 0, 0))[0] / steps)},
+            "exchange": {"bytes_per_gpu_per_step": exchanged, "what": "12-byte records leaving each GPU over NVLink (uniform owners)",
+                         "kernel": "scatter_peer", "ms_per_step": sc_ms,
+                         "nvlink_GBps": exchanged / (sc_ms * 1e-3) / 1e9 if sc_ms else None,
+                         "nvlink_frac": exchanged / (sc_ms * 1e-3) / 1e9 / 900.0 if sc_ms else None,
+                         "nvlink_peak": "900 GB/s per direction per GPU (NVLink 5)"},
             "kernels": kernels}

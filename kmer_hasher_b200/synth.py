@@ -56,17 +56,17 @@ def make_query(ref: np.ndarray, Lq: int, seed: int, *, unrelated=0.2, sub=0.01, 
 
 
 # ---- the BASELINE.json configurations, scalable by `scale` for tests -----------------
-def config_c2(L: int = 40_000_000, out=None) -> np.ndarray:
+def config_c2(L: int = 40_000_000, out=None, seed: int = 0xC2) -> np.ndarray:
     """40 Mbp repeat-rich, no N (index at k=32)."""
-    return generate(L, 0xC2, repeat=0.30, tandem=0.10, homo=0.05, lower=0.20, out=out)
+    return generate(L, seed, repeat=0.30, tandem=0.10, homo=0.05, lower=0.20, out=out)
 
 
-def config_c3(L: int = 250_000_000, tail_k: int = 0, out=None) -> np.ndarray:
+def config_c3(L: int = 250_000_000, tail_k: int = 0, out=None, seed: int = 0xC3) -> np.ndarray:
     """250 Mbp chromosome with N gaps (index at k=21; also C4's index at k=32).  Tandem arrays and
     homopolymer runs are kept short (microsatellite scale) so that the C4 dot plot stays below the
     2^31-1 rows an R matrix can hold; config 2 carries the heavy satellite arrays instead."""
     scale = L / 250_000_000
-    return generate(L, 0xC3, repeat=0.30, tandem=0.02, homo=0.0005, lower=0.20, tandem_len_min=100,
+    return generate(L, seed, repeat=0.30, tandem=0.02, homo=0.0005, lower=0.20, tandem_len_min=100,
                     tandem_len_max=2000, homo_len_max=60,
                     n_gaps=max(1, int(60 * scale)), gap_min=10, gap_max=max(10, int(500_000 * scale)),
                     n_single=max(1, int(2000 * scale)), tail_k=tail_k, out=out)

@@ -347,7 +347,7 @@ def test_peer_scatter_single_process(kh, oracle, world, k, L, order):
     # halo + splitter sample in one exchange (kmg_shard_pack -> "all-gather" -> kmg_shard_open_packed)
     ns = 512 if L > 1000 else 4
     owns = [eng.upload(seq[min(r * per, L):min((r + 1) * per, L)]) for r in range(world)]
-    mixed = order == 0 and k >= 25                          # owners then hold ranges of the mixed key
+    mixed = order == 0 and k >= 21                          # owners then hold ranges of the mixed key (grouped build: k >= 21)
     packs = [eng.shard_pack(o, k, ns, order) for o in owns]
     allpack = torch.cat(packs)
     handles, spls = [], []
@@ -659,3 +659,96 @@ def test_grouped_build_falls_back_when_the_task_list_overflows(kh, oracle):
     finally:
         _lib.check(L.kmg_tune(b"hash_bits", 0))
         _lib.check(L.kmg_tune(b"fix_cap", 0))
+
+
+@pytest.mark.parametrize("world,k,L", [(2, 32, 500_000), (4, 27, 300_000), (3, 21, 500_000), (8, 32, 2_000_000), (8, 32, 100), (5, 24, 23)])
+def test_region_exchange_single_process(kh, oracle, world, k, L):
+    """The region exchange of the grouped sharded build (kmg_shard_scatter_ranges / kmg_build_regions /
+    kmg_query_regions) with the ranks played one after another on one GPU: owners are equal ranges of the mixed key,
+    every source writes into its own region of every owner's arrays, the scatter's last tile leaves the counts with
+    the owners.  The owners' indexes together must be the reference's index; sharded extraction numbers k-mers globally."""
+    import ctypes as C
+    import torch
+    from kmer_hasher_b200 import dist as kdist, synth, _lib
+    L_ = _lib.load()
+    dev = torch.device("cuda", 0)
+    eng = kdist.CudaEngine(dev)
+    seq = synth.config_c3(L, tail_k=k) if L > 1000 else synth.generate(L, 11, n_single=2)
+    per = (L + world - 1) // world
+    if L > 1000:
+        seq[per - 2:per + 1] = np.frombuffer(b"nAC", np.uint8)      # breaker at the first cut
+        seq[3000:3000 + 40_000 // world] = ord("A")                  # a homopolymer: one k-mer, one owner, many copies
+    whole = oracle.build(seq, k)
+    want = whole.extract(2 | 8)
+    owns = [eng.upload(seq[min(r * per, L):min((r + 1) * per, L)]) for r in range(world)]
+    packs = [eng.shard_pack(o, k, 2, 0) for o in owns]
+    allpack = torch.cat(packs)
+    handles = [eng.shard_open_packed(owns[r], L, world, r, k, 2, allpack, 0, splitters=False)[0] for r in range(world)]
+
+    def exchange(hs, region_cap, pos_add):
+        cap = region_cap * world
+        keys = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(world)]
+        pos = [torch.zeros(cap, dtype=torch.int32, device=dev) for _ in range(world)]
+        cnts = [torch.full((16,), -1, dtype=torch.int64, device=dev) for _ in range(world)]
+        slots = []
+        for r in range(world):
+            sl = kdist._Slot()
+            sl.keys, sl.pos, sl.counts = keys[r].data_ptr(), pos[r].data_ptr(), cnts[r].data_ptr()
+            sl.peer_keys = (C.c_void_p * world)(*[t.data_ptr() for t in keys])
+            sl.peer_pos = (C.c_void_p * world)(*[t.data_ptr() for t in pos])
+            sl.peer_counts = (C.c_void_p * world)(*[t.data_ptr() for t in cnts])
+            slots.append(sl)
+            eng.shard_scatter_ranges(hs[r], world, r, sl, region_cap, pos_add)
+        torch.cuda.synchronize()
+        return slots, (keys, pos, cnts)
+
+    region_cap = int(per / world * 1.5) + 50_000
+    slots, keep = exchange(handles, region_cap, 0)
+    sent = torch.stack(keep[2])[:, :world].cpu().numpy()            # [owner][source]
+    assert sent.min() >= 0 and sent.sum() == whole.N
+    owners, U_all, N_all = [], [], []
+    for o in range(world):
+        ix = eng.build_regions(slots[o], region_cap, world, k)
+        assert L_.kmg_index_order(ix._handle()) == 0 and ix.sizes[1] == sent[o].sum()
+        owners.append(ix); U_all.append(ix.sizes[0]); N_all.append(ix.sizes[1])
+    assert sum(U_all) == whole.U and sum(N_all) == whole.N
+    # sharded extraction (SURVEY.md 8e): every owner writes its slice of ONE matrix with global k-mer numbers
+    pos_all = torch.zeros((whole.N, 2), dtype=torch.int32, device=dev)
+    cnt_all = torch.zeros(whole.U, dtype=torch.int32, device=dev)
+    keys_all = np.empty(whole.U, np.uint64)
+    for o, ix in enumerate(owners):
+        sh = kdist.ShardedIndex(ix, k, o, world, U_all, N_all, None, eng)
+        r0, i0 = sh.row_offset, sh.i_offset
+        got = sh.kmer_pos(2 | 8, out={"pos": pos_all[r0:r0 + N_all[o]], "count": cnt_all[i0:i0 + U_all[o]]})
+        assert got["i_offset"] == i0 and got["row_offset"] == r0
+        keys_all[i0:i0 + U_all[o]] = kh.kmer_keys(ix)
+    pos_all, cnt_all = pos_all.cpu().numpy(), cnt_all.cpu().numpy()
+    assert np.array_equal(pos_all[:, 0], np.repeat(np.arange(1, whole.U + 1, dtype=np.int32), cnt_all))   # global i, grouped
+    order = np.argsort(keys_all, kind="stable")
+    rank = np.empty(whole.U, np.int64); rank[order] = np.arange(whole.U)
+    assert np.array_equal(keys_all[order], want["keys"]) and np.array_equal(cnt_all[order], want["count"])
+    assert np.array_equal(kh._renumber(pos_all, rank).ravel(), want["pos"])
+    # routed probe: query records go to the key's owner through the same scatter (pos_add = k - 1: the END coordinate)
+    if L > 1000:
+        q = synth.config_c4_query(seq, L // 3)
+        qper = (len(q) + world - 1) // world
+        qowns = [eng.upload(q[min(r * qper, len(q)):min((r + 1) * qper, len(q))]) for r in range(world)]
+        qpacks = torch.cat([eng.shard_pack(o, k, 2, 0) for o in qowns])
+        qh = [eng.shard_open_packed(qowns[r], len(q), world, r, k, 2, qpacks, 0, splitters=False)[0] for r in range(world)]
+        qslots, qkeep = exchange(qh, int(qper / world * 1.5) + 50_000, k - 1)
+        rows = [eng.query_regions(owners[o], qslots[o], int(qper / world * 1.5) + 50_000, world).cpu().numpy() for o in range(world)]
+        rows = np.concatenate(rows)
+        rows = rows[np.argsort(rows[:, 0], kind="stable")]
+        assert len(rows) > 0 and np.array_equal(rows.ravel(), whole.query(q, k))
+        for h in qh:
+            eng.shard_close(h)
+        # a region too small for what a source sends is reported, not overrun
+        tiny = max(per // world // 4, 1)
+        tslots, tkeep = exchange(handles, tiny, 0)
+        with pytest.raises(_lib.KmgError) as e:
+            eng.build_regions(tslots[0], tiny, world, k)
+        assert e.value.code == -3
+    for ix in owners:
+        ix.free()
+    for h in handles:
+        eng.shard_close(h)
