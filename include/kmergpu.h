@@ -131,7 +131,7 @@ int kmg_query_free(kmg_query *st);
  * kmg_join_begin + kmg_join_emit replace kmer_pair_pos, src/kmer_hash.c:1174-1203 (kmer_hash.R:30-34):
  * for every k-mer of index `a` that index `b` also holds, the rows (a_pos, b_pos), a position outer,
  * b position inner (:1190-1195).  The reference walks a's hash buckets without kh_exist and crashes
- * (test.R:330-331); this is its evident intent, with a's k-mers taken in ascending key order.  Keys
+ * (test.R:330-331); this is its evident intent, with a's k-mers taken in a's own k-mer order (kmg_index_order).  Keys
  * are compared as raw 2-bit codes, whatever k each index was built with, as kh_get does (:1185).
  * Both indexes must be on the same device.  M = number of rows. */
 int kmg_join_begin(const kmg_index *a, const kmg_index *b, kmg_join **st, uint64_t *M);

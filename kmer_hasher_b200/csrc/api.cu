@@ -1240,42 +1240,34 @@ static int ensure_hash(kmg_index *ix) {
   const bool stream = ix->grouped && ix->hbits >= 8 && ix->hbits <= 56 && !g_hash_cas && (ix->hbits >= 40 || ix->U <= (uint64_t(1) << ix->hbits));
   if (stream) {
     const uint64_t nb = std::max<uint64_t>(ix->U, 4);
-    const uint32_t ov_cap = (uint32_t)std::min<uint64_t>(ix->U / 4 + 1024, UINT32_MAX);
-    uint32_t *ov = nullptr;
+    uint64_t *d_last = nullptr;
     TRY(dalloc(&slots, nb * BUCKET_SLOTS, s));
-    int rc = dalloc(&ov, (size_t)ov_cap + 1, s);
+    int rc = dalloc(&d_last, 1, s);
     if (rc != KMG_OK) { dfree(slots, s); return rc; }
-    uint32_t h_ov = 0;
     auto body = [&]() -> int {
-      CU(cudaMemsetAsync(ov + ov_cap, 0, 4, s));
       KeyHash kt{slots, nb, ix->hbits};
-      LAUNCH("hash_stream", s, hash_stream_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, kt, ov, ov + ov_cap, ov_cap));
-      CU(cudaMemcpyAsync(&h_ov, ov + ov_cap, 4, cudaMemcpyDeviceToHost, s));
+      uint64_t h_last = 0;
+      LAUNCH("hash_stream", s, hash_stream_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, kt, d_last));
+      CU(cudaMemcpyAsync(&h_last, d_last, 8, cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
-      if (h_ov > ov_cap) return KMG_OK;                  // too many crowded buckets (never seen): the CAS build below
-      if (h_ov) {
-        const unsigned g2 = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(h_ov, 256), (uint64_t)g_ctx.sms * 32);
-        LAUNCH("hash_insert", s, hash_insert_kernel<<<g2, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, kt, ov, ov + ov_cap));
-        CU(cudaStreamSynchronize(s));
-      }
+      if (h_last + 1 < nb) CU(cudaMemsetAsync(slots + (h_last + 1) * BUCKET_SLOTS, 0, (nb - h_last - 1) * BUCKET_SLOTS * sizeof(uint4), s));
+      LAUNCH("hash_insert", s, hash_insert_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, kt, true));
+      CU(cudaStreamSynchronize(s));
       return KMG_OK;
     };
     rc = body();
-    dfree(ov, s);
+    dfree(d_last, s);
     if (rc != KMG_OK) { dfree(slots, s); return rc; }
-    if (h_ov <= ov_cap) {
-      ix->hash = slots; ix->hash_nb = nb; ix->hash_hbits = ix->hbits;
-      prof_bytes("hash_stream", 12.0 * ix->U + 16.0 * BUCKET_SLOTS * nb);
-      prof_bytes("hash_insert", 28.0 * h_ov);
-      return KMG_OK;
-    }
-    dfree(slots, s);
+    ix->hash = slots; ix->hash_nb = nb; ix->hash_hbits = ix->hbits;
+    prof_bytes("hash_stream", 12.0 * ix->U + 16.0 * BUCKET_SLOTS * nb);
+    prof_bytes("hash_insert", 8.0 * ix->U);
+    return KMG_OK;
   }
   uint64_t cap = 4 * BUCKET_SLOTS;
   while (cap < 2 * ix->U) cap <<= 1;                          // load <= 0.5
   TRY(dalloc(&slots, cap, s));
   CU(cudaMemsetAsync(slots, 0, cap * sizeof(uint4), s));
-  LAUNCH("hash_insert", s, hash_insert_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, KeyHash{slots, cap / BUCKET_SLOTS, 0}, nullptr, nullptr));
+  LAUNCH("hash_insert", s, hash_insert_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, KeyHash{slots, cap / BUCKET_SLOTS, 0}, false));
   CU(cudaStreamSynchronize(s));
   ix->hash = slots; ix->hash_nb = cap / BUCKET_SLOTS; ix->hash_hbits = 0;
   prof_bytes("hash_insert", 12.0 * ix->U + 16.0 * ix->U);

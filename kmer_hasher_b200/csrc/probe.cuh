@@ -77,30 +77,35 @@ __device__ __forceinline__ void cas_insert(const KeyHash &kh, uint64_t key, uint
 }
 
 // Distinct keys only: one 128-bit CAS claims a slot and fills it (a stored slot is never all-zero: count >= 1).
-// `list` (optional): insert only the k-mers it names (the overflow of hash_stream_kernel).
+// overflow_only (tables written by hash_stream_kernel): insert only a bucket's third and later k-mers, found by the same
+// test as there (the two k-mers before it share its home bucket).
 __global__ void hash_insert_kernel(const uint64_t *__restrict__ ukeys, const uint32_t *__restrict__ ustart, uint64_t U, KeyHash kh,
-                                   const uint32_t *__restrict__ list, const uint32_t *__restrict__ n_list) {
-  const uint64_t n = list ? (uint64_t)*n_list : U;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t u = list ? list[i] : i;
+                                   const bool overflow_only) {
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = ukeys[u];
+    if (overflow_only) {
+      if (u < 2) continue;
+      const uint64_t b = kh.bucket(key);
+      if (kh.bucket(ukeys[u - 1]) != b || kh.bucket(ukeys[u - 2]) != b) continue;
+    }
     const uint32_t start = ustart[u];
-    cas_insert(kh, ukeys[u], start, ustart[u + 1] - start);
+    cas_insert(kh, key, start, ustart[u + 1] - start);
   }
 }
 
 // Table of a grouped index, written front to back (no memset, no atomics): the k-mers come in ascending home-bucket order,
 // so the first k-mer of a bucket (its leader) writes the whole 32-byte bucket -- itself, the next k-mer if it shares the
-// bucket, else an empty slot -- and zero-fills the empty buckets before it; a bucket's third and later k-mers (~10 % at
-// one k-mer per bucket on average) go to `overflow` and are CAS-inserted afterwards by hash_insert_kernel, which places
-// each in the first bucket after its home that has room: exactly the table the all-CAS build gives up to slot order.
+// bucket, else an empty slot -- and zero-fills the empty buckets before it.  A bucket's third and later k-mers (~10 % at
+// one k-mer per bucket on average) are CAS-inserted afterwards by hash_insert_kernel(overflow_only), which places each in
+// the first bucket after its home that has room: exactly the table the all-CAS build gives up to slot order.
+// The buckets after the last k-mer's are zeroed by the caller.
 __global__ void hash_stream_kernel(const uint64_t *__restrict__ ukeys, const uint32_t *__restrict__ ustart, uint64_t U, KeyHash kh,
-                                   uint32_t *__restrict__ overflow, uint32_t *n_overflow, uint32_t ov_cap) {
+                                   uint64_t *last_bucket) {
   const uint4 zero = make_uint4(0, 0, 0, 0);
   for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t key = ukeys[u];
     const uint64_t b = kh.bucket(key);
     const int64_t bp1 = u > 0 ? (int64_t)kh.bucket(ukeys[u - 1]) : -1;
-    const int64_t bp2 = u > 1 ? (int64_t)kh.bucket(ukeys[u - 2]) : -1;
     if (bp1 != (int64_t)b) {                               // leader of bucket b
       const uint32_t s0 = ustart[u], s1 = ustart[u + 1];
       uint4 second = zero;
@@ -111,12 +116,8 @@ __global__ void hash_stream_kernel(const uint64_t *__restrict__ ukeys, const uin
       kh.slots[b * BUCKET_SLOTS] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), s0, s1 - s0);
       kh.slots[b * BUCKET_SLOTS + 1] = second;
       for (int64_t g = bp1 + 1; g < (int64_t)b; ++g) { kh.slots[g * BUCKET_SLOTS] = zero; kh.slots[g * BUCKET_SLOTS + 1] = zero; }
-    } else if (bp2 == (int64_t)b) {                         // third or later k-mer of its bucket
-      const uint32_t i = atomicAdd(n_overflow, 1u);
-      if (i < ov_cap) overflow[i] = (uint32_t)u;
     }
-    if (u + 1 == U)                                         // the empty buckets after the last k-mer's
-      for (uint64_t g = b + 1; g < kh.nb; ++g) { kh.slots[g * BUCKET_SLOTS] = zero; kh.slots[g * BUCKET_SLOTS + 1] = zero; }
+    if (u + 1 == U) *last_bucket = b;
   }
 }
 

@@ -622,10 +622,11 @@ owner_offsets_kernel(const uint64_t *__restrict__ matrix, int nparts, int rank, 
     tab->keys[b] = b < nparts ? ptrs.keys[b] : nullptr;
     tab->pos[b] = b < nparts ? ptrs.pos[b] : nullptr;
     tab->delta[b] = (int64_t)before - (int64_t)gbase[b];
+    tab->counts[b] = nullptr;
     if (b == rank) info[0] = total;
     if (total > cap) info[1] = 1;
   }
-  if (b == 0) tab->cap = cap;
+  if (b == 0) { tab->cap = cap; tab->rank = (uint32_t)rank; tab->region = 0; }
 }
 
 // ---- all passes' histograms from the sequence, in one sweep -------------------------------------------

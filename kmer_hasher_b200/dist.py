@@ -346,6 +346,7 @@ class ShardedIndex:
         self._U_all, self._N_all, self._splitters, self.engine = U_all, N_all, splitters, engine
         self.splitters_dev, self.group = splitters_dev, group
         self.mixed, self.order = False, 1                    # set by the peer-memory build when owners hold ranges of the mix
+        self.ranges = False                                  # owners are equal ranges of the mixed key (region exchange)
 
     def _gather_sizes(self):
         if self._U_all is None:

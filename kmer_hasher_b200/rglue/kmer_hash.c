@@ -268,6 +268,19 @@ SEXP kmer_positions(SEXP ptr_r, SEXP opt_flag_r) {
   return ret;
 }
 
+/* allocMatrix() can longjmp (allocation failure, interrupt) while a kmg_query / kmg_join holds device memory: the state is
+ * parked in an external pointer whose finaliser releases it, so nothing leaks past an R error. */
+static void finalise_query_guard(SEXP g) {
+  kmg_query *q = (kmg_query *)R_ExternalPtrAddr(g);
+  if (q) kmg_query_free(q);
+  R_ClearExternalPtr(g);
+}
+static void finalise_join_guard(SEXP g) {
+  kmg_join *j = (kmg_join *)R_ExternalPtrAddr(g);
+  if (j) kmg_join_free(j);
+  R_ClearExternalPtr(g);
+}
+
 SEXP sequence_kmer_positions(SEXP ptr_r, SEXP seq_r, SEXP k_r) {
   kmer_handle *h = index_handle_or_error(ptr_r);
   if (TYPEOF(seq_r) != STRSXP || length(seq_r) != 1) error("seq_r should be a single sequence");
@@ -285,10 +298,13 @@ SEXP sequence_kmer_positions(SEXP ptr_r, SEXP seq_r, SEXP k_r) {
     kmg_query_free(q);
     error("seq.kmer.pos would return %llu rows, more than an R matrix can hold (2^31-1)", (unsigned long long)M);
   }
+  SEXP guard = PROTECT(R_MakeExternalPtr(q, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(guard, finalise_query_guard, TRUE);
   SEXP m = PROTECT(allocMatrix(INTSXP, 2, (int)M)); /* rows (i,j); seq.kmer.pos() names and transposes */
   const int rc = kmg_query_emit(q, INTEGER(m));
   kmg_query_free(q);
-  UNPROTECT(1);
+  R_ClearExternalPtr(guard);
+  UNPROTECT(2);
   if (rc != KMG_OK) error("seq.kmer.pos failed: %s", kmg_last_error());
   return m;
 }
@@ -305,10 +321,13 @@ SEXP kmer_pair_pos(SEXP ptr_a, SEXP ptr_b) {
     kmg_join_free(j);
     error("kmer.pairs would return %llu rows, more than an R matrix can hold (2^31-1)", (unsigned long long)M);
   }
+  SEXP guard = PROTECT(R_MakeExternalPtr(j, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(guard, finalise_join_guard, TRUE);
   SEXP m = PROTECT(allocMatrix(INTSXP, 2, (int)M));
   const int rc = kmg_join_emit(j, INTEGER(m));
   kmg_join_free(j);
-  UNPROTECT(1);
+  R_ClearExternalPtr(guard);
+  UNPROTECT(2);
   if (rc != KMG_OK) error("kmer.pairs failed: %s", kmg_last_error());
   return m;
 }

@@ -155,3 +155,175 @@ def test_choose_splitters_quantiles():
     assert choose_splitters(s, 1).size == 0
     big = np.array([2**63 + 5, 1, 2**64 - 1, 7], np.uint64)        # unsigned order, not int64 order
     assert choose_splitters(big, 2).tolist() == [2**63 + 5]
+
+
+# ---- the region exchange (grouped sharded build) with a test double ------------------------------------------------
+M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def np_mix64(x):
+    x = x.astype(np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33); x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33); x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    return x
+
+
+def np_unmix64(x):
+    x = x.astype(np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33); x *= np.uint64(0x9cb4b2f8129337db)
+        x ^= x >> np.uint64(33); x *= np.uint64(0x4f74430c22a54005)
+        x ^= x >> np.uint64(33)
+    return x
+
+
+class _Box:
+    pass
+
+
+class GlooExchange:
+    """Stand-in for dist.PeerExchange: `barrier` performs the exchange that peer stores over NVLink do on the GPU."""
+
+    def __init__(self, region_cap):
+        self.region_cap = region_cap
+        self.slot = None
+
+    def next_slot(self):
+        self.slot = _Box()
+        self.slot.outbox, self.slot.inbox = None, None
+        return self.slot
+
+    def barrier(self):
+        world = dist.get_world_size()
+        out = self.slot.outbox                                # per owner: (mixed keys u64, payload i32)
+        send_counts = torch.tensor([len(o[0]) for o in out], dtype=torch.int64)
+        recv_counts = torch.empty(world, dtype=torch.int64)
+        dist.all_to_all_single(recv_counts, send_counts)
+        rc, sc = recv_counts.tolist(), send_counts.tolist()
+        sk = torch.from_numpy(np.concatenate([o[0] for o in out]).view(np.int64).copy())
+        sp = torch.from_numpy(np.concatenate([o[1] for o in out]).astype(np.int32))
+        rk, rp = torch.empty(sum(rc), dtype=torch.int64), torch.empty(sum(rc), dtype=torch.int32)
+        dist.all_to_all_single(rk, sk, rc, sc)
+        dist.all_to_all_single(rp, sp, rc, sc)
+        offs = np.concatenate([[0], np.cumsum(rc)])
+        self.slot.inbox = [(rk.numpy()[offs[r]:offs[r + 1]].view(np.uint64), rp.numpy()[offs[r]:offs[r + 1]]) for r in range(world)]
+
+    def agree(self, status):
+        t = torch.tensor([int(status)], dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
+
+
+class RegionEngine(OracleEngine):
+    """OracleEngine + the region-exchange interface of dist.CudaEngine."""
+
+    def shard_pack(self, own, k, n_samples, order=0):
+        b = self._bytes(own)
+        pack = np.zeros(48 + 8 * n_samples, np.uint8)
+        pack[:min(k - 1, len(b))] = b[:k - 1]
+        if len(b):
+            pack[40] = b[-1]
+        return torch.from_numpy(pack)
+
+    def shard_open_packed(self, own, L, world, rank, k, n_samples, allpack, order=0, splitters=True):
+        from kmer_hasher_b200.dist import shard_bounds
+        packs = allpack.numpy().reshape(world, -1)
+        s0, s1, g0, g1 = shard_bounds(L, world, rank, k)
+        b = self._bytes(own)
+        left = packs[rank - 1][40:41] if g0 < s0 else np.empty(0, np.uint8)
+        need, right, r = g1 - s1, [], rank + 1
+        while need > 0 and r < world:
+            rs0, rs1, _, _ = shard_bounds(L, world, r, k)
+            take = min(need, rs1 - rs0, k - 1)
+            right.append(packs[r][:take]); need -= take; r += 1
+        h = _Box()
+        h.bytes, h.g0, h.g1, h.s0, h.s1, h.L, h.k = np.concatenate([left, b] + right), g0, g1, s0, s1, L, k
+        return h, None
+
+    def shard_close(self, h):
+        pass
+
+    def shard_scatter_ranges(self, h, nparts, rank, slot, region_cap, pos_add):
+        b = h.bytes
+        if h.g1 < h.L:
+            b = np.concatenate([b, np.frombuffer(b"A", np.uint8)])
+        keys, pos = self.o.windows(b, h.k)
+        gpos = pos.astype(np.int64) + h.g0
+        keep = (gpos - 1 >= h.s0) & (gpos - 1 < h.s1)
+        mixed, gpos = np_mix64(keys[keep]), gpos[keep] + pos_add
+        owner = ((mixed.astype(object) * nparts) >> 64).astype(np.int64) if len(mixed) else np.zeros(0, np.int64)   # __umul64hi(h, nparts)
+        slot.outbox = [(mixed[owner == o], gpos[owner == o].astype(np.int32)) for o in range(nparts)]
+
+    def build_regions(self, slot, region_cap, nparts, k):
+        from kmer_hasher_b200._lib import KmgError
+        if any(len(h) > region_cap for h, _ in slot.inbox):
+            raise KmgError(-3, "an owner received more than the exchange capacity")
+        keys = np_unmix64(np.concatenate([h for h, _ in slot.inbox]))
+        pos = np.concatenate([p for _, p in slot.inbox])
+        return self.build_records(torch.from_numpy(keys.view(np.int64).copy()), torch.from_numpy(pos), len(keys), k)
+
+    def query_regions(self, index, slot, region_cap, nparts, count_only=False):
+        keys = np_unmix64(np.concatenate([h for h, _ in slot.inbox]))
+        co = np.concatenate([p for _, p in slot.inbox])
+        return self.query_records(index, torch.from_numpy(keys.view(np.int64).copy()), torch.from_numpy(co), len(keys))
+
+
+def _region_worker(rank, world, port, seq, query, k, region_cap, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kmer_hasher_b200 import dist as kdist
+        eng, L = RegionEngine(), len(seq)
+        s0, s1, _, _ = kdist.shard_bounds(L, world, rank, k)
+        ix = kdist.sharded_build_ranges(seq[s0:s1], L, k, eng, GlooExchange(region_cap))
+        e = ix.local.extract(2 | 8)
+        pos = e["pos"].reshape(-1, 2).copy()
+        pos[:, 0] += ix.i_offset                              # global k-mer numbers, owners in rank order
+        rows = None
+        if ix.ranges:
+            Lq = len(query)
+            q0, q1, _, _ = kdist.shard_bounds(Lq, world, rank, k)
+            rows = kdist.sharded_query_ranges(ix, query[q0:q1], Lq, k, GlooExchange(region_cap)).numpy()
+        ret[rank] = dict(keys=e["keys"], count=e["count"], pos=pos, rows=rows, ranges=ix.ranges, row_offset=ix.row_offset,
+                         N_total=ix.N_total)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,k,n,cap", [(2, 32, 20000, 1 << 20), (3, 21, 9001, 1 << 20), (2, 27, 6000, 500)])
+def test_region_exchange_build_and_query(oracle, world, k, n, cap):
+    """sharded_build_ranges / sharded_query_ranges over gloo: halo packs, owners = equal ranges of the mixed key, per-source
+    regions, collective agreement on the outcome.  cap = 500 makes every region overflow: all ranks must then take the
+    general path together (no hang, same result)."""
+    seq = random_dna(n, 7 + world, p_n=0.002, p_lower=0.2, n_runs=5)
+    per = (n + world - 1) // world
+    seq[per - 3:per + 2] = np.frombuffer(b"ACNGT", np.uint8)
+    seq[n - k - 1] = ord("N")
+    seq[200:200 + 3 * k] = ord("a")                                  # a repeat: many copies of one k-mer go to one owner
+    query = random_dna(n // 2, 99, p_n=0.001)
+    query[100:100 + n // 4] = seq[50:50 + n // 4]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_region_worker, args=(world, _free_port(), seq, query, k, cap, ret), nprocs=world, join=True)
+    whole = oracle.build(seq, k)
+    want = whole.extract(2 | 8)
+    assert all(ret[r]["ranges"] == (cap > 500) for r in range(world))
+    keys = np.concatenate([ret[r]["keys"] for r in range(world)])
+    cnt = np.concatenate([ret[r]["count"] for r in range(world)])
+    pos = np.concatenate([ret[r]["pos"] for r in range(world)])
+    assert ret[0]["N_total"] == whole.N and [ret[r]["row_offset"] for r in range(world)] == np.concatenate([[0], np.cumsum([len(ret[r]["pos"]) for r in range(world)])])[:-1].tolist()
+    order = np.argsort(keys, kind="stable")                          # owners hold ranges of the MIXED key: canonicalise
+    rank = np.empty(len(keys), np.int64); rank[order] = np.arange(len(keys))
+    assert np.array_equal(keys[order], want["keys"]) and np.array_equal(cnt[order], want["count"])
+    new_i = rank[pos[:, 0].astype(np.int64) - 1] + 1
+    o2 = np.argsort(new_i, kind="stable")
+    canon = pos[o2].copy(); canon[:, 0] = new_i[o2]
+    assert np.array_equal(canon.ravel(), want["pos"])
+    if cap > 500:
+        rows = np.concatenate([ret[r]["rows"] for r in range(world)])
+        rows = rows[np.argsort(rows[:, 0], kind="stable")]
+        assert np.array_equal(rows.ravel(), whole.query(query, k))
