@@ -277,6 +277,12 @@ def probe_leg(kh, torch, _lib, w, seq_pin, seq_dev, k, steps, hbm_peak):
     begin(q_dev.data_ptr())
     rows_n = int(M.value)
     Lb.kmg_query_free(st)
+    if rows_n > 2**31 - 1:               # more rows than an R matrix holds: seq.kmer.pos refuses (the glue checks M first)
+        ms_b = timed(torch, lambda: (begin(q_dev.data_ptr()), Lb.kmg_query_free(st)), max(3, steps // 2))
+        h.free()
+        return {"metric": "kmers_queried_per_s", "value": None, "unit": "k-mers/s", "rows": rows_n, "ms_begin": ms_b,
+                "first_probe_ms": ms_first, "note": "this query has more result rows than an R matrix can hold (2^31-1): seq.kmer.pos "
+                "refuses it, so only kmg_query_begin (match + count + scan) is timed and no throughput with emission is claimed"}
     rows_dev = torch.empty((max(rows_n, 1), 2), dtype=torch.int32, device="cuda")
     rows_pin = kh.pinned_empty((max(rows_n, 1), 2), np.int32)
     n_rep = max(3, steps // 2)

@@ -240,6 +240,22 @@ int kmg_count_spectrum(const kmg_counter *c, int source /* < 0: summed over sour
 int kmg_index_spectrum(const kmg_index *idx, uint32_t max_count, double *spec /* max_count+1 */);
 int kmg_count_free(kmg_counter *c);
 
+/* ---- FASTA / FASTQ ingestion ---------------------------------------------------------
+ * Replaces, for the index path, what the reference does with klib's kseq.h over zlib (src/kseq.h; read loop
+ * src/kmer_reader.c:41-77): the host inflates the file, the DEVICE finds and classifies the lines and packs the records'
+ * sequences (csrc/reads.cuh).  Record names are the header up to the first white space; line ends (and a trailing CR)
+ * are removed.  FASTA may be multi-line; FASTQ must be the four-line form.  An index is then built from a record without
+ * the sequence ever being an R string (no 2^31-1 limit on the file, no host copy), and count.kmers can take a whole file. */
+typedef struct kmg_reads kmg_reads;
+int kmg_reads_open(const char *path, kmg_reads **out);                       /* plain or gz */
+int kmg_reads_from_memory(const void *text, int64_t len, kmg_reads **out);   /* inflated file contents, host or device */
+int kmg_reads_count(const kmg_reads *r, uint64_t *n_records, uint64_t *total_bases);
+int kmg_reads_record(const kmg_reads *r, uint64_t i, int64_t *seq_len, char *name_buf, int name_cap);
+int kmg_reads_sequence(const kmg_reads *r, uint64_t i, char *out /* seq_len bytes, host or device */);
+int kmg_build_record(const kmg_reads *r, uint64_t i, int k, int order, kmg_index **out);  /* make.kmer.hash on record i */
+int kmg_count_add_reads(kmg_counter *c, const kmg_reads *r, int source);     /* count.kmers over every record */
+int kmg_reads_free(kmg_reads *r);
+
 /* ---- instrumentation (bench.py / profiles) ------------------------------------------------------ */
 int kmg_profile_enable(int on);          /* bracket every kernel with CUDA events               */
 int kmg_profile_reset(void);

@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib
 from ._lib import KmgError, check
 
-__all__ = ["KmerHash", "KmerCounts", "make_kmer_hash", "kmer_pos", "seq_kmer_pos", "kmer_pairs", "count_kmers", "kmer_spectrum",
+__all__ = ["KmerHash", "KmerCounts", "SequenceFile", "make_kmer_hash_file", "count_kmers_file", "make_kmer_hash", "kmer_pos", "seq_kmer_pos", "kmer_pairs", "count_kmers", "kmer_spectrum",
            "pinned_empty", "KmgError",
            "OPT_KMER", "OPT_POS", "OPT_PAIRS", "OPT_COUNT"]
 
@@ -331,6 +331,102 @@ def _count_table_pos(ct: KmerCounts, opt_flag: int) -> dict:
     if opt_flag & OPT_COUNT:
         res["count"] = np.full(U, sn, np.int32)
     return res
+
+
+class SequenceFile:
+    """The records of a FASTA / FASTQ file (plain or gz), parsed on the device and kept there (kmg_reads_*): what the
+    reference gets from kseq_read (src/kmer_reader.c:41-77) -- names up to the first white space, sequences with the line
+    ends removed -- without the sequences ever becoming host strings."""
+
+    def __init__(self, path_or_text):
+        h = C.c_void_p()
+        if isinstance(path_or_text, (bytes, bytearray, np.ndarray)) or hasattr(path_or_text, "data_ptr"):
+            ptr, n, keep = _seq_buffer(path_or_text)
+            check(_L.kmg_reads_from_memory(ptr, n, C.byref(h)))
+        else:
+            check(_L.kmg_reads_open(str(path_or_text).encode(), C.byref(h)))
+        self._h = h.value
+        n, tot = C.c_uint64(), C.c_uint64()
+        check(_L.kmg_reads_count(self._h, C.byref(n), C.byref(tot)))
+        self.n_records, self.total_bases = n.value, tot.value
+
+    def record(self, i: int):
+        """(name, sequence length) of record i"""
+        ln, buf = C.c_int64(), C.create_string_buffer(4096)
+        check(_L.kmg_reads_record(self._h, i, C.byref(ln), buf, 4096))
+        return buf.value.decode("latin-1"), ln.value
+
+    def sequence(self, i: int) -> bytes:
+        _, ln = self.record(i)
+        out = np.empty(max(ln, 1), np.uint8)
+        check(_L.kmg_reads_sequence(self._h, i, _out_ptr(out)))
+        return out[:ln].tobytes()
+
+    def names(self):
+        return [self.record(i)[0] for i in range(self.n_records)]
+
+    def free(self):
+        if self._h:
+            _L.kmg_reads_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def make_kmer_hash_file(file, k, record=0, do_sort=False) -> KmerHash:
+    """make.kmer.hash on one record of a FASTA / FASTQ file (by number or by name): the sequence goes file -> device
+    -> index, never through a host string.  `file` is a path or an open SequenceFile."""
+    sf = file if isinstance(file, SequenceFile) else SequenceFile(file)
+    try:
+        if isinstance(record, str):
+            names = sf.names()
+            if record not in names:
+                raise KeyError(f"no record named {record!r}")
+            record = names.index(record)
+        k = int(k)
+        if k < 1 or k > MAX_K:
+            raise ValueError("k must be a positive integer less than 1+MAX_K")
+        if sf.record(record)[1] <= k:
+            raise ValueError("the length of the sequence must be at least k")
+        h = C.c_void_p()
+        check(_L.kmg_build_record(sf._h, record, k, ORDER_SORTED if int(do_sort) else ORDER_GROUPED, C.byref(h)))
+        return KmerHash(h.value, k)
+    finally:
+        if not isinstance(file, SequenceFile):
+            sf.free()
+
+
+def count_kmers_file(file, params, hash_ptr: "KmerCounts | None" = None) -> KmerCounts:
+    """count.kmers over every record of a FASTA / FASTQ file: as count_kmers(list of the records' sequences, params,
+    hash_ptr) -- records no longer than k are skipped, every record keeps the reference's end-of-string rule -- but the
+    whole file is counted by ONE index build on the device."""
+    params = [int(p) for p in params]
+    if len(params) != 3:
+        raise ValueError("k_r must be an integer vector of length 3")
+    k, source, source_n = params
+    sf = file if isinstance(file, SequenceFile) else SequenceFile(file)
+    try:
+        if hash_ptr is None:
+            if k < 1 or k > MAX_K:
+                raise ValueError("k must be a positive integer less than 1+MAX_K")
+            if source_n < 1 or source >= source_n or source < 0:
+                raise ValueError("source_n must be larger than 1 and larger than source")
+            h = C.c_void_p()
+            check(_L.kmg_count_new(k, source_n, C.byref(h)))
+            hash_ptr = KmerCounts(h.value, k, source_n)
+        elif not isinstance(hash_ptr, KmerCounts) or hash_ptr.k != k or hash_ptr.source_n != source_n:
+            raise ValueError("mismatch between specified k and that given in the external pointer")
+        if source < 0 or source >= source_n:
+            raise ValueError("source_n must be larger than 1 and larger than source")
+        check(_L.kmg_count_add_reads(hash_ptr._handle(), sf._h, source))
+        return hash_ptr
+    finally:
+        if not isinstance(file, SequenceFile):
+            sf.free()
 
 
 def kmer_spectrum(ptr, max_count: int, source: "int | None" = None) -> np.ndarray:

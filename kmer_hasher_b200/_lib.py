@@ -86,6 +86,14 @@ SIGNATURES = {
     "kmg_count_spectrum": (C.c_int, [vp, C.c_int, C.c_uint32, C.POINTER(C.c_double)]),
     "kmg_index_spectrum": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_double)]),
     "kmg_count_free": (C.c_int, [vp]),
+    "kmg_reads_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "kmg_reads_from_memory": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
+    "kmg_reads_count": (C.c_int, [vp, u64p, u64p]),
+    "kmg_reads_record": (C.c_int, [vp, C.c_uint64, C.POINTER(C.c_int64), C.c_char_p, C.c_int]),
+    "kmg_reads_sequence": (C.c_int, [vp, C.c_uint64, vp]),
+    "kmg_build_record": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]),
+    "kmg_count_add_reads": (C.c_int, [vp, vp, C.c_int]),
+    "kmg_reads_free": (C.c_int, [vp]),
     "kmg_tune_get": (C.c_int64, [C.c_char_p, C.c_int64]),
     "kmg_trim": (C.c_int, []),
     "kmg_cached_bytes": (C.c_uint64, []),

@@ -1237,9 +1237,9 @@ static int ensure_hash(kmg_index *ix) {
   uint4 *slots = nullptr;
   // grouped index: the k-mers are in ascending order of the sorted bits of their mix, which a monotone bucket function
   // turns into ascending bucket order: the table is streamed out (one bucket per k-mer on average = load 0.5)
-  const bool stream = ix->grouped && ix->hbits >= 8 && ix->hbits <= 56 && !g_hash_cas && (ix->hbits >= 40 || ix->U <= (uint64_t(1) << ix->hbits));
+  const bool stream = ix->grouped && ix->hbits >= 8 && ix->hbits <= 56 && !g_hash_cas && (ix->hbits >= 40 || ix->U + ix->U / 4 <= (uint64_t(1) << ix->hbits));
   if (stream) {
-    const uint64_t nb = std::max<uint64_t>(ix->U, 4);
+    const uint64_t nb = std::max<uint64_t>(ix->U + ix->U / 4, 4);      // 1.25 buckets of two slots per k-mer: load 0.4
     uint64_t *d_last = nullptr;
     TRY(dalloc(&slots, nb * BUCKET_SLOTS, s));
     int rc = dalloc(&d_last, 1, s);
@@ -2439,5 +2439,228 @@ extern "C" int kmg_index_spectrum(const kmg_index *ix, uint32_t max_count, doubl
   }
   if (rc == KMG_OK) rc = spectrum_out(d, max_count, spec, s);
   dfree(d, s);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FASTA / FASTQ ingestion: inflate on the host, parse on the device (reads.cuh)
+// ------------------------------------------------------------------------------------------------
+#include <zlib.h>
+#include "reads.cuh"
+
+struct kmg_reads {
+  int device = 0;
+  uint64_t n_records = 0, total_bases = 0;
+  uint8_t *seq = nullptr;            // packed sequences: record r at rec_off[r], one 'N' after each
+  std::vector<uint64_t> rec_off;     // [n_records + 1] (host copy)
+  uint64_t *d_rec_off = nullptr;
+  std::vector<std::string> names;
+};
+
+extern "C" int kmg_reads_free(kmg_reads *r) {
+  if (!r) return KMG_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(r->device);
+  const bool mine = g_ctx.ready && g_ctx.device == r->device;
+  if (mine) cudaStreamSynchronize(g_ctx.stream()); else cudaDeviceSynchronize();
+  g_arena[r->device & 63].put(r->seq, nullptr, true);
+  g_arena[r->device & 63].put(r->d_rec_off, nullptr, true);
+  cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
+  delete r;
+  return KMG_OK;
+}
+
+// text: the (inflated) file contents, host or device memory
+extern "C" int kmg_reads_from_memory(const void *text, int64_t len, kmg_reads **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (len < 0 || (len > 0 && !text)) return fail(KMG_ERR_ARG, "bad text pointer/length");
+  TRY(ctx_init());
+  cudaStream_t s = g_ctx.stream();
+  kmg_reads *r = new (std::nothrow) kmg_reads();
+  if (!r) return fail(KMG_ERR_NOMEM, "host allocation failed");
+  r->device = g_ctx.device;
+  r->rec_off.assign(1, 0);
+  if (len == 0) { *out = r; return KMG_OK; }
+  const uint64_t n = (uint64_t)len, nblocks = (n + 15) / 16;
+  uint8_t *d_text = nullptr, *kind = nullptr;
+  uint64_t *nl = nullptr, *seq_len = nullptr, *seq_before = nullptr, *hdr_before = nullptr, *name_pos = nullptr;
+  uint32_t *blk_nl = nullptr, *tickets = nullptr, *name_len = nullptr;
+  Pair64 *status = nullptr;
+  ReadsInfo *info = nullptr;
+  ReadsInfo h{};
+  std::vector<uint64_t> h_name_pos;
+  std::vector<uint32_t> h_name_len;
+  auto body = [&]() -> int {
+    const size_t cap = (size_t)nblocks * 16 + 64;
+    TRY(dalloc(&d_text, cap, s));
+    CU(cudaMemsetAsync(d_text + (cap - 80), 0, 80, s));
+    if (n > (uint64_t)(8 << 20) && staged_transfers() && ptr_kind(text) == PK_HOST_PAGEABLE) TRY(staged_upload(d_text, text, n, s));
+    else CU(cudaMemcpyAsync(d_text, text, n, cudaMemcpyDefault, s));
+    TRY(dalloc(&info, 1, s));
+    TRY(dalloc(&tickets, 4, s));
+    CU(cudaMemsetAsync(info, 0, sizeof(ReadsInfo), s));
+    CU(cudaMemsetAsync(tickets, 0, 16, s));
+    // 1. newlines (a line-start byte decides FASTA / FASTQ: the first byte of the file)
+    uint8_t first = 0;
+    CU(cudaMemcpyAsync(&first, d_text, 1, cudaMemcpyDeviceToHost, s));
+    const uint64_t tiles1 = ceil_div<uint64_t>(nblocks, 256 * 4);
+    TRY(dalloc(&status, (size_t)std::max<uint64_t>(tiles1, 1), s));
+    CU(cudaMemsetAsync(status, 0, (size_t)tiles1 * sizeof(Pair64), s));
+    unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(&info->total_bases), h_cnt = 0;    // borrowed until line_scan sets it
+    LAUNCH("nl_count", s, nl_count_kernel<<<(unsigned)std::min<uint64_t>(ceil_div<uint64_t>(nblocks, 256), (uint64_t)g_ctx.sms * 16), 256, 0, s>>>(d_text, n, d_cnt));
+    CU(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    TRY(dalloc(&nl, (size_t)h_cnt + 2, s));
+    TRY(dalloc(&blk_nl, (size_t)nblocks, s));
+    LAUNCH("nl_scan", s, nl_scan_kernel<256><<<(unsigned)tiles1, 256, 0, s>>>(d_text, n, nl, blk_nl, status, tickets + 0, info));
+    CU(cudaMemcpyAsync(&h, info, sizeof h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (first != '>' && first != '@') return fail(KMG_ERR_ARG, "not a FASTA/FASTQ file: it starts with byte 0x%02x", first);
+    const bool fastq = first == '@';
+    const uint64_t nlines = h.n_lines;
+    TRY(dalloc(&seq_len, (size_t)nlines + 1, s));
+    TRY(dalloc(&kind, (size_t)nlines + 1, s));
+    TRY(dalloc(&seq_before, (size_t)nlines + 1, s));
+    TRY(dalloc(&hdr_before, (size_t)nlines + 1, s));
+    const unsigned lgrid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(std::max<uint64_t>(nlines, 1), 256), (uint64_t)g_ctx.sms * 16);
+    LAUNCH("line_info", s, line_info_kernel<<<lgrid, 256, 0, s>>>(d_text, n, nl, info, fastq, seq_len, kind, info));
+    const uint64_t tiles2 = ceil_div<uint64_t>(std::max<uint64_t>(nlines, 1), 256 * 8);
+    dfree(status, s);
+    TRY(dalloc(&status, (size_t)tiles2, s));
+    CU(cudaMemsetAsync(status, 0, (size_t)tiles2 * sizeof(Pair64), s));
+    LAUNCH("line_scan", s, line_scan_kernel<256, 8><<<(unsigned)tiles2, 256, 0, s>>>(seq_len, kind, info, seq_before, hdr_before, status, tickets + 1));
+    CU(cudaMemcpyAsync(&h, info, sizeof h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (h.bad) return fail(KMG_ERR_ARG, "malformed FASTQ: only the four-line form (@name / sequence / + / qualities of the same length) is read");
+    r->n_records = h.n_records; r->total_bases = h.total_bases;
+    const uint64_t packed = h.total_bases + h.n_records;
+    TRY(dalloc(&r->seq, (size_t)packed + 16, s));
+    TRY(dalloc(&r->d_rec_off, (size_t)h.n_records + 1, s));
+    TRY(dalloc(&name_pos, (size_t)h.n_records + 1, s));
+    TRY(dalloc(&name_len, (size_t)h.n_records + 1, s));
+    LAUNCH("records", s, record_kernel<<<lgrid, 256, 0, s>>>(d_text, n, nl, info, kind, seq_before, hdr_before, r->d_rec_off, name_pos, name_len));
+    const unsigned pgrid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(nblocks, 256), (uint64_t)g_ctx.sms * 16);
+    LAUNCH("pack_reads", s, pack_kernel<<<pgrid, 256, 0, s>>>(d_text, n, nl, blk_nl, info, kind, seq_before, hdr_before, r->seq, info));
+    if (h.n_records)
+      LAUNCH("record_finish", s, record_finish_kernel<<<(unsigned)std::min<uint64_t>(ceil_div<uint64_t>(h.n_records, 256), (uint64_t)g_ctx.sms * 16), 256, 0, s>>>(info, r->d_rec_off, r->seq));
+    r->rec_off.resize((size_t)h.n_records + 1);
+    h_name_pos.resize((size_t)h.n_records + 1);
+    h_name_len.resize((size_t)h.n_records + 1);
+    CU(cudaMemcpyAsync(r->rec_off.data(), r->d_rec_off, (h.n_records + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_name_pos.data(), name_pos, (h.n_records + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_name_len.data(), name_len, (h.n_records + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&h, info, sizeof h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (h.bad) return fail(KMG_ERR_ARG, "sequence data before the first header line");
+    // names: short strings, fetched from the text where it lives
+    r->names.resize((size_t)h.n_records);
+    const bool text_on_host = ptr_kind(text) != PK_DEVICE;
+    std::vector<char> tmp;
+    for (uint64_t i = 0; i < h.n_records; ++i) {
+      if (text_on_host) r->names[i].assign((const char *)text + h_name_pos[i], h_name_len[i]);
+      else {
+        tmp.resize(h_name_len[i]);
+        if (h_name_len[i]) CU(cudaMemcpy(tmp.data(), d_text + h_name_pos[i], h_name_len[i], cudaMemcpyDeviceToHost));
+        r->names[i].assign(tmp.data(), h_name_len[i]);
+      }
+    }
+    prof_bytes("nl_scan", (double)n); prof_bytes("pack_reads", (double)n + (double)packed);
+    return KMG_OK;
+  };
+  const int rc = body();
+  dfree(d_text, s); dfree(kind, s); dfree(nl, s); dfree(seq_len, s); dfree(seq_before, s); dfree(hdr_before, s);
+  dfree(name_pos, s); dfree(blk_nl, s); dfree(tickets, s); dfree(name_len, s); dfree(status, s); dfree(info, s);
+  if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_reads_free(r); return rc; }
+  *out = r;
+  return KMG_OK;
+}
+
+// gz or plain FASTA / FASTQ file (zlib reads both, as the reference's gzopen does: src/kmer_reader.c:43)
+extern "C" int kmg_reads_open(const char *path, kmg_reads **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (!path) return fail(KMG_ERR_ARG, "path is NULL");
+  gzFile gz = gzopen(path, "rb");
+  if (!gz) return fail(KMG_ERR_ARG, "cannot open %s", path);
+  gzbuffer(gz, 1 << 20);
+  std::vector<char> text;
+  size_t used = 0;
+  for (;;) {
+    if (text.size() - used < (size_t(16) << 20)) text.resize(std::max<size_t>(text.size() * 2, size_t(64) << 20));
+    const int got = gzread(gz, text.data() + used, (unsigned)std::min<size_t>(text.size() - used, size_t(1) << 30));
+    if (got < 0) { gzclose(gz); return fail(KMG_ERR_ARG, "read error in %s", path); }
+    if (got == 0) break;
+    used += (size_t)got;
+  }
+  gzclose(gz);
+  return kmg_reads_from_memory(text.data(), (int64_t)used, out);
+}
+
+static int use_reads(const kmg_reads *r) {
+  if (!r) return fail(KMG_ERR_ARG, "reads is NULL");
+  TRY(ctx_init());
+  if (r->device != g_ctx.device) return fail(KMG_ERR_ARG, "the reads live on device %d but this thread works on device %d", r->device, g_ctx.device);
+  return KMG_OK;
+}
+extern "C" int kmg_reads_count(const kmg_reads *r, uint64_t *n_records, uint64_t *total_bases) {
+  if (!r) return fail(KMG_ERR_ARG, "reads is NULL");
+  if (n_records) *n_records = r->n_records;
+  if (total_bases) *total_bases = r->total_bases;
+  return KMG_OK;
+}
+extern "C" int kmg_reads_record(const kmg_reads *r, uint64_t i, int64_t *seq_len, char *name_buf, int name_cap) {
+  if (!r) return fail(KMG_ERR_ARG, "reads is NULL");
+  if (i >= r->n_records) return fail(KMG_ERR_ARG, "record %llu out of range (have %llu)", (unsigned long long)i, (unsigned long long)r->n_records);
+  if (seq_len) *seq_len = (int64_t)(r->rec_off[i + 1] - 1 - r->rec_off[i]);
+  if (name_buf && name_cap > 0) { strncpy(name_buf, r->names[i].c_str(), (size_t)name_cap - 1); name_buf[name_cap - 1] = 0; }
+  return KMG_OK;
+}
+extern "C" int kmg_reads_sequence(const kmg_reads *r, uint64_t i, char *out) {
+  TRY(use_reads(r));
+  if (i >= r->n_records) return fail(KMG_ERR_ARG, "record out of range");
+  const uint64_t len = r->rec_off[i + 1] - 1 - r->rec_off[i];
+  if (len == 0) return KMG_OK;
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  CU(cudaMemcpyAsync(out, r->seq + r->rec_off[i], len, cudaMemcpyDefault, g_ctx.stream()));
+  CU(cudaStreamSynchronize(g_ctx.stream()));
+  return KMG_OK;
+}
+// make.kmer.hash on record i of the file: no R string, no 2^31-1 limit on the file, the sequence never leaves the device
+extern "C" int kmg_build_record(const kmg_reads *r, uint64_t i, int k, int order, kmg_index **out) {
+  if (!out) return fail(KMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  TRY(use_reads(r));
+  if (i >= r->n_records) return fail(KMG_ERR_ARG, "record out of range");
+  const uint64_t len = r->rec_off[i + 1] - 1 - r->rec_off[i];
+  return kmg_build_ordered((const char *)r->seq + r->rec_off[i], (int64_t)len, k, order, out);
+}
+// count.kmers over every record of the file (those longer than k), column `source`: ONE build of the packed buffer
+extern "C" int kmg_count_add_reads(kmg_counter *c, const kmg_reads *r, int source) {
+  TRY(use_counter(c));
+  TRY(use_reads(r));
+  if (r->n_records == 0) return KMG_OK;
+  cudaStream_t s = g_ctx.stream();
+  const uint64_t packed = r->total_bases + r->n_records;
+  uint8_t *tmp = nullptr;
+  ReadsInfo *info = nullptr;
+  TRY(dalloc(&tmp, (size_t)packed + 16, s));
+  int rc = dalloc(&info, 1, s);
+  if (rc == KMG_OK) {
+    ReadsInfo h{};
+    h.n_records = r->n_records; h.total_bases = r->total_bases;
+    if (cudaMemcpyAsync(info, &h, sizeof h, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(tmp, r->seq, (size_t)packed, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(KMG_ERR_CUDA, "copy failed");
+    if (rc == KMG_OK) {
+      const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(r->n_records, 256), (uint64_t)g_ctx.sms * 16);
+      mask_for_counting_kernel<<<grid, 256, 0, s>>>(info, r->d_rec_off, c->k, tmp);
+      if (cudaStreamSynchronize(s) != cudaSuccess) rc = fail(KMG_ERR_CUDA, "masking failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    // the last record's separator is the final byte: drop it so that the end-of-string rule sees the record's own end... it is an 'N' either way
+    if (rc == KMG_OK) rc = kmg_count_add(c, (const char *)tmp, (int64_t)packed, source);
+  }
+  dfree(tmp, s); dfree(info, s);
   return rc;
 }

@@ -64,9 +64,10 @@ __device__ __forceinline__ bool claim_slot(uint4 *slot, uint4 desired) {
   return olo == 0 && ohi == 0;
 }
 
-__device__ __forceinline__ void cas_insert(const KeyHash &kh, uint64_t key, uint32_t start, uint32_t count) {
+// skip_home: the home bucket is known to be full (overflow of the streamed build): start at the next one
+__device__ __forceinline__ void cas_insert(const KeyHash &kh, uint64_t key, uint32_t start, uint32_t count, uint64_t b, bool skip_home) {
   const uint4 rec = make_uint4((uint32_t)key, (uint32_t)(key >> 32), start, count);
-  uint64_t b = kh.bucket(key);
+  if (skip_home) b = kh.next(b);
   bool placed = false;
   while (!placed) {
 #pragma unroll
@@ -83,13 +84,13 @@ __global__ void hash_insert_kernel(const uint64_t *__restrict__ ukeys, const uin
                                    const bool overflow_only) {
   for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t key = ukeys[u];
+    const uint64_t b = kh.bucket(key);
     if (overflow_only) {
       if (u < 2) continue;
-      const uint64_t b = kh.bucket(key);
       if (kh.bucket(ukeys[u - 1]) != b || kh.bucket(ukeys[u - 2]) != b) continue;
     }
     const uint32_t start = ustart[u];
-    cas_insert(kh, key, start, ustart[u + 1] - start);
+    cas_insert(kh, key, start, ustart[u + 1] - start, b, overflow_only);
   }
 }
 

@@ -332,12 +332,86 @@ SEXP kmer_pair_pos(SEXP ptr_a, SEXP ptr_b) {
   return m;
 }
 
+/* ---- additive entry points: a sequence file instead of an R string ------------------------
+ * make.kmer.hash.file(file, record, k, do.sort) and count.kmers.file(file, params, hash.ptr): the file is inflated on
+ * the host and parsed on the device (kmg_reads_*), so the sequence never becomes an R CHARSXP (whose 2^31-1 byte limit
+ * is what bounds make.kmer.hash in the reference).  record: 1-based record number. */
+static SEXP new_tagged_pointer(kmer_handle *h) {
+  SEXP tag = PROTECT(allocVector(STRSXP, 1));
+  SET_STRING_ELT(tag, 0, mkChar(KMER_HASH_TAG));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, tag, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, finalise_handle, TRUE);
+  UNPROTECT(2);
+  return ptr;
+}
+
+SEXP make_kmer_h_index_file(SEXP file_r, SEXP record_r, SEXP k_r, SEXP sort_pos_r) {
+  if (TYPEOF(file_r) != STRSXP || length(file_r) != 1) error("file_r should be a single file name");
+  if (TYPEOF(record_r) != INTSXP || length(record_r) != 1) error("record_r should be a single integer");
+  if (TYPEOF(k_r) != INTSXP || length(k_r) < 1) error("k_r must be an integer vector of length at least one");
+  if (TYPEOF(sort_pos_r) != INTSXP || length(sort_pos_r) < 1) error("sort_pos_r must be an integer vector of length at least one");
+  const int k = INTEGER(k_r)[0], rec = INTEGER(record_r)[0];
+  if (k < 1 || k > KMG_MAX_K) error("k must be a positive integer less than 1+MAX_K");
+  kmg_reads *rd = NULL;
+  if (kmg_reads_open(CHAR(STRING_ELT(file_r, 0)), &rd) != KMG_OK) error("make.kmer.hash.file failed: %s", kmg_last_error());
+  uint64_t nrec = 0;
+  int64_t len = 0;
+  kmg_reads_count(rd, &nrec, NULL);
+  if (rec < 1 || (uint64_t)rec > nrec) { kmg_reads_free(rd); error("the file holds %llu records; record %d does not exist", (unsigned long long)nrec, rec); }
+  kmg_reads_record(rd, (uint64_t)rec - 1, &len, NULL, 0);
+  if (len <= k) { kmg_reads_free(rd); error("the length of the sequence must be at least k"); }
+  kmer_handle *h = (kmer_handle *)calloc(1, sizeof *h);
+  if (!h) { kmg_reads_free(rd); error("out of memory"); }
+  h->k = k;
+  const int rc = kmg_build_record(rd, (uint64_t)rec - 1, k, INTEGER(sort_pos_r)[0] ? KMG_ORDER_SORTED : KMG_ORDER_GROUPED, &h->index);
+  kmg_reads_free(rd);
+  if (rc != KMG_OK) { free(h); error("make.kmer.hash.file failed: %s", kmg_last_error()); }
+  return new_tagged_pointer(h);
+}
+
+SEXP count_kmers_file(SEXP hash_ptr_r, SEXP params_r, SEXP file_r) {
+  if (TYPEOF(file_r) != STRSXP || length(file_r) != 1) error("file_r should be a single file name");
+  if (TYPEOF(params_r) != INTSXP || length(params_r) != 3) error("k_r must be an integer vector of length 3");
+  const int *params = INTEGER(params_r);
+  const int k = params[0], source = params[1], source_n = params[2];
+  if (k < 1 || k > KMG_MAX_K) error("k must be a positive integer less than 1+MAX_K");
+  if (source_n < 1 || source >= source_n || source < 0) error("source_n must be larger than 1 and larger than source");
+  kmer_handle *h = NULL;
+  SEXP ptr_r = hash_ptr_r;
+  int fresh = 0;
+  if (ptr_r == R_NilValue) {
+    h = (kmer_handle *)calloc(1, sizeof *h);
+    if (!h) error("out of memory");
+    h->k = k;
+    if (kmg_count_new(k, source_n, &h->counter) != KMG_OK) { free(h); error("count.kmers.file failed: %s", kmg_last_error()); }
+    ptr_r = PROTECT(new_tagged_pointer(h));
+    fresh = 1;
+  } else {
+    h = handle_or_null(hash_ptr_r);
+    if (!h || !h->counter) error("failed to extract kmer counts from external pointer");
+    int sn = 0;
+    kmg_count_sizes(h->counter, NULL, &sn, NULL, NULL);
+    if (h->k != k || sn != source_n) error("mismatch between specified k and that given in the external pointer");
+  }
+  kmg_reads *rd = NULL;
+  int rc = kmg_reads_open(CHAR(STRING_ELT(file_r, 0)), &rd);
+  if (rc == KMG_OK) {
+    rc = kmg_count_add_reads(h->counter, rd, source);
+    kmg_reads_free(rd);
+  }
+  if (fresh) UNPROTECT(1);
+  if (rc != KMG_OK) error("count.kmers.file failed: %s", kmg_last_error());
+  return ptr_r;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"make_kmer_h_index", (DL_FUNC)&make_kmer_h_index, 3},
     {"kmer_positions", (DL_FUNC)&kmer_positions, 2},
     {"sequence_kmer_positions", (DL_FUNC)&sequence_kmer_positions, 3},
     {"kmer_pair_pos", (DL_FUNC)&kmer_pair_pos, 2},
     {"count_kmers", (DL_FUNC)&count_kmers, 3},
+    {"make_kmer_h_index_file", (DL_FUNC)&make_kmer_h_index_file, 4},
+    {"count_kmers_file", (DL_FUNC)&count_kmers_file, 3},
     {NULL, NULL, 0}};
 
 void R_init_kmer_hash(DllInfo *info) { R_registerRoutines(info, NULL, call_methods, NULL, NULL); }

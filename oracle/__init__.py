@@ -276,6 +276,9 @@ class Reference:
         lib.ref_free_buf.argtypes = [C.c_void_p]
         lib.ref_pairs_join.restype = C.c_int64
         lib.ref_pairs_join.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_i32p)]
+        lib.ref_reads_parse.restype = C.c_int64
+        lib.ref_reads_parse.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_int64))]
+        lib.ref_reads_free.argtypes = [C.c_void_p]
         lib.ref_count_new.restype = C.c_void_p
         lib.ref_count_new.argtypes = [C.c_int]
         lib.ref_count_add.restype = C.c_int
@@ -306,6 +309,23 @@ class Reference:
         self.lib.ref_sizes(table._h, C.byref(U), C.byref(N), C.byref(P), C.byref(B), C.byref(W))
         table.U, table.N, table.P, table.buckets, table.new_kmers = U.value, N.value, P.value, B.value, W.value
         return table
+
+    def parse_reads(self, path: str):
+        """(names, sequences) of a FASTA/FASTQ file (plain or gz) as the reference's own parser reads it: klib kseq.h over
+        zlib, unmodified (oracle/ref_fasta.c; src/kmer_reader.c:41-77 is the reference's read loop)."""
+        names, seqs, lens = C.c_char_p(), C.c_void_p(), C.POINTER(C.c_int64)()
+        n = self.lib.ref_reads_parse(path.encode(), C.byref(names), C.byref(seqs), C.byref(lens))
+        if n < 0:
+            raise FileNotFoundError(path)
+        out_names = names.value.decode().split("\n")[:n] if n else []
+        ll = [lens[i] for i in range(n)]
+        raw = C.string_at(seqs, sum(ll) + n) if n else b""
+        out_seqs, o = [], 0
+        for ln in ll:
+            out_seqs.append(raw[o:o + ln]); o += ln + 1
+        for p_ in (names, seqs, lens):
+            self.lib.ref_reads_free(p_)
+        return out_names, out_seqs
 
     @staticmethod
     def available() -> bool:
