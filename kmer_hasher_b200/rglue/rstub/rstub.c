@@ -144,6 +144,7 @@ SEXP rstub_int_vector(int n, const int *values) {
 }
 typedef SEXP (*fn2)(SEXP, SEXP);
 typedef SEXP (*fn3)(SEXP, SEXP, SEXP);
+typedef SEXP (*fn4)(SEXP, SEXP, SEXP, SEXP);
 SEXP rstub_call(const char *name, int nargs, SEXP *args, char *errbuf, int errlen) {
   if (errbuf && errlen) errbuf[0] = 0;
   const R_CallMethodDef *r = routines;
@@ -155,7 +156,7 @@ SEXP rstub_call(const char *name, int nargs, SEXP *args, char *errbuf, int errle
   SEXP out = NULL;
   top = &here;
   if (setjmp(here) == 0) {
-    out = nargs == 2 ? ((fn2)r->fun)(args[0], args[1]) : ((fn3)r->fun)(args[0], args[1], args[2]);
+    out = nargs == 2 ? ((fn2)r->fun)(args[0], args[1]) : nargs == 3 ? ((fn3)r->fun)(args[0], args[1], args[2]) : ((fn4)r->fun)(args[0], args[1], args[2], args[3]);
   } else {
     if (errbuf && errlen) snprintf(errbuf, errlen, "%s", errmsg);
     protect_depth = depth;        /* R unwinds the protect stack on error */
