@@ -254,11 +254,15 @@ class PeerExchange:
         """Device-side: every rank's scatter has finished before any rank reads what it received."""
         dist.all_reduce(self._token, group=self.group)
 
-    def agree(self, status: int) -> int:
-        """The worst status any rank reports (a collective): what to do next is decided together, never by one rank alone."""
-        t = torch.tensor([int(status)], dtype=torch.int32, device=self.engine.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        return int(t.item())
+    def agree(self, status: int, sizes=(0, 0)):
+        """The worst status any rank reports, and every rank's (U, N) -- ONE small all-gather: what to do next is decided
+        together, never by one rank alone, and the global k-mer numbering needs no further collective."""
+        world = dist.get_world_size(self.group)
+        t = torch.tensor([int(status), int(sizes[0]), int(sizes[1])], dtype=torch.int64, device=self.engine.device)
+        allt = torch.empty(3 * world, dtype=torch.int64, device=self.engine.device)
+        dist.all_gather_into_tensor(allt, t, group=self.group)
+        a = allt.cpu().numpy().reshape(world, 3)
+        return int(a[:, 0].max()), a[:, 1].tolist(), a[:, 2].tolist()
 
     def close(self):
         torch.cuda.synchronize()
@@ -508,14 +512,14 @@ def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerE
     # -3: an owner overflowed or its fix-up lists did (the latter is local to one rank); -7: the position-order check
     # failed on one device.  The ranks agree on the worst status and act together: a rank must never enter the general
     # path's collectives alone.
-    worst = xchg.agree(status)
+    worst, U_all, N_all = xchg.agree(status, local.sizes[:2] if local is not None else (0, 0))
     if worst:
         if local is not None:
             local.free()
         if worst == 7:                                      # that device now ranks by bitmap match: same path again
             return sharded_build_p2p(own, L, k, engine, xchg, group, n_samples, order)
         return sharded_build(own, L, k, engine, group)
-    ix = ShardedIndex(local, k, rank, world, None, None, None, engine, splitters_dev=spl, group=group)
+    ix = ShardedIndex(local, k, rank, world, U_all, N_all, None, engine, splitters_dev=spl, group=group)
     ix.mixed = engine.L.kmg_index_order(local._handle()) == 0   # owner ranges are those of the mixed key
     ix.order = order
     return ix
@@ -553,14 +557,14 @@ def sharded_build_ranges(own_bytes, L: int, k: int, engine, xchg, group=None) ->
             status = -e.code
     finally:
         engine.shard_close(sh)
-    worst = xchg.agree(status)
+    worst, U_all, N_all = xchg.agree(status, local.sizes[:2] if local is not None else (0, 0))
     if worst:
         if local is not None:
             local.free()
         if worst == 7:                                         # a device switched to the bitmap rank variant: once more
             return sharded_build_ranges(own, L, k, engine, xchg, group)
         return sharded_build(own, L, k, engine, group)         # a region overflowed (a huge repeat): the exact-size path
-    ix = ShardedIndex(local, k, rank, world, None, None, None, engine, group=group)
+    ix = ShardedIndex(local, k, rank, world, U_all, N_all, None, engine, group=group)
     ix.mixed, ix.ranges, ix.order = True, True, 0
     return ix
 

@@ -210,10 +210,13 @@ class GlooExchange:
         offs = np.concatenate([[0], np.cumsum(rc)])
         self.slot.inbox = [(rk.numpy()[offs[r]:offs[r + 1]].view(np.uint64), rp.numpy()[offs[r]:offs[r + 1]]) for r in range(world)]
 
-    def agree(self, status):
-        t = torch.tensor([int(status)], dtype=torch.int32)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return int(t.item())
+    def agree(self, status, sizes=(0, 0)):
+        world = dist.get_world_size()
+        t = torch.tensor([int(status), int(sizes[0]), int(sizes[1])], dtype=torch.int64)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        a = torch.stack(allt).numpy()
+        return int(a[:, 0].max()), a[:, 1].tolist(), a[:, 2].tolist()
 
 
 class RegionEngine(OracleEngine):
