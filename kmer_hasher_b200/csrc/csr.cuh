@@ -41,7 +41,7 @@ rle_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos, 
   const uint64_t w0 = q0 + (uint64_t)warp * (32 * ITEMS);
   uint64_t key[ITEMS];
   uint32_t p[ITEMS];
-  uint32_t heads = 0, before[ITEMS], running = 0;
+  uint32_t heads = 0, running = 0;
   uint64_t carry = 0;                                  // key just before this warp item (lane 0's predecessor)
   uint32_t pcarry = 0;                                 // and its position
   bool bad = false;
@@ -69,9 +69,7 @@ rle_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos, 
     if (lane == 0) { prev = carry; pprev = pcarry; }
     const bool head = ok && (idx == 0 || key[i] != prev);
     bad |= ok && !head && p[i] <= pprev;               // same k-mer as the record before: its position must be larger
-    const unsigned bal = __ballot_sync(FULL, head);
-    before[i] = running + __popc(bal & lanemask_lt());
-    running += __popc(bal);
+    running += __popc(__ballot_sync(FULL, head));
     if (head) heads |= 1u << i;
     carry = __shfl_sync(FULL, key[i], 31);             // lane 0 uses it next round
     pcarry = __shfl_sync(FULL, p[i], 31);
@@ -92,14 +90,17 @@ rle_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos, 
     if (lane == 0) s_base = ea;
   }
   __syncthreads();
-  const uint64_t base = s_base + wbase;
+  uint64_t base = s_base + wbase;                      // heads before this warp's item i (ballots are cheaper than 16 live registers)
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    if ((heads >> i) & 1u) {
-      const uint64_t u = base + before[i];
+    const bool head = (heads >> i) & 1u;
+    const unsigned bal = __ballot_sync(FULL, head);
+    if (head) {
+      const uint64_t u = base + __popc(bal & lanemask_lt());
       ukeys[u] = hashed ? unmix64(key[i]) : key[i];        // grouped build: records carry mix64(key)
       ustart[u] = (uint32_t)(w0 + i * 32 + lane);
     }
+    base += __popc(bal);
   }
   if (q0 + TILE >= n && tid == 0) {                    // the last tile closes the CSR
     const uint64_t U = s_base + total;

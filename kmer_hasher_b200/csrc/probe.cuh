@@ -140,7 +140,7 @@ __device__ __forceinline__ uint2 resolve_key(const KeyHash &kh, uint64_t key, ui
 // flight at a time; there is no block-wide step after the tile is packed, so the kernel runs at the
 // random-access rate of HBM.
 template <int THREADS, int ITEMS, bool FROM_SEQ>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 4)
 probe_lookup_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, int64_t n_in, const uint64_t *__restrict__ n_dev,
                     const KeyHash kh, uint2 *__restrict__ found, const bool mixed = false) {
   constexpr int TILE = THREADS * ITEMS;
