@@ -637,7 +637,8 @@ static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P,
 template <bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
 static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s, int rb = RADIX_BITS) {
   const int rank = rank_variant();
-  const int shape = (rb == 8) ? g_sort_shape : (g_sort_shape == 2 ? 0 : g_sort_shape);
+  // the fused encode + first pass gains 4 % from 28 records per thread (its positions are 16-bit in shared memory), the record passes nothing
+  const int shape = (rb == 8) ? ((FROM_SEQ && g_sort_shape == 0) ? 1 : g_sort_shape) : (g_sort_shape == 2 ? 0 : g_sort_shape);
 #define KMG_GO(T, I, M, RK, RB) return launch_pass_cfg<PassCfg<T, I, M, RK, (RK >= 3 ? 4 : 8), RB>, FROM_SEQ, BinFn, NextFn, HAS_NEXT>(name, P, n_upper, s)
 #define KMG_SHAPES(RK, RB)                         \
   do {                                             \
@@ -1819,7 +1820,8 @@ static int owner_build(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, con
   uint64_t h_info[2] = {0, 0};
   SegMap h_seg{};
   const bool grouped = grouped_for(k, order, n);
-  const SortPlan gp = grouped_plan(n);
+  // the arrays are sized with slack (1.25-1.3x what an owner expects); the digit plan follows the expected record count
+  const SortPlan gp = grouped_plan(d_counts ? n * 10 / 13 : n * 4 / 5);
   auto body = [&]() -> int {
     TRY(scratch_alloc(sc, n, s, grouped ? gp.rb : RADIX_BITS));
     TRY(dalloc(&kb, (size_t)n, s));

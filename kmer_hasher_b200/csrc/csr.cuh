@@ -135,10 +135,18 @@ __device__ __forceinline__ uint64_t first_at_least(const uint64_t *h, uint64_t n
 }
 
 __device__ __forceinline__ void file_group(const uint64_t *__restrict__ h, uint64_t n, uint64_t lowmask, uint64_t i, const FixLists &fl) {
-  // h[i-1] and h[i] share the low bits and differ: a boundary between two k-mers inside one group
+  // h[i-1] and h[i] share the low bits and differ: a boundary between two k-mers inside one group.
+  // The group's extent: almost every group is a handful of records, so walk outwards a few steps (the lines were just
+  // streamed: L2 hits) and fall back to binary searches only for long groups (a repeat k-mer that happens to collide).
   const uint64_t low = h[i] & lowmask;
-  const uint64_t s = first_at_least(h, n, lowmask, low);
-  const uint64_t e = low == lowmask ? n : first_at_least(h, n, lowmask, low + 1);
+  constexpr int WALK = 24;
+  uint64_t s = i, e = i + 1;
+  int w = 0;
+  while (s > 0 && w < WALK && (h[s - 1] & lowmask) == low) { --s; ++w; }
+  if (s > 0 && (h[s - 1] & lowmask) == low) s = first_at_least(h, n, lowmask, low);
+  w = 0;
+  while (e < n && w < WALK && (h[e] & lowmask) == low) { ++e; ++w; }
+  if (e < n && (h[e] & lowmask) == low) e = low == lowmask ? n : first_at_least(h, n, lowmask, low + 1);
   if (e - s <= SMALL_GROUP) {
     bool first = true;                                   // the group's first boundary files the task
     const uint64_t h0 = h[s];
@@ -195,6 +203,16 @@ __global__ void small_fix_kernel(uint64_t *__restrict__ h, uint32_t *__restrict_
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const uint2 se = fl.small_tasks[t];
     const int c = (int)(se.y - se.x);
+    if (c <= 8) {                                          // the common case (2-3 records): sort in place, no staging arrays
+      for (int j = 1; j < c; ++j) {
+        const uint64_t x = h[se.x + j];
+        const uint32_t y = pos[se.x + j];
+        int m = j - 1;
+        while (m >= 0 && h[se.x + m] > x) { h[se.x + m + 1] = h[se.x + m]; pos[se.x + m + 1] = pos[se.x + m]; --m; }
+        if (m + 1 != j) { h[se.x + m + 1] = x; pos[se.x + m + 1] = y; }
+      }
+      continue;
+    }
     uint64_t hh[SMALL_GROUP];
     uint32_t pp[SMALL_GROUP];
     for (int j = 0; j < c; ++j) { hh[j] = h[se.x + j]; pp[j] = pos[se.x + j]; }
