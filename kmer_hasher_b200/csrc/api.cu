@@ -529,7 +529,7 @@ static void demote_rank_variant() {
 struct SortPlan { int rb, passes; int bits() const { return rb * passes; } };
 // Bits of mix64(key) the grouped build sorts on (kmg_tune "hash_bits": 0 = chosen from the record count, else a multiple
 // of 8 or 9; tests lower it to force collisions).  With b bits ~N^2 / 2^(b+1) pairs of distinct k-mers collide and are
-// fixed up afterwards: 36 bits (4 passes of 9) up to 2^26 records, 40 bits (5 passes of 8) beyond.
+// fixed up afterwards: 32 bits (4 passes of 8) up to 48 M records, 36 bits (4 passes of 9) up to 2^26, 40 bits (5 x 8) beyond.
 static int g_hash_bits = 0;
 static int g_hash_rb = 0;      // kmg_tune "hash_rb": force the digit width (tuning runs)
 static int g_scatter_bitmap = 0; // kmg_tune "scatter_bitmap": 1 = region scatter ranks by bitmap match even where the one-atomic variant is valid
@@ -541,9 +541,11 @@ static SortPlan grouped_plan(int64_t n_upper) {
     return SortPlan{rb, g_hash_bits / rb};
   }
   if (g_hash_rb > 0) return SortPlan{g_hash_rb, (36 + g_hash_rb - 1) / g_hash_rb};
-  // measured on B200 (profiles/r02_sortbench_*.log): a 9-bit pass costs 1.18x an 8-bit one and 36 bits leave ~16x the colliding
-  // groups of 40, so 4 x 9 wins up to ~64 M records (2.11 vs 2.17 ms at 40 M) and 5 x 8 beyond (11.7 vs 12.1 ms at 250 M);
-  // 4 x 8 = 32 bits loses everywhere to the fix-up of its collisions, 10-bit digits cost 1.66x
+  // measured on B200 (profiles/r02_sortbench_*_b.log): a 9-bit pass costs 1.18x an 8-bit one, 10-bit 1.66x, and b sorted bits
+  // leave ~N^2 / 2^(b+1) colliding pairs to detect and fix.  At 40 M records 4 x 8 = 32 bits wins (1.84 ms against 1.92 for
+  // 4 x 9 and 1.97 for 5 x 8); at 250 M the 7 M colliding pairs of 32 bits cost 4 ms and 5 x 8 = 40 bits wins (10.4 ms against
+  // 11.5 and 12.5); 4 x 9 = 36 bits covers the stretch in between.
+  if (n_upper <= 48000000) return SortPlan{8, 4};
   return n_upper <= (int64_t(1) << 26) ? SortPlan{9, 4} : SortPlan{8, 5};
 }
 // is the grouped build used for this k and requested order?  From k = 21 on (keys of more than 40 bits: a sort by key would
