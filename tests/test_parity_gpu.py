@@ -752,3 +752,38 @@ def test_region_exchange_single_process(kh, oracle, world, k, L):
         ix.free()
     for h in handles:
         eng.shard_close(h)
+
+
+def test_arena_cache_can_be_trimmed(kh):
+    """an R session must be able to give the cached device memory of freed indexes back (kmg_trim)."""
+    from kmer_hasher_b200 import synth, _lib
+    L_ = _lib.load()
+    seq = synth.config_c2(2_000_000)
+    kh.make_kmer_hash(seq, 32).free()
+    assert L_.kmg_cached_bytes() > 0                       # freed blocks are kept for the next build ...
+    _lib.check(L_.kmg_trim())
+    assert L_.kmg_cached_bytes() == 0                      # ... until asked to return them
+    ix = kh.make_kmer_hash(seq, 32)                        # and the library keeps working
+    assert ix.sizes[1] == len(seq) - 31
+    ix.free()
+
+
+def test_pageable_buffers_take_the_staged_path(kh, oracle):
+    """Large pageable inputs/outputs (what R hands the glue) go through pinned staging slots and host copy threads; the
+    result must be the same bytes as with device or pinned buffers (chunk boundaries, odd sizes)."""
+    import torch
+    from kmer_hasher_b200 import synth
+    seq = synth.config_c3(12_000_003)                      # > 8 MB: staged upload; pos matrix 96 MB: two staged chunks
+    ix_pageable = kh.make_kmer_hash(seq, 21)               # numpy array = pageable
+    ix_device = kh.make_kmer_hash(torch.from_numpy(seq).cuda(), 21)
+    assert ix_pageable.sizes == ix_device.sizes
+    U, N, _ = ix_device.sizes
+    got = kh.kmer_pos(ix_pageable, 2 | 8)                  # pageable numpy outputs
+    dpos = torch.empty((N, 2), dtype=torch.int32, device="cuda")
+    dcnt = torch.empty(U, dtype=torch.int32, device="cuda")
+    kh.kmer_pos(ix_device, 2 | 8, out={"pos": dpos, "count": dcnt})
+    assert np.array_equal(got["pos"], dpos.cpu().numpy()) and np.array_equal(got["count"], dcnt.cpu().numpy())
+    pin = kh.pinned_empty((N, 2), np.int32)
+    kh.kmer_pos(ix_device, 2, out={"pos": pin})
+    assert np.array_equal(pin, got["pos"])
+    ix_pageable.free(); ix_device.free()
