@@ -320,7 +320,6 @@ def probe_leg(kh, torch, _lib, w, seq_pin, seq_dev, k, steps, hbm_peak):
             "unit": "GB/s", "frac": merge_bytes / ((ms_b + ms_e) * 1e-3) / 1e9 / hbm_peak,
             "note": "graded denominator = SURVEY.md 8d's sort-merge formulation (Lq + 32 Nq + 8 U + 12 M); the shipped probe is one "
                     "random table access per window, which moves a whole 128-byte line of HBM per lookup",
-            "lookup_kernel": "probe_match_kernel: table lookups + ordered compaction of the hits + 64-bit scan in one launch",
             "lookup_line_bytes": int(128 * Nq), "lookup_line_GBps": 128 * Nq / (lookup_ms * 1e-3) / 1e9 if lookup_ms else None,
             "lookup_line_frac": 128 * Nq / (lookup_ms * 1e-3) / 1e9 / hbm_peak if lookup_ms else None,
             "ncu_dram_bytes_lookup": ncu["traffic_bytes_per_launch"] if ncu else None,

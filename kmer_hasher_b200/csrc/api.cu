@@ -532,7 +532,7 @@ struct SortPlan { int rb, passes; int bits() const { return rb * passes; } };
 // fixed up afterwards: 32 bits (4 passes of 8) up to 48 M records, 36 bits (4 passes of 9) up to 2^26, 40 bits (5 x 8) beyond.
 static int g_hash_bits = 0;
 static int g_hash_rb = 0;      // kmg_tune "hash_rb": force the digit width (tuning runs)
-static int g_probe_blocks = 4;   // kmg_tune "probe_blocks": resident blocks per SM the fused probe kernel is compiled for (3: no spills, 4: more in flight)
+static int g_scatter_shape = 0;
 static int g_scatter_bitmap = 0; // kmg_tune "scatter_bitmap": 1 = region scatter ranks by bitmap match even where the one-atomic variant is valid
 static int g_hash_cas = 0;     // kmg_tune "hash_cas": 1 = always build the probe's key table by CAS (tests, tuning)
 static int g_fix_cap = 0;      // kmg_tune "fix_cap": capacity of the short-group task list (0 = max(2^20, N/8)); tests shrink it
@@ -575,8 +575,8 @@ extern "C" int kmg_tune(const char *key, int value) {
   if (key && !strcmp(key, "sort_dbg")) { g_sort_dbg = (uint32_t)value; return KMG_OK; }
   if (key && !strcmp(key, "fix_cap")) { g_fix_cap = value > 0 ? value : 0; return KMG_OK; }
   if (key && !strcmp(key, "hash_cas")) { g_hash_cas = value != 0; return KMG_OK; }
-  if (key && !strcmp(key, "probe_blocks")) { g_probe_blocks = value == 3 ? 3 : 4; return KMG_OK; }
   if (key && !strcmp(key, "scatter_bitmap")) { g_scatter_bitmap = value != 0; return KMG_OK; }
+  if (key && !strcmp(key, "scatter_shape")) { g_scatter_shape = value; return KMG_OK; }
   if (key && !strcmp(key, "hash_bits")) {
     if (value != 0 && (value < 8 || value > 56 || (value % 8 && value % 9 && value % 10))) return fail(KMG_ERR_ARG, "hash_bits must be 0 (auto) or a multiple of 8, 9 or 10 in [8,56]");
     g_hash_bits = value;
@@ -625,7 +625,7 @@ extern "C" int kmg_selftest_lane_order(uint32_t *failures) {
   if (!failures) return fail(KMG_ERR_ARG, "failures is NULL");
   return lane_order_failures(failures);
 }
-constexpr int SORT_TILE_MIN = 5120;   // status sizing: smallest tile of any shape
+constexpr int SORT_TILE_MIN = 4096;   // status sizing: smallest tile of any shape
 
 template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false>
 static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
@@ -1293,8 +1293,9 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
   QueryStats *qs = nullptr;
   Pair64 *status = nullptr;
   uint32_t *ticket = nullptr;
+  uint2 *found = nullptr;
   auto body = [&]() -> int {
-    const uint64_t tiles = ceil_div<uint64_t>((uint64_t)total, PROBE_TILE);
+    const uint64_t tiles = ceil_div<uint64_t>((uint64_t)total, COMPACT_TILE);
     TRY(dalloc(&q->hit_i, (size_t)total, s));
     TRY(dalloc(&q->hit_start, (size_t)total, s));
     TRY(dalloc(&q->row_off, (size_t)total, s));
@@ -1305,16 +1306,17 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
     CU(cudaMemsetAsync(status, 0, tiles * sizeof(Pair64), s));
     CU(cudaMemsetAsync(ticket, 0, 4, s));
     KeyHash kt{ix->hash, ix->hash_nb, ix->hash_hbits};
-    // lookups and ordered compaction of the hits in ONE kernel (no per-window (slot, count) array in between)
-#define KMG_MATCH(SEQ, MINB, NAME, ...) LAUNCH(NAME, s, probe_match_kernel<PROBE_THREADS, PROBE_ITEMS, SEQ, MINB><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(__VA_ARGS__))
+    TRY(dalloc(&found, (size_t)total, s));
+    const unsigned ltiles = (unsigned)ceil_div<uint64_t>((uint64_t)total, PROBE_TILE);
     if (from_seq) {
-      if (g_probe_blocks == 3) KMG_MATCH(true, 3, "probe_match", sv, nullptr, nullptr, 0, nullptr, kt, false, sv.s0 + sv.k, q->hit_i, q->hit_start, q->row_off, qs, status, ticket);
-      else KMG_MATCH(true, 4, "probe_match", sv, nullptr, nullptr, 0, nullptr, kt, false, sv.s0 + sv.k, q->hit_i, q->hit_start, q->row_off, qs, status, ticket);
+      LAUNCH("probe_lookup", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, true><<<ltiles, PROBE_THREADS, 0, s>>>(sv, nullptr, 0, nullptr, kt, found));
+      LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, COMPACT_ITEMS, true><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+                                     found, sv.s0 + sv.k, nullptr, total, nullptr, q->hit_i, q->hit_start, q->row_off, qs, status, ticket));
     } else {
-      if (g_probe_blocks == 3) KMG_MATCH(false, 3, "probe_match_rec", sv, d_keys, d_i, n, d_n, kt, mixed, 0, q->hit_i, q->hit_start, q->row_off, qs, status, ticket);
-      else KMG_MATCH(false, 4, "probe_match_rec", sv, d_keys, d_i, n, d_n, kt, mixed, 0, q->hit_i, q->hit_start, q->row_off, qs, status, ticket);
+      LAUNCH("probe_lookup_rec", s, probe_lookup_kernel<PROBE_THREADS, PROBE_ITEMS, false><<<ltiles, PROBE_THREADS, 0, s>>>(sv, d_keys, n, d_n, kt, found, mixed));
+      LAUNCH("probe_compact", s, probe_compact_kernel<PROBE_THREADS, COMPACT_ITEMS, false><<<(unsigned)tiles, PROBE_THREADS, 0, s>>>(
+                                     found, 0, d_i, n, d_n, q->hit_i, q->hit_start, q->row_off, qs, status, ticket));
     }
-#undef KMG_MATCH
     QueryStats h;
     CU(cudaMemcpyAsync(&h, qs, sizeof h, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -1322,10 +1324,11 @@ static int query_common(const kmg_index *cix, bool from_seq, const SeqView &sv, 
     return KMG_OK;
   };
   rc = body();
-  dfree(qs, s); dfree(status, s); dfree(ticket, s);
+  dfree(qs, s); dfree(status, s); dfree(ticket, s); dfree(found, s);
   if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_query_free(q); return rc; }
   // a lookup moves one 128-byte line of HBM (measured: tools/micro/gups.cu), whatever it uses of it
-  prof_bytes(from_seq ? "probe_match" : "probe_match_rec", (from_seq ? (double)sv.avail : 12.0 * total) + 128.0 * total + 16.0 * q->H);
+  prof_bytes(from_seq ? "probe_lookup" : "probe_lookup_rec", (from_seq ? (double)sv.avail : 8.0 * total) + 128.0 * total + 8.0 * total);
+  prof_bytes("probe_compact", 8.0 * total + 16.0 * q->H);
   *out = q;
   if (M) *M = q->M;
   return KMG_OK;
@@ -1957,9 +1960,12 @@ extern "C" int kmg_shard_scatter_ranges(const kmg_shard *sh, int nparts, int ran
     P.hashed = 1;
     P.peer = tab;
     P.bin = RangeBin{(uint32_t)nparts};
-    if (rank_variant() >= 3 && !g_scatter_bitmap)
-      TRY((launch_pass_cfg<PassCfg<256, 24, 2, 3, 4, 4>, true, RangeBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
-    else
+    // kmg_tune "scatter_shape" (tuning runs): more resident tiles per SM = more remote stores in flight on the NVLink
+    if (rank_variant() >= 3 && !g_scatter_bitmap) {
+      if (g_scatter_shape == 1) TRY((launch_pass_cfg<PassCfg<256, 24, 3, 3, 4, 4>, true, RangeBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
+      else if (g_scatter_shape == 2) TRY((launch_pass_cfg<PassCfg<256, 16, 4, 3, 4, 4>, true, RangeBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
+      else TRY((launch_pass_cfg<PassCfg<256, 24, 2, 3, 4, 4>, true, RangeBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
+    } else
       TRY((launch_pass_cfg<PassCfg<256, 24, 2, 0, 8, 4>, true, RangeBin, NoBin, false, true>("scatter_peer", P, sh->sv.nstarts, s)));
     prof_bytes("scatter_peer", (double)sh->sv.avail + 12.0 * (double)sh->sv.nstarts);
     return KMG_OK;

@@ -277,110 +277,9 @@ probe_compact_kernel(const uint2 *__restrict__ found, int64_t coord0, const int3
   if (q0 + TILE >= total && tid == 0) { qs->H = s_bh + th; qs->M = s_br + tr; }
 }
 
-// ---- passes 1 + 2 in one kernel: look the windows up AND compact the hits ---------------------------------------------
-// What probe_lookup_kernel + probe_compact_kernel do, without the (first slot, count) array in between (16 bytes per window
-// of HBM traffic): a thread's ITEMS consecutive windows stay in registers from the table lookups to the ordered compaction.
-// Tiles take their number from a ticket so that the chained scan of (hits, rows) never waits on a tile that is not resident;
-// a tile's aggregate is only needed after its own lookups, by which time its predecessors have long published theirs.
-template <int THREADS, int ITEMS, bool FROM_SEQ, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-probe_match_kernel(const SeqView sv, const uint64_t *__restrict__ keys_in, const int32_t *__restrict__ i_in, int64_t n_in,
-                   const uint64_t *__restrict__ n_dev, const KeyHash kh, const bool mixed, const int64_t coord0,
-                   int32_t *__restrict__ hit_i, uint32_t *__restrict__ hit_start, uint64_t *__restrict__ row_off, QueryStats *qs,
-                   Pair64 *status, uint32_t *ticket) {
-  constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32, BATCH = 4;
-  static_assert(ITEMS % BATCH == 0, "items in batches");
-  static_assert(TILE <= 4096, "rows inside a tile: at most TILE * (2^32 - 1) < 2^48");
-  __shared__ TileCodes<FROM_SEQ ? TILE : 16> tc;
-  __shared__ uint32_t s_tile, s_wh[WARPS];
-  __shared__ uint64_t s_wr[WARPS], s_bh, s_br;
-  __shared__ int32_t st_i[TILE];
-  __shared__ uint32_t st_start[TILE], st_row[TILE];
-  __shared__ uint16_t st_row_hi[TILE];
-  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const int64_t q0 = (int64_t)tile * TILE;
-  const int64_t total = FROM_SEQ ? sv.nstarts : (n_dev ? min((int64_t)*n_dev, n_in) : n_in);
-  if (q0 >= total) return;
-  const int t0 = tid * ITEMS;
-  bool special = false;
-  if constexpr (FROM_SEQ) special = tile_pack<TILE, THREADS>(sv, q0, tc);
-  uint2 f[ITEMS];
-  uint64_t key = 0;
-  const uint64_t kmask = key_mask(FROM_SEQ ? sv.k : 32);
-#pragma unroll
-  for (int i0 = 0; i0 < ITEMS; i0 += BATCH) {
-    uint4 s0[BATCH], s1[BATCH];
-    uint64_t kk[BATCH], home[BATCH];
-    bool ok[BATCH];
-#pragma unroll
-    for (int j = 0; j < BATCH; ++j) {
-      const int i = i0 + j;
-      if constexpr (FROM_SEQ) {
-        if (i == 0) key = tile_key<TILE>(tc, t0, sv.k);
-        else {
-          const int p = t0 + i + sv.k - 1;
-          key = ((key << 2) | ((tc.codes[p >> 4] >> (30 - 2 * (p & 15))) & 3u)) & kmask;
-        }
-        ok[j] = tile_valid<TILE>(sv, tc, q0, t0 + i, special);
-      } else {
-        ok[j] = q0 + t0 + i < total;
-        key = ok[j] ? ld_stream_u64(keys_in + q0 + t0 + i) : 0;
-        if (mixed) key = unmix64(key);
-      }
-      kk[j] = key;
-      home[j] = kh.bucket(key);
-      if (ok[j]) ld_stream_sector(kh.slots + home[j] * BUCKET_SLOTS, s0[j], s1[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < BATCH; ++j) f[i0 + j] = ok[j] ? resolve_key(kh, kk[j], home[j], s0[j], s1[j]) : make_uint2(0u, 0u);
-  }
-  // ---- ordered compaction of the tile's hits + chained scan (as probe_compact_kernel)
-  uint32_t hmine = 0;
-  uint64_t rmine = 0;
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) { hmine += f[i].y != 0; rmine += f[i].y; }
-  const uint32_t hincl = warp_incl_scan(hmine);
-  const uint64_t rincl = warp_incl_scan64(rmine);
-  if (lane == 31) { s_wh[warp] = hincl; s_wr[warp] = rincl; }
-  __syncthreads();
-  uint64_t bh = 0, br = 0, th = 0, tr = 0;
-#pragma unroll
-  for (int w = 0; w < WARPS; ++w) {
-    if (w < (int)warp) { bh += s_wh[w]; br += s_wr[w]; }
-    th += s_wh[w]; tr += s_wr[w];
-  }
-  if (warp == 0) {
-    uint64_t ea, eb;
-    pair_lookback(status, tile, th, tr, ea, eb);
-    if (lane == 0) { s_bh = ea; s_br = eb; }
-  }
-  {
-    uint32_t hl = (uint32_t)bh + (hincl - hmine);
-    uint64_t rl = br + (rincl - rmine);
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      if (f[i].y) {
-        st_i[hl] = FROM_SEQ ? (int32_t)(coord0 + q0 + t0 + i) : i_in[q0 + t0 + i];
-        st_start[hl] = f[i].x;
-        st_row[hl] = (uint32_t)rl;
-        st_row_hi[hl] = (uint16_t)(rl >> 32);
-        ++hl;
-        rl += f[i].y;
-      }
-    }
-  }
-  __syncthreads();
-  const uint64_t gh = s_bh, gr = s_br;
-  for (uint32_t idx = tid; idx < (uint32_t)th; idx += THREADS) {
-    hit_i[gh + idx] = st_i[idx];
-    hit_start[gh + idx] = st_start[idx];
-    row_off[gh + idx] = gr + (((uint64_t)st_row_hi[idx] << 32) | st_row[idx]);
-  }
-  if (q0 + TILE >= total && tid == 0) { qs->H = s_bh + th; qs->M = s_br + tr; }
-}
+// (A fused lookup + compaction kernel was measured in round 2 and dropped: keeping a thread's eight (slot, count) pairs in
+// registers through a ticket-ordered chained scan costs the latency-bound lookups more -- 29 KB of staging per block, spills
+// at 64 registers -- than the 16 bytes per window of HBM traffic it saves: 3.57 ms against 2.73 + 0.62; profiles/r02_notes.md.)
 
 // Emit rows [first, first+nrows): row r belongs to hit h = largest h with row_off[h] <= r; it pairs
 // the hit's query coordinate with the (r - row_off[h])-th position of its k-mer.

@@ -701,6 +701,9 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = torch.device("cuda", torch.cuda.current_device())
     engine = CudaEngine(dev)
+    for key in ("scatter_shape", "scatter_bitmap"):          # tuning runs: KMG_TUNE_scatter_shape=1 ...
+        if os.environ.get("KMG_TUNE_" + key):
+            engine._lib.check(engine.L.kmg_tune(key.encode(), int(os.environ["KMG_TUNE_" + key])))
     strong = args.scaling == "strong"
     Ltot = L if strong else L * world
     if Ltot > 2**31 - 2:
