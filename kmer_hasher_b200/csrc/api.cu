@@ -532,6 +532,7 @@ struct SortPlan { int rb, passes; int bits() const { return rb * passes; } };
 // fixed up afterwards: 32 bits (4 passes of 8) up to 48 M records, 36 bits (4 passes of 9) up to 2^26, 40 bits (5 x 8) beyond.
 static int g_hash_bits = 0;
 static int g_hash_rb = 0;      // kmg_tune "hash_rb": force the digit width (tuning runs)
+static int g_no_regions = 0;     // kmg_tune "no_regions": 1 = the grouped build's first pass takes its bin sizes from a histogram sweep (tests, tuning)
 static int g_scatter_shape = 0;
 static int g_scatter_bitmap = 0; // kmg_tune "scatter_bitmap": 1 = region scatter ranks by bitmap match even where the one-atomic variant is valid
 static int g_hash_cas = 0;     // kmg_tune "hash_cas": 1 = always build the probe's key table by CAS (tests, tuning)
@@ -577,6 +578,7 @@ extern "C" int kmg_tune(const char *key, int value) {
   if (key && !strcmp(key, "hash_cas")) { g_hash_cas = value != 0; return KMG_OK; }
   if (key && !strcmp(key, "scatter_bitmap")) { g_scatter_bitmap = value != 0; return KMG_OK; }
   if (key && !strcmp(key, "scatter_shape")) { g_scatter_shape = value; return KMG_OK; }
+  if (key && !strcmp(key, "no_regions")) { g_no_regions = value != 0; return KMG_OK; }
   if (key && !strcmp(key, "hash_bits")) {
     if (value != 0 && (value < 8 || value > 56 || (value % 8 && value % 9 && value % 10))) return fail(KMG_ERR_ARG, "hash_bits must be 0 (auto) or a multiple of 8, 9 or 10 in [8,56]");
     g_hash_bits = value;
@@ -627,23 +629,26 @@ extern "C" int kmg_selftest_lane_order(uint32_t *failures) {
 }
 constexpr int SORT_TILE_MIN = 4096;   // status sizing: smallest tile of any shape
 
-template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false>
-static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s) {
+template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false, bool SEGS = false>
+static int launch_pass_cfg(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s, int extra_tiles = 0) {
   using S = PassSmem<Cfg, FROM_SEQ>;
-  auto kern = scatter_pass_kernel<Cfg, FROM_SEQ, BinFn, NextFn, HAS_NEXT, PEER>;
+  if constexpr (!FROM_SEQ && !PEER && !SEGS) {             // a segmented record source runs the separately compiled variant
+    if (P.segs) return launch_pass_cfg<Cfg, FROM_SEQ, BinFn, NextFn, HAS_NEXT, PEER, true>(name, P, n_upper, s, extra_tiles);
+  }
+  auto kern = scatter_pass_kernel<Cfg, FROM_SEQ, BinFn, NextFn, HAS_NEXT, PEER, SEGS>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
-  const int64_t tiles = ceil_div<int64_t>(n_upper, Cfg::TILE);
+  const int64_t tiles = ceil_div<int64_t>(n_upper, Cfg::TILE) + extra_tiles;   // extra: a segmented source has one partial tile per segment
   if (tiles == 0) return KMG_OK;
   LAUNCH(name, s, kern<<<(unsigned)tiles, Cfg::THREADS, sizeof(S), s>>>(P));
   return KMG_OK;
 }
 // rb: digit width of the pass (bins = 2^rb); P.bin / P.next must carry the matching mask
 template <bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT>
-static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s, int rb = RADIX_BITS) {
+static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int64_t n_upper, cudaStream_t s, int rb = RADIX_BITS, int extra_tiles = 0) {
   const int rank = rank_variant();
   // the fused encode + first pass gains 4 % from 28 records per thread (its positions are 16-bit in shared memory), the record passes nothing
   const int shape = (rb == 8) ? ((FROM_SEQ && g_sort_shape == 0) ? 1 : g_sort_shape) : (g_sort_shape == 2 ? 0 : g_sort_shape);
-#define KMG_GO(T, I, M, RK, RB) return launch_pass_cfg<PassCfg<T, I, M, RK, (RK >= 3 ? 4 : 8), RB>, FROM_SEQ, BinFn, NextFn, HAS_NEXT>(name, P, n_upper, s)
+#define KMG_GO(T, I, M, RK, RB) return launch_pass_cfg<PassCfg<T, I, M, RK, (RK >= 3 ? 4 : 8), RB>, FROM_SEQ, BinFn, NextFn, HAS_NEXT>(name, P, n_upper, s, extra_tiles)
 #define KMG_SHAPES(RK, RB)                         \
   do {                                             \
     if (shape == 1) KMG_GO(256, 28, 2, RK, RB);    \
@@ -662,6 +667,13 @@ static int launch_pass(const char *name, const PassParams<BinFn, NextFn> &P, int
 #undef KMG_SHAPES
 #undef KMG_GO
   return fail(KMG_ERR_ARG, "bad sort configuration");
+}
+
+// records per tile of a RECORD pass with digits of rb bits (mirrors launch_pass's choice of shape)
+static uint32_t record_tile(int rb) {
+  const int shape = (rb == 8) ? g_sort_shape : (g_sort_shape == 2 ? 0 : g_sort_shape);
+  if (rank_variant() == 4 || rb == 10) return 256 * 24;
+  return shape == 1 ? 256 * 28 : shape == 2 ? 256 * 20 : 256 * 24;
 }
 
 // Scratch shared by the sort passes of one build.
@@ -684,7 +696,7 @@ static int scratch_clear(SortScratch &sc, cudaStream_t s) {
 static int scratch_alloc(SortScratch &sc, int64_t n_upper, cudaStream_t s, int rb = RADIX_BITS) {
   sc.small_words = 2 * SortScratch::H + RADIX + 16 + sizeof(IndexStats) / 4;
   TRY(dalloc(&sc.small, sc.small_words, s));
-  const size_t tiles = (size_t)ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, SORT_TILE_MIN);
+  const size_t tiles = (size_t)ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, SORT_TILE_MIN) + MAX_SEGS + 1;   // segment-aligned tiles: one partial tile per segment
   sc.status_words = tiles << rb;
   TRY(dalloc(&sc.status, sc.status_words, s));
   return scratch_clear(sc, s);
@@ -746,24 +758,26 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
 // final_pos (optional): the last pass writes its positions there instead of into the ping-pong buffer
 // (the array the index keeps), so `pa` is meaningless afterwards.
 static int sort_tail(SortScratch &sc, SortPlan plan, int first_pass, bool has_next, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
-                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr, const SegMap *seg0 = nullptr) {
+                     uint32_t *&pb, int64_t n_upper, cudaStream_t s, uint32_t *final_pos = nullptr, const TileSegs *seg0 = nullptr, int nsegs0 = 0,
+                     int end_pass = -1) {
   const int R = plan.passes, rb = plan.rb;
   const uint32_t mask = (1u << rb) - 1;
-  for (int r = first_pass; r < R; ++r) {
+  for (int r = first_pass; r < (end_pass > 0 ? end_pass : R); ++r) {
     PassParams<DigitBin, DigitBin> P{};
     P.keys_in = ka; P.pos_in = pa; P.keys_out = kb; P.pos_out = (final_pos && r == R - 1) ? final_pos : pb;
     P.gbase = sc.gbase(r); P.hist_next = sc.hist(r + 1);
     P.status = sc.status; P.ticket = sc.ticket(r); P.epoch = (uint32_t)(r + 1);
     P.n_records = &sc.stats()->n;
-    P.seg = r == first_pass ? seg0 : nullptr;               // records in regions (owner side of a region-mode scatter)
+    P.segs = r == first_pass ? seg0 : nullptr;              // the first pass may read a segmented source (TileSegs)
+    const int extra = r == first_pass && seg0 ? nsegs0 : 0;
     P.bin = DigitBin{r * rb, mask}; P.next = DigitBin{(r + 1) * rb, mask};
     P.dbg = g_sort_dbg;
     P.trace = (r == 2 && g_trace && ceil_div<int64_t>(n_upper, SORT_TILE_MIN) <= g_trace_tiles) ? g_trace : nullptr;   // trace the third pass
     if (has_next && r + 1 < R) {
-      TRY((launch_pass<false, DigitBin, DigitBin, true>("sort_pass_hist", P, n_upper, s, rb)));
+      TRY((launch_pass<false, DigitBin, DigitBin, true>("sort_pass_hist", P, n_upper, s, rb, extra)));
       TRY(launch_scan_hist(rb, s, sc.hist(r + 1), sc.gbase(r + 1), (uint64_t *)nullptr));
     } else {
-      TRY((launch_pass<false, DigitBin, DigitBin, false>("sort_pass", P, n_upper, s, rb)));
+      TRY((launch_pass<false, DigitBin, DigitBin, false>("sort_pass", P, n_upper, s, rb, extra)));
     }
     std::swap(ka, kb);
     std::swap(pa, pb);
@@ -795,15 +809,22 @@ static int fix_groups(SortScratch &sc, int bits, uint64_t *keys, uint32_t *pos, 
 }
 
 // Grouped build: equal k-mers contiguous, k-mers in the order of (low bits of mix64(key), mix64(key)).
+// regions (the default): the first pass needs no histogram of its digit -- the mixed digit is uniform, so every bin gets its
+// own region of 1.25x the mean bin size and the pass writes bin b from b * cap on; its last tile leaves the bins' sizes,
+// from which the second pass reads the regions tile by tile (TileSegs).  This drops the histogram sweep over the sequence
+// (hist_seq_kernel: 0.41 ms of 11.7 at 250 Mbp).  A bin that outgrows its region (a k-mer with more copies than a quarter of
+// a mean bin) sets a flag, the tile's records are dropped, and the caller redoes the build with the histogram.
 static int build_grouped(const SeqView &sv, SortPlan plan, kmg_index *ix, SortScratch &sc, uint64_t *&ka, uint32_t *&pa, uint64_t *&kb,
-                         uint32_t *&pb, int64_t n_upper, cudaStream_t s, bool *overflow) {
-  const int R = plan.passes, rb = plan.rb;
+                         uint32_t *&pb, int64_t n_upper, cudaStream_t s, bool *overflow, bool regions, bool *region_overflow) {
+  const int R = plan.passes, rb = plan.rb, NB = 1 << rb;
   const uint32_t mask = (1u << rb) - 1;
-  const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
-  const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
-  LAUNCH("hist_seq", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, HashDigitBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), HashDigitBin{0, mask}));
-  TRY(launch_scan_hist(rb, s, sc.hist(0), sc.gbase(0), &sc.stats()->n));
-  {
+  uint64_t *kr = nullptr, *d_counts = nullptr;
+  uint32_t *pr = nullptr, *d_over = nullptr;
+  TileSegs *segs = nullptr;
+  uint32_t h_over = 0;
+  regions = regions && R > 1 && NB <= MAX_SEGS && n_upper <= (int64_t)1600000000;   // region offsets are 32-bit signed in the pass
+  const uint32_t cap = (uint32_t)(((uint64_t)(n_upper / NB) * 5 / 4 + 4096 + 15) & ~uint64_t(15));
+  auto body = [&]() -> int {
     PassParams<DigitBin, DigitBin> P{};
     P.sv = sv; P.keys_out = ka; P.pos_out = pa;
     P.gbase = sc.gbase(0); P.hist_next = sc.hist(1);
@@ -811,23 +832,51 @@ static int build_grouped(const SeqView &sv, SortPlan plan, kmg_index *ix, SortSc
     P.hashed = 1;
     P.dbg = g_sort_dbg;
     P.bin = DigitBin{0, mask}; P.next = DigitBin{rb, mask};
-    if (R > 1) {
+    if (regions) {
+      TRY(dalloc(&kr, (size_t)NB * cap, s));
+      TRY(dalloc(&pr, (size_t)NB * cap, s));
+      TRY(dalloc(&d_counts, (size_t)MAX_SEGS, s));
+      TRY(dalloc(&d_over, 4, s));
+      TRY(dalloc(&segs, 1, s));
+      CU(cudaMemsetAsync(d_counts, 0, MAX_SEGS * sizeof(uint64_t), s));
+      LAUNCH("region_gbase", s, region_gbase_kernel<<<1, 256, 0, s>>>(sc.gbase(0), NB, cap, d_over));
+      P.keys_out = kr; P.pos_out = pr;
+      P.bin_counts = d_counts; P.bin_cap = cap; P.bin_overflow = d_over;
       TRY((launch_pass<true, DigitBin, DigitBin, true>("sort_pass_seq", P, n_upper, s, rb)));
       TRY(launch_scan_hist(rb, s, sc.hist(1), sc.gbase(1), (uint64_t *)nullptr));
+      LAUNCH("tile_segs", s, tile_segs_kernel<<<1, MAX_SEGS, 0, s>>>(d_counts, NB, (uint64_t)cap, record_tile(rb), segs, &sc.stats()->n));
+      CU(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, s));
+      // second pass: regions -> (ka, pa); afterwards the region arrays are free
+      TRY(sort_tail(sc, plan, 1, true, kr, pr, ka, pa, n_upper, s, nullptr, segs, NB, 2));
+      std::swap(kr, ka); std::swap(pr, pa);                  // sort_tail swapped (in, out): the data is in what it calls `kr`
+      TRY(sort_tail(sc, plan, 2, true, ka, pa, kb, pb, n_upper, s));
     } else {
-      TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq", P, n_upper, s, rb)));
+      const int64_t tiles = ceil_div<int64_t>(n_upper, HIST_TILE);
+      const unsigned hgrid = (unsigned)std::min<int64_t>(tiles, (int64_t)g_ctx.sms * 2);
+      LAUNCH("hist_seq", s, hist_seq_kernel<HIST_THREADS, HIST_ITEMS, HashDigitBin><<<hgrid, HIST_THREADS, 0, s>>>(sv, sc.hist(0), HashDigitBin{0, mask}));
+      TRY(launch_scan_hist(rb, s, sc.hist(0), sc.gbase(0), &sc.stats()->n));
+      if (R > 1) {
+        TRY((launch_pass<true, DigitBin, DigitBin, true>("sort_pass_seq", P, n_upper, s, rb)));
+        TRY(launch_scan_hist(rb, s, sc.hist(1), sc.gbase(1), (uint64_t *)nullptr));
+      } else {
+        TRY((launch_pass<true, DigitBin, DigitBin, false>("sort_pass_seq", P, n_upper, s, rb)));
+      }
+      TRY(sort_tail(sc, plan, 1, true, ka, pa, kb, pb, n_upper, s));   // records ordered by the low bits of the mix, in (ka, pa)
     }
-  }
-  TRY(sort_tail(sc, plan, 1, true, ka, pa, kb, pb, n_upper, s));   // records ordered by the low bits of the mix, in (ka, pa)
+    return KMG_OK;
+  };
+  int rc = body();
   uint32_t h_cnt[4] = {0, 0, 0, 0};
   uint32_t *fixmem = nullptr;
-  int rc = fix_groups(sc, plan.bits(), ka, pa, kb, pb, n_upper, s, h_cnt, &fixmem);   // kb, pb are free: scratch
+  if (rc == KMG_OK) rc = fix_groups(sc, plan.bits(), ka, pa, kb, pb, n_upper, s, h_cnt, &fixmem);   // kb, pb are free: scratch
   if (rc == KMG_OK) rc = finish_index(ix, sc, ka, pa, n_upper, s, true);      // synchronises
   dfree(fixmem, s);
+  dfree(kr, s); dfree(pr, s); dfree(d_counts, s); dfree(d_over, s); dfree(segs, s);
   *overflow = h_cnt[2] != 0;
+  *region_overflow = h_over != 0;
   ix->hbits = plan.bits();
   const double N = (double)ix->N, L = (double)sv.avail;
-  prof_bytes("hist_seq", L);
+  if (!regions) prof_bytes("hist_seq", L);
   prof_bytes("sort_pass_seq", L + 12 * N);
   if (R > 2) prof_bytes("sort_pass_hist", 24 * N * (R - 2));
   if (R > 1) prof_bytes("sort_pass", 24 * N);
@@ -850,8 +899,17 @@ static int build_attempt(const SeqView &sv, int k, kmg_index *ix, int order, cud
     TRY(dalloc(&pa, (size_t)n_upper, s));
     if (R > 1) { TRY(dalloc(&kb, (size_t)n_upper, s)); TRY(dalloc(&pb, (size_t)n_upper, s)); }
     if (grouped) {
-      bool overflow = false;
-      TRY(build_grouped(sv, gp, ix, sc, ka, pa, kb, pb, n_upper, s, &overflow));
+      bool overflow = false, region_overflow = false;
+      TRY(build_grouped(sv, gp, ix, sc, ka, pa, kb, pb, n_upper, s, &overflow, !g_no_regions, &region_overflow));
+      if (region_overflow) {                              // a bin outgrew its region (a huge repeat): once more with the histogram
+        if (log_on()) fprintf(stderr, "[kmergpu] a first-pass bin outgrew its region: rebuilding with the histogram sweep\n");
+        void *old[3] = {ix->ukeys, ix->ustart, nullptr};
+        for (void *p : old) g_arena[ix->device & 63].put(p, s, false);
+        ix->ukeys = nullptr; ix->ustart = nullptr; ix->pos = nullptr; ix->hbits = 0; ix->unstable = false;
+        TRY(scratch_clear(sc, s));
+        overflow = false;
+        TRY(build_grouped(sv, gp, ix, sc, ka, pa, kb, pb, n_upper, s, &overflow, false, &region_overflow));
+      }
       if (!overflow) { pa = nullptr; ix->grouped = true; return KMG_OK; }
       // more colliding groups than the task lists hold (not seen in practice): rebuild sorted by key
       void *old[3] = {ix->ukeys, ix->ustart, nullptr};
@@ -1820,9 +1878,9 @@ static int owner_build(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, con
   SortScratch sc;
   uint64_t *ka = d_keys, *kb = nullptr;
   uint32_t *pa = d_pos, *pb = nullptr, *pfinal = nullptr;
-  SegMap *seg = nullptr;
+  TileSegs *seg = nullptr;
   uint64_t h_info[2] = {0, 0};
-  SegMap h_seg{};
+  uint32_t h_seg_overflow = 0;
   const bool grouped = grouped_for(k, order, n);
   // the arrays are sized with slack (1.25-1.3x what an owner expects); the digit plan follows the expected record count
   const SortPlan gp = grouped_plan(d_counts ? n * 10 / 13 : n * 4 / 5);
@@ -1834,9 +1892,9 @@ static int owner_build(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, con
     const int rb0 = grouped ? gp.rb : RADIX_BITS;
     if (d_counts) {
       TRY(dalloc(&seg, 1, s));
-      LAUNCH("seg_prefix", s, seg_prefix_kernel<<<1, 32, 0, s>>>(d_counts, nsegs, region_cap, seg, &sc.stats()->n));
+      LAUNCH("tile_segs", s, tile_segs_kernel<<<1, MAX_SEGS, 0, s>>>(d_counts, nsegs, region_cap, record_tile(rb0), seg, &sc.stats()->n));
       LAUNCH("hist_rec", s, hist_seg_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, seg, sc.hist(0), DigitBin{0, (1u << rb0) - 1}));
-      CU(cudaMemcpyAsync(&h_seg, seg, sizeof h_seg, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync(&h_seg_overflow, &seg->overflow, 4, cudaMemcpyDeviceToHost, s));
     } else {
       LAUNCH("set_n", s, set_n_kernel<<<1, 1, 0, s>>>(d_info, capacity, &sc.stats()->n));
       LAUNCH("hist_rec", s, hist_rec_kernel<256, DigitBin><<<hgrid, 256, 0, s>>>(d_keys, n, &sc.stats()->n, sc.hist(0), DigitBin{0, (1u << rb0) - 1}));
@@ -1848,7 +1906,7 @@ static int owner_build(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, con
       // records carry mix64(key): sort on its low bits, then partition the groups in which k-mers share them.
       // The passes ping-pong (caller's arrays <-> ours); the fix-up needs the result and a scratch pair, so the
       // last pass may not divert into pfinal: copy the positions at the end instead.
-      TRY(sort_tail(sc, gp, 0, true, ka, pa, kb, pb, n, s, nullptr, seg));
+      TRY(sort_tail(sc, gp, 0, true, ka, pa, kb, pb, n, s, nullptr, seg, nsegs));
       uint32_t h_cnt[4] = {0, 0, 0, 0};
       uint32_t *fixmem = nullptr;
       int rc = fix_groups(sc, gp.bits(), ka, pa, kb, pb, n, s, h_cnt, &fixmem);
@@ -1869,7 +1927,7 @@ static int owner_build(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, con
       ix->grouped = true;
       ix->hbits = gp.bits();
     } else {
-      TRY(sort_tail(sc, SortPlan{RADIX_BITS, num_passes(k)}, 0, true, ka, pa, kb, pb, n, s, pfinal, seg));
+      TRY(sort_tail(sc, SortPlan{RADIX_BITS, num_passes(k)}, 0, true, ka, pa, kb, pb, n, s, pfinal, seg, nsegs));
       TRY(finish_index(ix, sc, ka, pfinal, n, s));            // synchronises
     }
     pfinal = nullptr;
@@ -1889,7 +1947,7 @@ static int owner_build(uint64_t *d_keys, uint32_t *d_pos, uint64_t capacity, con
   dfree(pfinal, s);
   dfree(seg, s);
   scratch_free(sc, s);
-  if (rc == KMG_OK && (h_info[1] || h_seg.overflow))
+  if (rc == KMG_OK && (h_info[1] || h_seg_overflow))
     rc = fail(KMG_ERR_RANGE, "an owner received more than the exchange capacity of %llu records", (unsigned long long)(d_counts ? region_cap : capacity));
   if (rc != KMG_OK) { cudaStreamSynchronize(s); kmg_free(ix); return rc; }
   *out = ix;
@@ -1986,25 +2044,25 @@ extern "C" int kmg_query_regions(const kmg_index *ix, const uint64_t *d_keys, co
   TRY(use_index(ix));
   cudaStream_t s = g_ctx.stream();
   const uint64_t capacity = region_cap * (uint64_t)nparts;
-  SegMap *seg = nullptr;
+  TileSegs *seg = nullptr;
   uint64_t *dk = nullptr, *dn = nullptr;
   uint32_t *di = nullptr;
-  SegMap h_seg{};
+  uint32_t h_seg_overflow = 0;
   auto body = [&]() -> int {
     TRY(dalloc(&seg, 1, s));
     TRY(dalloc(&dn, 1, s));
     TRY(dalloc(&dk, (size_t)capacity, s));
     TRY(dalloc(&di, (size_t)capacity, s));
-    LAUNCH("seg_prefix", s, seg_prefix_kernel<<<1, 32, 0, s>>>(d_counts, nparts, region_cap, seg, dn));
+    LAUNCH("tile_segs", s, tile_segs_kernel<<<1, MAX_SEGS, 0, s>>>(d_counts, nparts, region_cap, (uint32_t)PROBE_TILE, seg, dn));
     const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(region_cap, 256), (uint64_t)g_ctx.sms * 8);
     LAUNCH("seg_compact", s, seg_compact_kernel<<<grid, 256, 0, s>>>(d_keys, (const uint32_t *)d_i, seg, dk, di));
-    CU(cudaMemcpyAsync(&h_seg, seg, sizeof h_seg, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&h_seg_overflow, &seg->overflow, 4, cudaMemcpyDeviceToHost, s));
     SeqView sv{};
     return query_common(ix, false, sv, dk, (const int32_t *)di, (int64_t)capacity, st, M, dn, true);   // synchronises
   };
   int rc = body();
   dfree(seg, s); dfree(dn, s); dfree(dk, s); dfree(di, s);
-  if (rc == KMG_OK && h_seg.overflow) {
+  if (rc == KMG_OK && h_seg_overflow) {
     kmg_query_free(*st);
     *st = nullptr;
     return fail(KMG_ERR_RANGE, "an owner received more than the exchange capacity of %llu records", (unsigned long long)region_cap);

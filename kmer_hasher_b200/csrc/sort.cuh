@@ -85,14 +85,20 @@ struct PeerTable {
   uint64_t *counts[MAX_PEERS];  // owner b's received-count array (indexed by source rank), or all null
   uint32_t rank, region;
 };
-// Record source made of `nsegs` regions of `stride` slots each, region r holding prefix[r+1] - prefix[r] records from its
-// start: what an owner receives from a region-mode scatter.  Logical record q lives at q + r * stride - prefix[r].
-struct SegMap {
-  uint64_t prefix[MAX_PEERS + 1];
-  uint64_t stride;
-  uint32_t nsegs, overflow;     // overflow: some source sent more than a region holds (its excess was dropped)
+// A record source (or destination) made of `nsegs` segments of `stride` slots each, segment r holding count[r] records from
+// its start: what an owner receives from a region-mode scatter (segment = source rank), and what the first pass of a grouped
+// build leaves when it writes every bin into its own over-provisioned region instead of needing the bins' sizes beforehand
+// (segment = bin).  The pass that reads it walks the segments tile by tile: tile_prefix[r] = tiles (of `tile` records) before
+// segment r, so a ticket maps to (segment, tile inside it) by one search, no tile straddles two segments, and every tile but
+// a segment's last takes the predicate-free path.
+constexpr int MAX_SEGS = 512;
+struct TileSegs {
+  uint32_t tile_prefix[MAX_SEGS + 1];
+  uint32_t count[MAX_SEGS];
+  uint64_t stride, total;       // slots per segment; records in all segments
+  uint32_t nsegs, tile;         // tile = records per tile of the reading pass
+  uint32_t overflow, pad;       // overflow: some segment was sent more than it holds (the excess was dropped)
 };
-
 template <class BinFn, class NextFn>
 struct PassParams {
   SeqView sv;                 // FROM_SEQ source
@@ -109,7 +115,10 @@ struct PassParams {
   uint32_t hashed;            // FROM_SEQ: records carry mix64(key) instead of the key (grouped build)
   uint32_t pos_add;           // FROM_SEQ: added to the 1-based start (k-1 turns it into the 1-based end of a query window)
   const PeerTable *peer;      // PEER: per-bin destination arrays (own or NVLink-mapped peer memory)
-  const SegMap *seg;          // record source in regions (owner side of a region-mode scatter), or nullptr
+  const TileSegs *segs;       // segmented record source (see TileSegs), or nullptr
+  uint64_t *bin_counts;       // FROM_SEQ, bins written into regions of bin_cap slots (gbase[b] = b * bin_cap): the last tile
+  uint32_t bin_cap;           //   stores every bin's total here; a bin that outgrows its region sets *bin_overflow
+  uint32_t *bin_overflow;
   unsigned long long *trace;  // tuning runs only: 8 clock64 stamps per tile, or nullptr
   uint32_t dbg;               // tuning runs only (wrong results): 1 no look-back wait, 2 no global stores
   BinFn bin;
@@ -153,7 +162,8 @@ struct PassSmem {
   uint32_t next[NB];
   uint32_t scratch[32];
   uint32_t tile;
-  SegMap seg;                                            // segmented record source only
+  uint32_t seg_tp[MAX_SEGS + 1];                         // segmented record source only: TileSegs::tile_prefix
+  uint32_t skip_write;                                   // region output: a bin outgrew its region, drop this tile's records
   PeerTable peer;                                        // PEER mode only
   TileCodes<FROM_SEQ ? TILE : 16> tc;
 };
@@ -243,18 +253,11 @@ __device__ __forceinline__ void st_status(uint64_t *p, const uint64_t (&w)[BPT])
   }
 }
 
-// physical - logical index of logical record q of a segmented source
-__device__ __forceinline__ int64_t seg_shift(const SegMap &sg, int64_t q) {
-  uint32_t r = 0;
-  while (r + 1 < sg.nsegs && (uint64_t)q >= sg.prefix[r + 1]) ++r;
-  return (int64_t)(r * sg.stride) - (int64_t)sg.prefix[r];
-}
-
 // One tile.  FULL: every slot of the tile holds a valid record (no predicates on the hot path).
 template <class Cfg, bool FROM_SEQ, bool FULL, class BinFn, class NextFn, bool HAS_NEXT, bool PEER>
 __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, PassSmem<Cfg, FROM_SEQ> &sm,
                                           const uint32_t tile, const int64_t q0, const int64_t n_in,
-                                          const uint32_t (&gbase)[Cfg::BPT], const bool special, const int64_t src_shift) {
+                                          const uint32_t (&gbase)[Cfg::BPT], const bool special) {
   using S = PassSmem<Cfg, FROM_SEQ>;
   constexpr int TILE = Cfg::TILE, THREADS = Cfg::THREADS, ITEMS = Cfg::ITEMS, WARPS = S::WARPS, NB = Cfg::NB, BPT = Cfg::BPT;
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -278,15 +281,14 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
         if (tile_valid<TILE>(P.sv, sm.tc, q0, t, special)) valid |= 1u << i;
     }
   } else {
-    // src_shift: physical - logical index (0 for a dense source; uniform over a FULL tile of a segmented one)
-    const uint64_t *ksrc = P.keys_in + q0 + t0 + (FULL ? src_shift : 0);
+    const uint64_t *ksrc = P.keys_in + q0 + t0;             // q0, n_in: physical indices (inside one segment of a segmented source)
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if constexpr (FULL) key[i] = ld_stream_u64(ksrc + i * 32);
       else {
         key[i] = 0;
         const int64_t q = q0 + t0 + i * 32;
-        if (q < n_in) { key[i] = ld_stream_u64(ksrc + i * 32 + (P.seg ? seg_shift(sm.seg, q) : 0)); valid |= 1u << i; }
+        if (q < n_in) { key[i] = ld_stream_u64(ksrc + i * 32); valid |= 1u << i; }
       }
     }
   }
@@ -406,8 +408,7 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     uint32_t val[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-      if constexpr (FULL) val[i] = ld_stream_u32(P.pos_in + q0 + t0 + i * 32 + src_shift);
-      else val[i] = ((valid >> i) & 1u) ? ld_stream_u32(P.pos_in + q0 + t0 + i * 32 + (P.seg ? seg_shift(sm.seg, q0 + t0 + i * 32) : 0)) : 0;
+      val[i] = (FULL || ((valid >> i) & 1u)) ? ld_stream_u32(P.pos_in + q0 + t0 + i * 32) : 0;
     }
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i)
@@ -468,6 +469,12 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     for (int q = 0; q < BPT; ++q) {
       const int64_t go = (int64_t)gbase[q] + (int64_t)excl[q] - (int64_t)lstart[q];   // index in this rank's stream of bin b - tile slot
       sm.goff[b0 + q] = (int32_t)go;
+      if constexpr (FROM_SEQ && !PEER) {                   // bins written into regions: totals from the last tile, overflow guard
+        if (P.bin_counts) {
+          if (excl[q] + cnt[q] > P.bin_cap) { *P.bin_overflow = 1; sm.skip_write = 1; }
+          if (q0 + TILE >= n_in) P.bin_counts[b0 + q] = excl[q] + cnt[q];
+        }
+      }
       if constexpr (PEER) {                                // region mode: the last tile reports this rank's total to each owner
         if (sm.peer.region && q0 + TILE >= n_in && b0 + q < MAX_PEERS && sm.peer.counts[b0 + q])
           sm.peer.counts[b0 + q][sm.peer.rank] = excl[q] + cnt[q];
@@ -478,6 +485,8 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
   KMG_STAMP(6);                                          // look-back finished for all bins
 
   // ---- stream the regrouped tile out: consecutive threads -> consecutive slots -> runs per bin
+  bool drop = false;
+  if constexpr (FROM_SEQ && !PEER) drop = sm.skip_write != 0;      // region output: a bin outgrew its region (the build is redone)
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const int s = j * THREADS + tid;
@@ -494,6 +503,7 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
         dst += sm.peer.delta[b];
         room = (uint64_t)(sm.peer.region ? local : dst) < sm.peer.cap;
       }
+      if constexpr (FROM_SEQ && !PEER) room = !drop;
       if (room && !(P.dbg & 2u)) {
         kout[dst] = kk;
         if constexpr (FROM_SEQ) pout[dst] = (uint32_t)(P.sv.s0 + q0 + 1) + P.pos_add + sm.pos[s];   // 1-based start (+ pos_add)
@@ -506,7 +516,9 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
 #undef KMG_STAMP
 }
 
-template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false>
+// SEGS: the record source is segmented (P.segs); compiled separately so that the dense record pass -- the dominant kernel,
+// at its 128-register limit -- does not carry the ticket-to-segment search.
+template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false, bool SEGS = false>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINBLOCKS)
 scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   using S = PassSmem<Cfg, FROM_SEQ>;
@@ -532,37 +544,46 @@ scatter_pass_kernel(const PassParams<BinFn, NextFn> P) {
   if constexpr (HAS_NEXT)
     for (int b = tid; b < NB; b += THREADS) sm.next[b] = 0;
   if constexpr (PEER) {
-    static_assert(sizeof(PeerTable) % 8 == 0 && sizeof(SegMap) % 8 == 0, "copied as 64-bit words");
+    static_assert(sizeof(PeerTable) % 8 == 0, "copied as 64-bit words");
     if (tid < sizeof(PeerTable) / 8) reinterpret_cast<uint64_t *>(&sm.peer)[tid] = reinterpret_cast<const uint64_t *>(P.peer)[tid];
   }
   uint32_t gbase[BPT];                                   // bin bases: a few KB, L2-resident
 #pragma unroll
   for (int q = 0; q < BPT; ++q) gbase[q] = (NB >= THREADS || tid < NB) ? __ldg(P.gbase + tid * BPT + q) : 0;
-  if constexpr (!FROM_SEQ) {
-    if (P.seg && tid < sizeof(SegMap) / 8) reinterpret_cast<uint64_t *>(&sm.seg)[tid] = reinterpret_cast<const uint64_t *>(P.seg)[tid];
+  static_assert(!(SEGS && FROM_SEQ), "only a record source can be segmented");
+  uint32_t nsegs = 0;
+  if constexpr (SEGS) {
+    nsegs = P.segs->nsegs;
+    for (uint32_t i = tid; i <= nsegs; i += THREADS) sm.seg_tp[i] = P.segs->tile_prefix[i];
   }
-  const int64_t n_in = FROM_SEQ ? P.sv.nstarts : (int64_t)*P.n_records;
+  if constexpr (FROM_SEQ) { if (tid == 0) sm.skip_write = 0; }
+  int64_t n_in = FROM_SEQ ? P.sv.nstarts : (SEGS ? 0 : (int64_t)*P.n_records);
   __syncthreads();
   const uint32_t tile = sm.tile;
-  const int64_t q0 = (int64_t)tile * TILE;
-  if (q0 >= n_in) return;
-  int64_t src_shift = 0;
-  bool seg_uniform = true;                               // segmented source: does the whole tile lie in one region?
-  if constexpr (!FROM_SEQ) {
-    if (P.seg) {
-      src_shift = seg_shift(sm.seg, q0);
-      seg_uniform = q0 + TILE <= n_in && seg_shift(sm.seg, q0 + TILE - 1) == src_shift;
+  int64_t q0 = (int64_t)tile * TILE;
+  if constexpr (SEGS) {
+    {                                                      // ticket -> (segment, tile inside it); q0, n_in become physical indices
+      if (tile >= sm.seg_tp[nsegs]) return;
+      uint32_t lo = 0, hi = nsegs;                         // largest r with tile_prefix[r] <= tile
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sm.seg_tp[mid] <= tile) lo = mid; else hi = mid;
+      }
+      const int64_t base = (int64_t)lo * (int64_t)P.segs->stride;
+      q0 = base + (int64_t)(tile - sm.seg_tp[lo]) * TILE;
+      n_in = base + (int64_t)P.segs->count[lo];
     }
   }
+  if (q0 >= n_in) return;
   if (P.trace && tid == 0) P.trace[(size_t)tile * 8] = (unsigned long long)t_start;
 
   bool special = false;
   if constexpr (FROM_SEQ) special = tile_pack<TILE, THREADS>(P.sv, q0, sm.tc);
   const bool touches_end = FROM_SEQ && (P.sv.s0 + q0 + TILE + P.sv.k > P.sv.L);
-  if (q0 + TILE <= n_in && !special && !touches_end && seg_uniform)
-    pass_tile<Cfg, FROM_SEQ, true, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special, src_shift);
+  if (q0 + TILE <= n_in && !special && !touches_end)
+    pass_tile<Cfg, FROM_SEQ, true, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special);
   else
-    pass_tile<Cfg, FROM_SEQ, false, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special, 0);
+    pass_tile<Cfg, FROM_SEQ, false, BinFn, NextFn, HAS_NEXT, PEER>(P, sm, tile, q0, n_in, gbase, special);
 
   if constexpr (HAS_NEXT) {
     __syncthreads();
@@ -779,16 +800,16 @@ hist_rec_kernel(const uint64_t *keys, int64_t n_host, const uint64_t *n_dev, uin
   }
 }
 
-// The same over a segmented record source (see SegMap).
+// The same over a segmented record source (see TileSegs).
 template <int THREADS, class BinFn>
 __global__ void __launch_bounds__(THREADS)
-hist_seg_kernel(const uint64_t *keys, const SegMap *seg, uint32_t *hist, BinFn bin) {
+hist_seg_kernel(const uint64_t *keys, const TileSegs *seg, uint32_t *hist, BinFn bin) {
   __shared__ uint32_t sh[MAX_NB];
   for (int b = threadIdx.x; b < MAX_NB; b += THREADS) sh[b] = 0;
   __syncthreads();
   const uint32_t nsegs = seg->nsegs;
   for (uint32_t r = 0; r < nsegs; ++r) {
-    const int64_t n = (int64_t)(seg->prefix[r + 1] - seg->prefix[r]);
+    const int64_t n = (int64_t)seg->count[r];
     const uint64_t *src = keys + (uint64_t)r * seg->stride;
     for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS)
       atomicAdd(&sh[bin(ld_stream_u64(src + i))], 1u);
@@ -800,32 +821,54 @@ hist_seg_kernel(const uint64_t *keys, const SegMap *seg, uint32_t *hist, BinFn b
   }
 }
 
-// counts (per source) -> SegMap; *n = records held; counts above the region size are clamped and flagged
-__global__ void seg_prefix_kernel(const uint64_t *__restrict__ counts, int nsegs, uint64_t stride, SegMap *seg, uint64_t *n) {
-  if (threadIdx.x == 0) {
-    uint64_t run = 0;
-    uint32_t over = 0;
-    for (int r = 0; r < MAX_PEERS; ++r) {
-      seg->prefix[r] = run;
-      if (r < nsegs) { uint64_t c = counts[r]; if (c > stride) { c = stride; over = 1; } run += c; }
-    }
-    seg->prefix[MAX_PEERS] = run;
-    seg->stride = stride; seg->nsegs = (uint32_t)nsegs; seg->overflow = over;
-    *n = run;
+// counts (per segment) -> TileSegs for a reading pass with tiles of `tile` records; *n = records held; counts above the
+// segment size are clamped and flagged.  One block of MAX_SEGS threads.
+__global__ void __launch_bounds__(MAX_SEGS)
+tile_segs_kernel(const uint64_t *__restrict__ counts, int nsegs, uint64_t stride, uint32_t tile, TileSegs *seg, uint64_t *n) {
+  __shared__ uint32_t part_t[MAX_SEGS / 32];
+  __shared__ uint64_t part_c[MAX_SEGS / 32];
+  __shared__ uint32_t over;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) over = 0;
+  __syncthreads();
+  uint64_t c = (int)tid < nsegs ? counts[tid] : 0;
+  if (c > stride) { c = stride; over = 1; }
+  const uint32_t t = (uint32_t)((c + tile - 1) / tile);
+  const uint32_t it = warp_incl_scan(t);
+  const uint64_t ic = warp_incl_scan64(c);
+  if (lane == 31) { part_t[warp] = it; part_c[warp] = ic; }
+  __syncthreads();
+  uint32_t bt = 0, tt = 0;
+  uint64_t tc = 0;
+  for (int w = 0; w < MAX_SEGS / 32; ++w) { if (w < (int)warp) bt += part_t[w]; tt += part_t[w]; tc += part_c[w]; }
+  seg->tile_prefix[tid] = bt + it - t;
+  seg->count[tid] = (uint32_t)c;
+  if (tid == 0) {
+    seg->tile_prefix[MAX_SEGS] = tt;
+    seg->stride = stride; seg->total = tc; seg->nsegs = (uint32_t)nsegs; seg->tile = tile; seg->overflow = over; seg->pad = 0;
+    *n = tc;
   }
+  if ((int)tid == nsegs) seg->tile_prefix[nsegs] = tt;      // (also covers nsegs < MAX_SEGS: the entry the reader bounds by)
 }
 // dense copy of a segmented (key, payload) source
-__global__ void seg_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay, const SegMap *seg,
+__global__ void seg_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay, const TileSegs *seg,
                                    uint64_t *__restrict__ okeys, uint32_t *__restrict__ opay) {
   const uint32_t nsegs = seg->nsegs;
+  uint64_t dst = 0;
   for (uint32_t r = 0; r < nsegs; ++r) {
-    const int64_t n = (int64_t)(seg->prefix[r + 1] - seg->prefix[r]);
-    const uint64_t src = (uint64_t)r * seg->stride, dst = seg->prefix[r];
+    const int64_t n = (int64_t)seg->count[r];
+    const uint64_t src = (uint64_t)r * seg->stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
       okeys[dst + i] = ld_stream_u64(keys + src + i);
       opay[dst + i] = ld_stream_u32(pay + src + i);
     }
+    dst += (uint64_t)n;
   }
+}
+// gbase[b] = b * cap (bins written into their own regions) and a zeroed overflow word
+__global__ void region_gbase_kernel(uint32_t *gbase, int nb, uint32_t cap, uint32_t *overflow) {
+  for (int b = threadIdx.x; b < MAX_NB; b += blockDim.x) gbase[b] = b < nb ? (uint32_t)b * cap : 0;
+  if (threadIdx.x == 0) *overflow = 0;
 }
 
 }  // namespace kmg

@@ -17,7 +17,9 @@ wl = sys.argv[4] if len(sys.argv) > 4 else "c2"
 lib = _lib.load()
 seq = torch.from_numpy(synth.config_c2(L) if wl == "c2" else synth.config_c3(L)).cuda()
 for spec in specs:
-    rank, shape, rb, bits = (int(x) for x in spec.split(":"))
+    parts = [int(x) for x in spec.split(":")]
+    rank, shape, rb, bits = parts[:4]
+    _lib.check(lib.kmg_tune(b"no_regions", parts[4] if len(parts) > 4 else 0))     # 5th field 1: first pass from a histogram sweep
     _lib.check(lib.kmg_tune(b"sort_cfg", rank))
     _lib.check(lib.kmg_tune(b"sort_shape", shape))
     _lib.check(lib.kmg_tune(b"hash_rb", rb))
@@ -37,7 +39,7 @@ for spec in specs:
     prof = kh.profile(enable=False)
     kh.profile(reset=True)
     sp = prof.get("sort_pass", (0, 1, 0))
-    line = f"rank {rank} shape {shape} rb {rb} bits {bits:2d} build {a.elapsed_time(b) / reps:7.3f} ms | sort_pass {sp[0] / max(sp[1], 1) * 1e3:7.1f} us {sp[2] / max(sp[0], 1e-9) / 1e6:7.0f} GB/s"
+    line = f"rank {rank} shape {shape} rb {rb} bits {bits:2d} noreg {parts[4] if len(parts) > 4 else 0} build {a.elapsed_time(b) / reps:7.3f} ms | sort_pass {sp[0] / max(sp[1], 1) * 1e3:7.1f} us {sp[2] / max(sp[0], 1e-9) / 1e6:7.0f} GB/s"
     sph = prof.get("sort_pass_hist")
     if sph:
         line += f" | sort_pass_hist {sph[0] / max(sph[1], 1) * 1e3:6.1f}us x{sph[1] // reps} {sph[2] / max(sph[0], 1e-9) / 1e6:5.0f} GB/s"
