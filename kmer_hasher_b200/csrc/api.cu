@@ -495,6 +495,7 @@ static int g_sort_shape = 0;
 static int g_rank_override = -1;               // kmg_tune "sort_cfg": -1 auto, 0 bitmap, 3 one-atomic
 static std::atomic<int> g_rank_dev[64];        // per device: 0 unknown, 1 bitmap, 2 one-atomic
 static std::atomic<uint64_t> g_unstable_rebuilds{0};
+static std::atomic<uint64_t> g_region_rebuilds{0};   // grouped builds redone because a first-pass bin outgrew its region
 static uint32_t g_sort_dbg = 0;
 static int lane_order_failures(uint32_t *failures);
 static bool log_on();
@@ -578,7 +579,7 @@ extern "C" int kmg_tune(const char *key, int value) {
   if (key && !strcmp(key, "hash_cas")) { g_hash_cas = value != 0; return KMG_OK; }
   if (key && !strcmp(key, "scatter_bitmap")) { g_scatter_bitmap = value != 0; return KMG_OK; }
   if (key && !strcmp(key, "scatter_shape")) { g_scatter_shape = value; return KMG_OK; }
-  if (key && !strcmp(key, "no_regions")) { g_no_regions = value != 0; return KMG_OK; }
+  if (key && !strcmp(key, "no_regions")) { g_no_regions = value; return KMG_OK; }    // 0 auto, 1 never, 2 always (tests: skips the sampled check)
   if (key && !strcmp(key, "hash_bits")) {
     if (value != 0 && (value < 8 || value > 56 || (value % 8 && value % 9 && value % 10))) return fail(KMG_ERR_ARG, "hash_bits must be 0 (auto) or a multiple of 8, 9 or 10 in [8,56]");
     g_hash_bits = value;
@@ -605,6 +606,7 @@ extern "C" int kmg_tune(const char *key, int value) {
 extern "C" int64_t kmg_tune_get(const char *key, int64_t arg) {
   if (key && !strcmp(key, "rank_variant")) return ctx_init() == KMG_OK ? rank_variant() : -1;
   if (key && !strcmp(key, "unstable_rebuilds")) return (int64_t)g_unstable_rebuilds.load();
+  if (key && !strcmp(key, "region_rebuilds")) return (int64_t)g_region_rebuilds.load();
   if (key && !strcmp(key, "hash_bits")) return grouped_plan(arg).bits();
   if (key && !strcmp(key, "hash_rb")) return grouped_plan(arg).rb;
   return -1;
@@ -627,6 +629,7 @@ extern "C" int kmg_selftest_lane_order(uint32_t *failures) {
   if (!failures) return fail(KMG_ERR_ARG, "failures is NULL");
   return lane_order_failures(failures);
 }
+constexpr int REGION_SAMPLE_STRIDE = 251;   // prime: tandem arrays are sampled in all their phases
 constexpr int SORT_TILE_MIN = 4096;   // status sizing: smallest tile of any shape
 
 template <class Cfg, bool FROM_SEQ, class BinFn, class NextFn, bool HAS_NEXT, bool PEER = false, bool SEGS = false>
@@ -824,6 +827,28 @@ static int build_grouped(const SeqView &sv, SortPlan plan, kmg_index *ix, SortSc
   uint32_t h_over = 0;
   regions = regions && R > 1 && NB <= MAX_SEGS && n_upper <= (int64_t)1600000000;   // region offsets are 32-bit signed in the pass
   const uint32_t cap = (uint32_t)(((uint64_t)(n_upper / NB) * 5 / 4 + 4096 + 15) & ~uint64_t(15));
+  if (regions && g_no_regions == 2) {
+    // tests: regions whatever the sample would say
+  } else if (regions && n_upper >= (int64_t)REGION_SAMPLE_STRIDE * 4096) {
+    // A repeat-rich sequence puts a k-mer's every copy into one bin: ask a 1-in-251 sample whether the heaviest bin stays
+    // clear of a region's size; if not, take the histogram path right away instead of finding out the expensive way.
+    uint32_t *d_s = nullptr, h_est = 0;
+    TRY(dalloc(&d_s, (size_t)MAX_NB + 1, s));
+    int rc0 = KMG_OK;
+    if (cudaMemsetAsync(d_s, 0, (MAX_NB + 1) * sizeof(uint32_t), s) != cudaSuccess) rc0 = fail(KMG_ERR_CUDA, "memset failed");
+    if (rc0 == KMG_OK) {
+      const unsigned g = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper / REGION_SAMPLE_STRIDE, 256), (int64_t)g_ctx.sms * 8);
+      region_sample_kernel<<<g, 256, 0, s>>>(sv, REGION_SAMPLE_STRIDE, mask, d_s);
+      region_estimate_kernel<<<1, 256, 0, s>>>(d_s, NB, REGION_SAMPLE_STRIDE, d_s + MAX_NB);
+      if (cudaMemcpyAsync(&h_est, d_s + MAX_NB, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+        rc0 = fail(KMG_ERR_CUDA, "region estimate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    dfree(d_s, s);
+    TRY(rc0);
+    if ((uint64_t)h_est * 10 > (uint64_t)cap * 9) regions = false;       // within 10 % of a region: not worth the risk
+  } else if (regions) {
+    regions = false;                                       // small inputs: the sweep is cheap and the slack relatively small
+  }
   auto body = [&]() -> int {
     PassParams<DigitBin, DigitBin> P{};
     P.sv = sv; P.keys_out = ka; P.pos_out = pa;
@@ -900,8 +925,9 @@ static int build_attempt(const SeqView &sv, int k, kmg_index *ix, int order, cud
     if (R > 1) { TRY(dalloc(&kb, (size_t)n_upper, s)); TRY(dalloc(&pb, (size_t)n_upper, s)); }
     if (grouped) {
       bool overflow = false, region_overflow = false;
-      TRY(build_grouped(sv, gp, ix, sc, ka, pa, kb, pb, n_upper, s, &overflow, !g_no_regions, &region_overflow));
+      TRY(build_grouped(sv, gp, ix, sc, ka, pa, kb, pb, n_upper, s, &overflow, g_no_regions != 1, &region_overflow));
       if (region_overflow) {                              // a bin outgrew its region (a huge repeat): once more with the histogram
+        g_region_rebuilds.fetch_add(1);
         if (log_on()) fprintf(stderr, "[kmergpu] a first-pass bin outgrew its region: rebuilding with the histogram sweep\n");
         void *old[3] = {ix->ukeys, ix->ustart, nullptr};
         for (void *p : old) g_arena[ix->device & 63].put(p, s, false);

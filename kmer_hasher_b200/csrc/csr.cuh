@@ -240,6 +240,7 @@ big_fix_kernel(uint64_t *__restrict__ h, uint32_t *__restrict__ pos, uint64_t *_
   for (uint32_t t = blockIdx.x; t < nt; t += gridDim.x) {
     const uint2 se = fl.big_tasks[t];
     const uint32_t s = se.x, e = se.y;
+    if (e <= s) continue;
     uint32_t placed = 0;
     bool have_last = false;
     uint64_t last = 0;
@@ -262,6 +263,7 @@ big_fix_kernel(uint64_t *__restrict__ h, uint32_t *__restrict__ pos, uint64_t *_
       }
       __syncthreads();
       const uint64_t cur = s_cur;
+      if (have_last && cur <= last) break;               // nothing left above `last` (only on inconsistent input): never spin
       for (uint32_t base = s; base < e; base += THREADS) {
         const uint32_t j = base + tid;
         const bool hit = j < e && h[j] == cur;

@@ -832,7 +832,10 @@ tile_segs_kernel(const uint64_t *__restrict__ counts, int nsegs, uint64_t stride
   if (tid == 0) over = 0;
   __syncthreads();
   uint64_t c = (int)tid < nsegs ? counts[tid] : 0;
-  if (c > stride) { c = stride; over = 1; }
+  if (c > stride) over = 1;
+  __syncthreads();
+  if (over) c = 0;      // a segment was sent more than it holds (the excess was dropped): hand out an EMPTY source, so that every
+                        // kernel queued behind this one is a no-op on well-defined data; the host sees the flag and takes another path
   const uint32_t t = (uint32_t)((c + tile - 1) / tile);
   const uint32_t it = warp_incl_scan(t);
   const uint64_t ic = warp_incl_scan64(c);
@@ -864,6 +867,37 @@ __global__ void seg_compact_kernel(const uint64_t *__restrict__ keys, const uint
     }
     dst += (uint64_t)n;
   }
+}
+// Is the mixed digit's heaviest bin safely below a region's size?  Every `stride`-th window (a prime, so that tandem arrays
+// are sampled in all their phases) is hashed and binned; est[0] = stride * largest sampled bin.  (Breakers are encoded like
+// any byte: this only steers a choice.)
+__global__ void region_sample_kernel(const SeqView sv, int stride, uint32_t mask, uint32_t *hist /* [MAX_NB], zero */) {
+  __shared__ uint32_t sh[MAX_NB];
+  for (int b = threadIdx.x; b < MAX_NB; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  const int64_t nsamp = sv.nstarts / stride;
+  const uint64_t kmask = key_mask(sv.k);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsamp; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t *p = sv.base + i * stride;
+    uint64_t w = 0;
+    for (int j = 0; j < sv.k; ++j) w = (w << 2) | ((p[j] >> 1) & 3u);
+    atomicAdd(&sh[(uint32_t)mix64(w & kmask) & mask], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < MAX_NB; b += blockDim.x) {
+    const uint32_t c = sh[b];
+    if (c) atomicAdd(hist + b, c);
+  }
+}
+__global__ void region_estimate_kernel(const uint32_t *hist, int nb, int stride, uint32_t *est) {
+  __shared__ uint32_t m;
+  if (threadIdx.x == 0) m = 0;
+  __syncthreads();
+  uint32_t mine = 0;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) mine = max(mine, hist[b]);
+  atomicMax(&m, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) est[0] = m * (uint32_t)stride;
 }
 // gbase[b] = b * cap (bins written into their own regions) and a zeroed overflow word
 __global__ void region_gbase_kernel(uint32_t *gbase, int nb, uint32_t cap, uint32_t *overflow) {

@@ -787,3 +787,40 @@ def test_pageable_buffers_take_the_staged_path(kh, oracle):
     kh.kmer_pos(ix_device, 2, out={"pos": pin})
     assert np.array_equal(pin, got["pos"])
     ix_pageable.free(); ix_device.free()
+
+
+def test_first_pass_regions_and_their_overflow_fallback(kh, oracle):
+    """The grouped build's first pass can write every bin of the mixed digit into its own region of 1.25x the mean bin
+    size (no histogram sweep over the sequence).  A 1-in-251 sample decides whether the heaviest bin stays clear of a
+    region; if a bin outgrows its region all the same (forced here), the build notices -- device flag, the reading pass
+    is handed an empty source -- and redoes itself with the histogram.  Same index every way."""
+    from kmer_hasher_b200 import synth, _lib
+    L_ = _lib.load()
+    k = 32
+    seq = synth.config_c3(3_000_000)
+    want = oracle.build(seq, k).extract(2 | 8)
+
+    def check(sq, wanted):
+        ix = kh.make_kmer_hash(sq, k)
+        got = kh.kmer_pos(ix, 2 | 8, canonical=True)
+        assert np.array_equal(kh.kmer_keys(ix, canonical=True), wanted["keys"])
+        assert np.array_equal(got["count"], wanted["count"]) and np.array_equal(got["pos"].ravel(), wanted["pos"])
+        ix.free()
+    before = L_.kmg_tune_get(b"region_rebuilds", 0)
+    try:
+        for mode in (0, 1, 2):                               # sampled choice, histogram always, regions always
+            _lib.check(L_.kmg_tune(b"no_regions", mode))
+            check(seq, want)
+        assert L_.kmg_tune_get(b"region_rebuilds", 0) == before
+        heavy = seq.copy()
+        heavy[100_000:160_000] = ord("A")                    # one k-mer with 59,969 copies: mean bin 11.7 k, region 18.7 k
+        heavy[300_000:340_000] = np.frombuffer(b"CA" * 20_000, np.uint8)
+        want_heavy = oracle.build(heavy, k).extract(2 | 8)
+        _lib.check(L_.kmg_tune(b"no_regions", 0))
+        check(heavy, want_heavy)                             # the sample sees the heavy bin: histogram path, nothing redone
+        assert L_.kmg_tune_get(b"region_rebuilds", 0) == before
+        _lib.check(L_.kmg_tune(b"no_regions", 2))
+        check(heavy, want_heavy)                             # forced: the bin overflows, the build is redone
+        assert L_.kmg_tune_get(b"region_rebuilds", 0) == before + 1
+    finally:
+        _lib.check(L_.kmg_tune(b"no_regions", 0))
