@@ -870,7 +870,7 @@ __global__ void seg_compact_kernel(const uint64_t *__restrict__ keys, const uint
 }
 // Is the mixed digit's heaviest bin safely below a region's size?  Every `stride`-th window (a prime, so that tandem arrays
 // are sampled in all their phases) is hashed and binned; est[0] = stride * largest sampled bin.  (Breakers are encoded like
-// any byte: this only steers a choice.)
+// any byte -- this only steers a choice -- but windows that contain one are skipped, as the index skips them.)
 __global__ void region_sample_kernel(const SeqView sv, int stride, uint32_t mask, uint32_t *hist /* [MAX_NB], zero */) {
   __shared__ uint32_t sh[MAX_NB];
   for (int b = threadIdx.x; b < MAX_NB; b += blockDim.x) sh[b] = 0;
@@ -880,8 +880,9 @@ __global__ void region_sample_kernel(const SeqView sv, int stride, uint32_t mask
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsamp; i += (int64_t)gridDim.x * blockDim.x) {
     const uint8_t *p = sv.base + i * stride;
     uint64_t w = 0;
-    for (int j = 0; j < sv.k; ++j) w = (w << 2) | ((p[j] >> 1) & 3u);
-    atomicAdd(&sh[(uint32_t)mix64(w & kmask) & mask], 1u);
+    bool clean = true;                                     // windows with a breaker are not indexed: an N gap must not look like a repeat
+    for (int j = 0; j < sv.k; ++j) { const uint8_t c = p[j]; clean &= (c | 0x20) != 'n'; w = (w << 2) | ((c >> 1) & 3u); }
+    if (clean) atomicAdd(&sh[(uint32_t)mix64(w & kmask) & mask], 1u);
   }
   __syncthreads();
   for (int b = threadIdx.x; b < MAX_NB; b += blockDim.x) {
