@@ -241,7 +241,7 @@ def timed(torch, fn, n):
 def index_leg(kh, torch, seq_dev, k, steps, warm):
     """build + kmer.pos(2|8), everything resident in HBM: (ms per step, N, U)."""
     ix = kh.make_kmer_hash(seq_dev, k)
-    U, N, _ = ix.sizes
+    U, N = ix.sizes_un
     ix.free()
     pos_dev = torch.empty((N, 2), dtype=torch.int32, device="cuda")
     cnt_dev = torch.empty(U, dtype=torch.int32, device="cuda")
@@ -268,7 +268,7 @@ def probe_leg(kh, torch, _lib, w, seq_pin, seq_dev, k, steps, hbm_peak):
     st, M = C.c_void_p(), C.c_uint64()
     # first probe of a fresh index: includes building the key table (once per index)
     h = kh.make_kmer_hash(seq_dev, k)
-    U = h.sizes[0]
+    U = h.sizes_un[0]
 
     def begin(qptr):
         _lib.check(Lb.kmg_query_begin(h._handle(), qptr, Lq, k, C.byref(st), C.byref(M)))

@@ -85,7 +85,9 @@ int kmg_index_order(const kmg_index *idx);
 int kmg_free(kmg_index *idx);
 
 /* U = distinct k-mers (kh_size, src/kmer_hash.c:1090), N = indexed windows = rows of `pos`,
- * P = sum n(n-1)/2 = rows of `pair.pos`.  Any pointer may be NULL. */
+ * P = sum n(n-1)/2 = rows of `pair.pos`.  Any pointer may be NULL; P is computed (one sweep of the index, then
+ * cached) the first time it is asked for, so callers that do not emit pairs pass NULL (the reference, too, walks the
+ * lists for pairs only under opt.flag 4, src/kmer_hash.c:1113). */
 int kmg_sizes(const kmg_index *idx, uint64_t *U, uint64_t *N, uint64_t *P);
 int kmg_index_k(const kmg_index *idx);   /* khash_ptr.k, src/kmer_pos.h:45 */
 

@@ -92,9 +92,17 @@ class KmerHash:
 
     @property
     def sizes(self):
+        """(U, N, P); P -- rows of pair.pos -- costs a sweep of the index the first time (cached afterwards)"""
         U, N, P = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(_L.kmg_sizes(self._handle(), C.byref(U), C.byref(N), C.byref(P)))
         return U.value, N.value, P.value
+
+    @property
+    def sizes_un(self):
+        """(U, N) only: what make.kmer.hash + kmer.pos without pair.pos need"""
+        U, N = C.c_uint64(), C.c_uint64()
+        check(_L.kmg_sizes(self._handle(), C.byref(U), C.byref(N), None))
+        return U.value, N.value
 
     def _handle(self):
         if not self._h:
@@ -127,6 +135,10 @@ class KmerCounts(KmerHash):
         check(_L.kmg_count_sizes(self._handle(), C.byref(U), None, None, C.byref(nt)))
         sn = self.source_n
         return U.value, U.value * sn, U.value * sn * (sn - 1) // 2
+
+    @property
+    def sizes_un(self):
+        return self.sizes[:2]
 
     @property
     def kmer_count(self):
@@ -185,7 +197,7 @@ def make_kmer_hash(seq, k, do_sort=False) -> KmerHash:
 
 def _by_key(ix: "KmerHash"):
     """(order, rank): order[j] = index (0-based) of the k-mer with the j-th smallest key, rank = its inverse."""
-    U = ix.sizes[0]
+    U = ix.sizes_un[0]
     keys = np.empty(U, np.uint64)
     check(_L.kmg_kmers_u64(ix._handle(), _out_ptr(keys)))
     order = np.argsort(keys, kind="stable")
@@ -220,7 +232,8 @@ def kmer_pos(ex_ptr, opt_flag, out: dict | None = None, canonical: bool = False)
     if isinstance(ix, KmerCounts):
         return _count_table_pos(ix, opt_flag)
     out = out or {}
-    U, N, P = ix.sizes
+    U, N = ix.sizes_un
+    P = ix.sizes[2] if opt_flag & OPT_PAIRS else 0
     h = ix._handle()
     res = {"kmer": None, "pos": None, "pair.pos": None, "count": None}
     if opt_flag & OPT_KMER:
@@ -451,7 +464,7 @@ def kmer_keys(ex_ptr, canonical: bool = False) -> np.ndarray:
     """The distinct k-mers as uint64 keys in the index's order, or ascending with canonical=True (not part of
     the R API; used by tests)."""
     ix = _extract(ex_ptr)
-    U, _, _ = ix.sizes
+    U, _ = ix.sizes_un
     a = np.empty(U, np.uint64)
     if isinstance(ix, KmerCounts):
         check(_L.kmg_count_kmers_u64(ix._handle(), _out_ptr(a)))

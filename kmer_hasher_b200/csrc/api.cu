@@ -454,8 +454,10 @@ static int upload_seq(const void *src, int64_t len, cudaStream_t s, DevSeq *out)
 struct kmg_index {
   int device = 0;
   int k = 0;
-  uint64_t U = 0, N = 0, P = 0, multi = 0;
+  uint64_t U = 0, N = 0;
+  uint64_t P = 0, multi = 0;    // sum n(n-1)/2, k-mers with more than one position, longest list: made on first use (ensure_stats)
   uint32_t maxc = 0;
+  bool have_stats = false;
   bool grouped = false;         // k-mers in the order of the grouped build instead of ascending key
   int hbits = 0;                // grouped: the records were sorted on the low hbits bits of mix64(key), then by mix64(key)
   bool unstable = false;        // a position list was found not ascending (never true of an index handed out)
@@ -731,12 +733,11 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
   CU(cudaMemsetAsync(status2, 0, (size_t)tiles * sizeof(Pair64), s));
   LAUNCH("rle", s, rle_kernel<RLE_THREADS, RLE_ITEMS><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(
                        keys_sorted, pos_sorted, st, ukeys, ustart, status2, sc.ticket(MAX_PASSES + 1), hashed));
-  const unsigned sgrid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_upper > 0 ? n_upper : 1, 256 * 16), g_ctx.sms * 8);
-  LAUNCH("stats", s, stats_kernel<256><<<sgrid, 256, 0, s>>>(ustart, st));
   IndexStats h;
   CU(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  ix->N = h.n; ix->U = h.U; ix->P = h.P; ix->multi = h.multi; ix->maxc = h.maxc; ix->unstable = h.unstable != 0;
+  ix->N = h.n; ix->U = h.U; ix->unstable = h.unstable != 0;
+  ix->have_stats = false;       // P, multi, max count: on first demand (ensure_stats)
   dfree(status2, s);
   // keep exact-size arrays when the over-allocation is large
   if (h.U * 2 < (uint64_t)n_upper) {
@@ -751,7 +752,6 @@ static int finish_index(kmg_index *ix, SortScratch &sc, uint64_t *keys_sorted, u
   ix->ukeys = ukeys; ix->ustart = ustart; ix->pos = pos_sorted;
   const double N = (double)h.n, U = (double)h.U;
   prof_bytes("rle", 12 * N + 12 * U);
-  prof_bytes("stats", 4 * U);
   return KMG_OK;
 }
 
@@ -1066,16 +1066,47 @@ extern "C" int kmg_free(kmg_index *ix) {
   return KMG_OK;
 }
 
+static int use_index(const kmg_index *ix);
+// P, multi and the longest list: one sweep of ustart (4U bytes), taken the first time something asks for them -- the pair
+// matrix's extent (kmg_sizes with P != NULL), kmg_index_stats, kmg_pairs*.  make.kmer.hash + kmer.pos(2|8) never does.
+static int ensure_stats(const kmg_index *cix) {
+  kmg_index *ix = const_cast<kmg_index *>(cix);
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->have_stats) return KMG_OK;
+  if (ix->U == 0) { ix->P = 0; ix->multi = 0; ix->maxc = 0; ix->have_stats = true; return KMG_OK; }
+  TRY(use_index(ix));
+  cudaStream_t s = g_ctx.stream();
+  IndexStats *st = nullptr, h;
+  TRY(dalloc(&st, 1, s));
+  auto body = [&]() -> int {
+    CU(cudaMemsetAsync(st, 0, sizeof(IndexStats), s));
+    const unsigned sgrid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(ix->U, 256 * 16), (uint64_t)g_ctx.sms * 8);
+    LAUNCH("stats", s, stats_kernel<256><<<sgrid, 256, 0, s>>>(ix->ustart, ix->U, st));
+    CU(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return KMG_OK;
+  };
+  const int rc = body();
+  dfree(st, s);
+  TRY(rc);
+  ix->P = h.P; ix->multi = h.multi; ix->maxc = h.maxc;
+  ix->have_stats = true;
+  prof_bytes("stats", 4.0 * (double)ix->U);
+  return KMG_OK;
+}
+
+// P may be NULL: the number of pair rows costs a sweep of the index the first time it is asked for (ensure_stats)
 extern "C" int kmg_sizes(const kmg_index *ix, uint64_t *U, uint64_t *N, uint64_t *P) {
   if (!ix) return fail(KMG_ERR_ARG, "index is NULL");
+  if (P) { TRY(ensure_stats(ix)); *P = ix->P; }
   if (U) *U = ix->U;
   if (N) *N = ix->N;
-  if (P) *P = ix->P;
   return KMG_OK;
 }
 extern "C" int kmg_index_k(const kmg_index *ix) { return ix ? ix->k : fail(KMG_ERR_ARG, "index is NULL"); }
 extern "C" int kmg_index_stats(const kmg_index *ix, uint64_t *multi, uint32_t *max_count) {
   if (!ix) return fail(KMG_ERR_ARG, "index is NULL");
+  TRY(ensure_stats(ix));
   if (multi) *multi = ix->multi;
   if (max_count) *max_count = ix->maxc;
   return KMG_OK;
@@ -1233,8 +1264,7 @@ extern "C" int kmg_kmers_ascii(const kmg_index *ix, char *out) {
 extern "C" int kmg_counts(const kmg_index *ix, int32_t *out) {
   TRY(use_index(ix));
   if (!out && ix->U) return fail(KMG_ERR_ARG, "counts is NULL");
-  if (ix->maxc > (uint32_t)INT32_MAX) return fail(KMG_ERR_RANGE, "a count exceeds int");
-  const uint32_t *ustart = ix->ustart;
+  const uint32_t *ustart = ix->ustart;            // a count is at most N <= INT32_MAX
   const int sms = g_ctx.sms;
   int rc = stream_rows(ix->U, 4, out, CHUNK_BYTES / 4, [=](uint64_t first, uint64_t rows, void *dst, uint64_t *, cudaStream_t s) -> int {
     const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div<uint64_t>(rows, 256), (uint64_t)sms * 16);
@@ -1266,6 +1296,7 @@ extern "C" int kmg_positions_base(const kmg_index *ix, uint64_t i_base, int32_t 
 }
 
 static int ensure_pair_index(kmg_index *ix) {
+  TRY(ensure_stats(ix));
   std::lock_guard<std::mutex> g(ix->mu);
   if (ix->pair_off || ix->multi == 0) return KMG_OK;
   cudaStream_t s = g_ctx.stream();
@@ -1294,6 +1325,7 @@ extern "C" int kmg_pairs_chunk_base(const kmg_index *cix, uint64_t i_base, uint6
   TRY(use_index(cix));
   if (i_base + cix->U > (uint64_t)INT32_MAX) return fail(KMG_ERR_RANGE, "k-mer numbers exceed int");
   kmg_index *ix = const_cast<kmg_index *>(cix);
+  TRY(ensure_stats(ix));
   if (first > ix->P || n > ix->P - first) return fail(KMG_ERR_ARG, "pair rows [%llu,+%llu) outside [0,%llu)", (unsigned long long)first, (unsigned long long)n, (unsigned long long)ix->P);
   if (n == 0) return KMG_OK;
   if (!out) return fail(KMG_ERR_ARG, "out is NULL");
@@ -1312,6 +1344,7 @@ extern "C" int kmg_pairs_chunk_base(const kmg_index *cix, uint64_t i_base, uint6
 }
 extern "C" int kmg_pairs(const kmg_index *ix, int32_t *out) {
   if (!ix) return fail(KMG_ERR_ARG, "index is NULL");
+  TRY(ensure_stats(ix));
   return kmg_pairs_chunk(ix, 0, ix->P, out);
 }
 
@@ -2043,6 +2076,7 @@ extern "C" int kmg_shard_scatter_ranges(const kmg_shard *sh, int nparts, int ran
     P.pos_add = (uint32_t)pos_add;
     P.hashed = 1;
     P.peer = tab;
+    P.dbg = g_sort_dbg;
     P.bin = RangeBin{(uint32_t)nparts};
     // kmg_tune "scatter_shape" (tuning runs): more resident tiles per SM = more remote stores in flight on the NVLink
     if (rank_variant() >= 3 && !g_scatter_bitmap) {

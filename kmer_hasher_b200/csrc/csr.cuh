@@ -290,10 +290,12 @@ big_fix_kernel(uint64_t *__restrict__ h, uint32_t *__restrict__ pos, uint64_t *_
 }
 
 // ---- per-k-mer facts: P, multi, max count -------------------------------------------------------------
+// Not part of the build: only pair.pos (its row count P, the list of k-mers with pairs) and kmg_index_stats need them, so
+// they are taken on first demand (api.cu, ensure_stats) -- as the reference only walks the lists for pairs under opt.flag 4
+// (src/kmer_hash.c:1113).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-stats_kernel(const uint32_t *__restrict__ ustart, IndexStats *st) {
-  const uint64_t U = st->U;
+stats_kernel(const uint32_t *__restrict__ ustart, const uint64_t U, IndexStats *st) {
   uint64_t P = 0, multi = 0;
   uint32_t maxc = 0;
   // four list starts per 16-byte load; the count of the last needs the next group's first start

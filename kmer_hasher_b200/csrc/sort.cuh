@@ -164,6 +164,7 @@ struct PassSmem {
   uint32_t tile;
   uint32_t seg_tp[MAX_SEGS + 1];                         // segmented record source only: TileSegs::tile_prefix
   uint32_t skip_write;                                   // region output: a bin outgrew its region, drop this tile's records
+  uint32_t bstart[MAX_PEERS], bcnt[MAX_PEERS];           // PEER mode only: first tile slot and size of every owner's run
   PeerTable peer;                                        // PEER mode only
   TileCodes<FROM_SEQ ? TILE : 16> tc;
 };
@@ -478,6 +479,7 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
       if constexpr (PEER) {                                // region mode: the last tile reports this rank's total to each owner
         if (sm.peer.region && q0 + TILE >= n_in && b0 + q < MAX_PEERS && sm.peer.counts[b0 + q])
           sm.peer.counts[b0 + q][sm.peer.rank] = excl[q] + cnt[q];
+        if (b0 + q < MAX_PEERS) { sm.bstart[b0 + q] = lstart[q]; sm.bcnt[b0 + q] = cnt[q]; }
       }
     }
   }
@@ -487,6 +489,38 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
   // ---- stream the regrouped tile out: consecutive threads -> consecutive slots -> runs per bin
   bool drop = false;
   if constexpr (FROM_SEQ && !PEER) drop = sm.skip_write != 0;      // region output: a bin outgrew its region (the build is redone)
+  bool aligned_out = false;
+  if constexpr (PEER) aligned_out = !(P.dbg & 4u);                 // dbg 4 (tuning runs): the generic write-out
+  if (aligned_out) {
+   if constexpr (PEER) {
+    // Owner by owner, every warp's 32 lanes covering one 32-record-ALIGNED block of the destination (256 bytes of keys, 128
+    // of positions: whole 128-byte lines): a remote store instruction then becomes full-line NVLink write packets instead of
+    // the 3 + 2 partial ones of an arbitrarily aligned run.  A handful of owners with long runs, so the per-owner loop and the
+    // idle lanes at a run's ends cost little.
+    constexpr int OWNERS = NB < MAX_PEERS ? NB : MAX_PEERS;
+    for (int b = 0; b < OWNERS; ++b) {
+      const int cb = (int)sm.bcnt[b];
+      if (cb == 0) continue;
+      const int st = (int)sm.bstart[b];
+      const int64_t go = sm.goff[b], delta = sm.peer.delta[b];
+      uint64_t *kout = sm.peer.keys[b];
+      uint32_t *pout = sm.peer.pos[b];
+      const int mis = (int)((go + st + delta) & 31);
+      for (int s = st - mis + (int)tid; s < st + cb; s += THREADS) {
+        if (s < st) continue;
+        const int64_t local = go + s, dst = local + delta;
+        const bool room = (uint64_t)(sm.peer.region ? local : dst) < sm.peer.cap;
+        const uint64_t kk = sm.keys[s];
+        if (room && !(P.dbg & 2u)) {
+          kout[dst] = kk;
+          if constexpr (FROM_SEQ) pout[dst] = (uint32_t)(P.sv.s0 + q0 + 1) + P.pos_add + sm.pos[s];
+          else pout[dst] = sm.pos[s];
+        }
+        if constexpr (HAS_NEXT) atomicAdd(&sm.next[P.next(kk)], 1u);
+      }
+    }
+   }
+  } else
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const int s = j * THREADS + tid;

@@ -354,7 +354,7 @@ class ShardedIndex:
 
     def _gather_sizes(self):
         if self._U_all is None:
-            U, N, _ = self.local.sizes
+            U, N = self.local.sizes_un
             dev = self.engine.device
             sizes = torch.tensor([U, N], dtype=torch.int64, device=dev)
             allsz = torch.empty(self.world * 2, dtype=torch.int64, device=dev)
@@ -386,7 +386,7 @@ class ShardedIndex:
         `row_offset` / `i_offset` into one matrix are the index's kmer.pos.  Collective on first use (sizes are gathered).
         out: optional preallocated {"pos": (N_local, 2) int32, "count": (U_local,) int32} (device or host)."""
         import kmer_hasher_b200 as kh
-        U, N, _ = self.local.sizes
+        U, N = self.local.sizes_un
         i_base = self.i_offset
         out = out or {}
         res = {"pos": None, "count": None, "i_offset": i_base, "row_offset": self.row_offset}
@@ -442,7 +442,7 @@ def sharded_build(own_bytes, L: int, k: int, engine, group=None, n_samples: int 
     n_local = sum(counts)
     if world == 1:
         local = engine.build_records(keys, pos, n_local, k)
-        U, N, _ = local.sizes
+        U, N = local.sizes_un
         return ShardedIndex(local, k, 0, 1, [U], [N], splitters, engine)
 
     # counts all-gather sizes the receive buffers; then ONE all-to-all per array
@@ -458,7 +458,7 @@ def sharded_build(own_bytes, L: int, k: int, engine, group=None, n_samples: int 
     dist.all_to_all_single(rpos[:n_recv], pos[:n_local], recv_counts, counts, group=group)
     del keys, pos
     local = engine.build_records(rkeys, rpos, n_recv, k)
-    U, N, _ = local.sizes
+    U, N = local.sizes_un
     sizes = torch.tensor([U, N], dtype=torch.int64, device=rkeys.device)
     all_sizes = [torch.empty_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes, group=group)
@@ -512,7 +512,7 @@ def sharded_build_p2p(own_bytes, L: int, k: int, engine: CudaEngine, xchg: PeerE
     # -3: an owner overflowed or its fix-up lists did (the latter is local to one rank); -7: the position-order check
     # failed on one device.  The ranks agree on the worst status and act together: a rank must never enter the general
     # path's collectives alone.
-    worst, U_all, N_all = xchg.agree(status, local.sizes[:2] if local is not None else (0, 0))
+    worst, U_all, N_all = xchg.agree(status, local.sizes_un if local is not None else (0, 0))
     if worst:
         if local is not None:
             local.free()
@@ -557,7 +557,7 @@ def sharded_build_ranges(own_bytes, L: int, k: int, engine, xchg, group=None) ->
             status = -e.code
     finally:
         engine.shard_close(sh)
-    worst, U_all, N_all = xchg.agree(status, local.sizes[:2] if local is not None else (0, 0))
+    worst, U_all, N_all = xchg.agree(status, local.sizes_un if local is not None else (0, 0))
     if worst:
         if local is not None:
             local.free()
@@ -670,7 +670,7 @@ def sharded_parity_sums(ix: ShardedIndex):
     sequence ('keys'[1], 'bind') -- plus whether every owner's position lists ascend."""
     import kmer_hasher_b200 as kh
     dev = ix.engine.device
-    U, N, _ = ix.local.sizes
+    U, N = ix.local.sizes_un
     keys = torch.empty(max(U, 1), dtype=torch.int64, device=dev)
     ix.engine._lib.check(ix.engine.L.kmg_kmers_u64(ix.local._handle(), keys.data_ptr()))
     keys = keys[:U]
@@ -700,8 +700,10 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     from bench import ClockSampler, config_of, METRIC
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = torch.device("cuda", torch.cuda.current_device())
+    from .affinity import bind_near_gpu
+    numa = {"bound": False, "why": "KMG_NO_NUMA_BIND set"} if os.environ.get("KMG_NO_NUMA_BIND") else bind_near_gpu(dev.index or 0)
     engine = CudaEngine(dev)
-    for key in ("scatter_shape", "scatter_bitmap"):          # tuning runs: KMG_TUNE_scatter_shape=1 ...
+    for key in ("scatter_shape", "scatter_bitmap", "sort_dbg"):          # tuning runs: KMG_TUNE_scatter_shape=1 ...
         if os.environ.get("KMG_TUNE_" + key):
             engine._lib.check(engine.L.kmg_tune(key.encode(), int(os.environ["KMG_TUNE_" + key])))
     strong = args.scaling == "strong"
@@ -733,7 +735,7 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
             return sharded_build_ranges(own, Ltot, k, engine, xchg)
         return sharded_build_p2p(own, Ltot, k, engine, xchg) if xchg is not None else sharded_build(own, Ltot, k, engine)
     ix = build(own_dev)
-    U, N, _ = ix.local.sizes
+    U, N = ix.local.sizes_un
     ntot = ix.N_total
     used_ranges = bool(ix.ranges)
     # ---- parity of the sharded index against the reference's digests of the same sequence (strong scaling only) ----
@@ -843,7 +845,7 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
                                     f"{world} shards of {L} bases each of one {Ltot}-base sequence") + "; (key,pos) records " + path,
                        "bases_total": Ltot, "kmers": int(ntot), "per_rank_kmers": all_sizes[:, 0].tolist(),
                        "per_rank_distinct": all_sizes[:, 1].tolist(), "l2": "inputs_exceed_l2"},
-            "parity_checked": parity,
+            "parity_checked": parity, "host_placement": numa,
             "e2e": {"value": ntot / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(Ltot),
                     "d2h_bytes_per_step": int((8 * all_sizes[:, 0] + 4 * all_sizes[:, 1]).sum()), "ms_per_step": ms_e2e,
                     "what": "per rank: pinned host shard -> device, sharded build, kmer_pos(2|8) of the owner's slice into pinned host arrays"},

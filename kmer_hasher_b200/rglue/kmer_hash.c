@@ -224,7 +224,9 @@ SEXP kmer_positions(SEXP ptr_r, SEXP opt_flag_r) {
   if (h->counter) return count_table_positions(h, flag);
 
   uint64_t U = 0, N = 0, P = 0;
-  if (kmg_sizes(h->index, &U, &N, &P) != KMG_OK) error("kmer.pos failed: %s", kmg_last_error());
+  /* P (rows of pair.pos) costs a sweep of the index the first time: asked for only under flag 4, as the reference only
+   * walks the lists for pairs there (src/kmer_hash.c:1113) */
+  if (kmg_sizes(h->index, &U, &N, (flag & F_PAIRS) ? &P : NULL) != KMG_OK) error("kmer.pos failed: %s", kmg_last_error());
   /* size checks BEFORE any allocation: R vectors/matrix extents are int */
   if ((flag & (F_KMER | F_COUNT)) && U > (uint64_t)INT_MAX) error("%llu distinct k-mers do not fit an R vector", (unsigned long long)U);
   if ((flag & F_POS) && N > (uint64_t)INT_MAX) error("%llu positions do not fit an R matrix", (unsigned long long)N);

@@ -62,6 +62,7 @@ class OracleEngine:
     def build_records(self, keys, pos, n, k):
         ix = self.o.build_from_records(keys.numpy()[:n].view(np.uint64), pos.numpy()[:n], k)
         ix.sizes = (ix.U, ix.N, ix.P)
+        ix.sizes_un = (ix.U, ix.N)
         ix.free = ix.close
         return ix
 
