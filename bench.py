@@ -431,15 +431,15 @@ def bench_single(args, kh, torch, w, k, L, steps, warm, hbm_peak, peak_src, dev)
                  "kernel_ms_sum": kern_ms,
                  "survey_formula_bytes": int(survey_bytes), "survey_formula_frac": survey_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
                  "note": "frac = bytes the launched kernels must move (their own algorithmic bytes, summed) / step time; survey_formula_* "
-                         f"charges SURVEY.md 8d's {R_key}-pass LSD sort by key although the grouped build runs 4 passes: equivalent work, "
-                         "not a kernel efficiency"}
+                         f"charges SURVEY.md 8d's {R_key}-pass LSD sort by key although the grouped build runs fewer passes: equivalent "
+                         "work, not a kernel efficiency"}
     h2d = L
     d2h = 8 * N + 4 * U
     cfg = config_of(w, k, L)
     hb = _lib.load().kmg_tune_get(b"hash_bits", int(N)) if k >= 21 else 0
     detail = {"kmers": int(N), "distinct": int(U),
-              "kmer_order": (f"grouped (make.kmer.hash default for k >= 21: 4 radix passes on {hb} bits of a mix of the key, colliding groups "
-                             "fixed up; do.sort=TRUE gives ascending keys)") if k >= 21 else "ascending key",
+              "kmer_order": (f"grouped (make.kmer.hash default for k >= 21: {hb // 8} radix passes on {hb} bits of a mix of the key, groups in "
+                             "which k-mers sharing those bits interleave fixed up; do.sort=TRUE gives ascending keys)") if k >= 21 else "ascending key",
               "l2": "inputs_exceed_l2 (keys 8N + pos 4N bytes per pass >> 126 MB)"}
     return {"metric": METRIC, "value": N / (ms * 1e-3), "unit": "k-mers/s", "n_gpus": 1, "steps": steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

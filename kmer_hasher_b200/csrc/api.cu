@@ -546,12 +546,10 @@ static SortPlan grouped_plan(int64_t n_upper) {
     return SortPlan{rb, g_hash_bits / rb};
   }
   if (g_hash_rb > 0) return SortPlan{g_hash_rb, (36 + g_hash_rb - 1) / g_hash_rb};
-  // measured on B200 (profiles/r02_sortbench_*_b.log): a 9-bit pass costs 1.18x an 8-bit one, 10-bit 1.66x, and b sorted bits
-  // leave ~N^2 / 2^(b+1) colliding pairs to detect and fix.  At 40 M records 4 x 8 = 32 bits wins (1.84 ms against 1.92 for
-  // 4 x 9 and 1.97 for 5 x 8); at 250 M the 7 M colliding pairs of 32 bits cost 4 ms and 5 x 8 = 40 bits wins (10.4 ms against
-  // 11.5 and 12.5); 4 x 9 = 36 bits covers the stretch in between.
-  if (n_upper <= 48000000) return SortPlan{8, 4};
-  return n_upper <= (int64_t(1) << 26) ? SortPlan{9, 4} : SortPlan{8, 5};
+  // measured on B200 (profiles/r02_sortbench_*): a 9-bit pass costs 1.18x an 8-bit one, 10-bit 1.66x, so 8-bit digits it is;
+  // b sorted bits leave ~N^2 / 2^(b+1) pairs of k-mers that share them.  Since only groups whose k-mers INTERLEAVE are fixed
+  // (a few per cent of the pairs: group_detect_kernel), 32 bits carry a 250 M-record build (7 M pairs) at 4 passes instead of 5.
+  return n_upper <= (int64_t)400000000 ? SortPlan{8, 4} : SortPlan{8, 5};
 }
 // is the grouped build used for this k and requested order?  From k = 21 on (keys of more than 40 bits: a sort by key would
 // need 6+ passes): independent of the size, so that every rank of a sharded build decides alike.

@@ -113,7 +113,8 @@ rle_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos, 
 // Records are ordered by the low bits of h = mix64(key), stably.  A "group" is a run of equal low bits; almost
 // every group holds one k-mer.  Where it holds several (a collision of the low bits: ~N^2 / 2^(bits+1) pairs)
 // they interleave and the group has to be partitioned by h, stably.  group_detect_kernel finds those groups
-// (read-only), small_fix_kernel sorts the short ones in place, big_fix_kernel partitions the long ones.
+// (read-only; groups whose k-mers are already contiguous are left alone), small_fix_kernel sorts the short ones in
+// place, big_fix_kernel partitions the long ones.
 constexpr int SMALL_GROUP = 64;
 constexpr uint32_t CLAIM_SLOTS = 1u << 16;
 
@@ -148,12 +149,24 @@ __device__ __forceinline__ void file_group(const uint64_t *__restrict__ h, uint6
   while (e < n && w < WALK && (h[e] & lowmask) == low) { ++e; ++w; }
   if (e < n && (h[e] & lowmask) == low) e = low == lowmask ? n : first_at_least(h, n, lowmask, low + 1);
   if (e - s <= SMALL_GROUP) {
-    bool first = true;                                   // the group's first boundary files the task
+    bool first = true;                                   // the group's first boundary decides for the group
     const uint64_t h0 = h[s];
     for (uint64_t j = s + 1; j < i; ++j) first &= h[j] == h0;
     if (first) {
-      const uint32_t t = atomicAdd(fl.counters + 0, 1u);
-      if (t < fl.small_cap) fl.small_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
+      // Only a group in which some k-mer's records are SEPARATED by another's needs work: k-mers that merely share the low
+      // bits but already sit one after the other (the usual case: two k-mers with one position each) are left as they
+      // are -- the order of the k-mers inside a group means nothing (the key table's bucket depends on the low bits only).
+      bool dirty = false;
+      for (uint64_t j = s + 1; j < e && !dirty; ++j) {
+        const uint64_t x = h[j];
+        if (x != h[j - 1])
+          for (uint64_t m = s; m + 1 < j; ++m)
+            if (h[m] == x) { dirty = true; break; }
+      }
+      if (dirty) {
+        const uint32_t t = atomicAdd(fl.counters + 0, 1u);
+        if (t < fl.small_cap) fl.small_tasks[t] = make_uint2((uint32_t)s, (uint32_t)e); else fl.counters[2] = 1;
+      }
     }
   } else {
     uint32_t slot = (uint32_t)(mix64(s) & (CLAIM_SLOTS - 1));
@@ -185,7 +198,15 @@ __global__ void group_detect_kernel(const uint64_t *__restrict__ h, const IndexS
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (q == 0 && j == 0) continue;
-      if (((v[j] ^ v[j + 1]) & lowmask) == 0 && v[j] != v[j + 1]) file_group(h, n, lowmask, 4 * q + j, fl);
+      if (((v[j] ^ v[j + 1]) & lowmask) == 0 && v[j] != v[j + 1]) {
+        // two k-mers share the low bits.  By far the commonest such group is just these two records (a collision of two
+        // k-mers with one position each): nothing to fix, and the neighbours needed to see it are mostly in registers
+        const uint64_t idx = 4 * q + j, low = v[j] & lowmask;
+        bool left_out = idx < 2, right_out = idx + 1 >= n;
+        if (!left_out) left_out = ((j >= 1 ? v[j - 1] : h[idx - 2]) & lowmask) != low;
+        if (!right_out) right_out = ((j + 2 <= 4 ? v[j + 2] : h[idx + 1]) & lowmask) != low;
+        if (!(left_out && right_out)) file_group(h, n, lowmask, idx, fl);
+      }
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < n - 4 * quads) {
