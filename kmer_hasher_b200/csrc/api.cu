@@ -897,6 +897,7 @@ static int build_grouped(const SeqView &sv, SortPlan plan, kmg_index *ix, SortSc
   dfree(kr, s); dfree(pr, s); dfree(d_counts, s); dfree(d_over, s); dfree(segs, s);
   *overflow = h_cnt[2] != 0;
   *region_overflow = h_over != 0;
+  if (log_on()) fprintf(stderr, "[kmergpu] grouped build on %d bits: %u short and %u long groups fixed\n", plan.bits(), h_cnt[0], h_cnt[1]);
   ix->hbits = plan.bits();
   const double N = (double)ix->N, L = (double)sv.avail;
   if (!regions) prof_bytes("hist_seq", L);

@@ -185,27 +185,78 @@ __device__ __forceinline__ void file_group(const uint64_t *__restrict__ h, uint6
   }
 }
 
-// four records per thread (two 16-byte loads + the predecessor); boundaries are rare, the stream is the cost
+// file_group by a whole warp (every lane calls with the same i): the 32 records around the boundary arrive as ONE coalesced
+// load instead of a serial walk; the group's extent comes from a ballot, "is this the group's first boundary" from another,
+// and "do some k-mer's records lie apart" from __match_any_sync.  Groups that reach the window's edge take the serial path.
+__device__ __forceinline__ void file_group_warp(const uint64_t *__restrict__ h, uint64_t n, uint64_t lowmask, uint64_t i, const FixLists &fl) {
+  const unsigned lane = lane_id();
+  const uint64_t w0 = i >= 16 ? i - 16 : 0;
+  const unsigned p = (unsigned)(i - w0);                   // the boundary's second record sits in lane p (>= 1)
+  const bool valid = w0 + lane < n;
+  const uint64_t x = valid ? h[w0 + lane] : 0;
+  const uint64_t low = __shfl_sync(FULL, x, p) & lowmask;
+  const unsigned m = __ballot_sync(FULL, valid && (x & lowmask) == low);
+  const unsigned below = ~m & ((1u << p) - 1u);            // lanes before p outside the group
+  const unsigned s = below ? 32u - __clz(below) : 0u;
+  const unsigned above = ~m >> p;                          // bit t: lane p + t outside the group (lane p itself is inside)
+  const unsigned e = above ? p + (unsigned)__ffs(above) - 1u : 32u;
+  if ((s == 0 && w0 > 0) || (e == 32 && w0 + 32 < n)) {    // may extend beyond the window: the general path
+    if (lane == 0) file_group(h, n, lowmask, i, fl);
+    return;
+  }
+  const unsigned run = (e >= 32 ? ~0u : ((1u << e) - 1u)) & ~((1u << s) - 1u);
+  const bool in = (run >> lane) & 1u;
+  const uint64_t xs = __shfl_sync(FULL, x, s);
+  if (__ballot_sync(FULL, in && lane < p && x != xs)) return;          // an earlier boundary of this group decides for it
+  const unsigned mm = __match_any_sync(FULL, in ? x : ~uint64_t(lane)) & run;   // lanes of the group with this lane's k-mer
+  const unsigned t = mm ? mm >> (__ffs(mm) - 1) : 0u;
+  const bool apart = in && (t & (t + 1u)) != 0;            // not one contiguous run
+  if (__ballot_sync(FULL, apart) && lane == 0) {
+    const uint32_t task = atomicAdd(fl.counters + 0, 1u);
+    if (task < fl.small_cap) fl.small_tasks[task] = make_uint2((uint32_t)(w0 + s), (uint32_t)(w0 + e)); else fl.counters[2] = 1;
+  }
+}
+
+// four records per thread; boundaries are rare, the stream is the cost
 __global__ void group_detect_kernel(const uint64_t *__restrict__ h, const IndexStats *st, int bits, FixLists fl) {
   const uint64_t n = st->n;
   const uint64_t lowmask = bits >= 64 ? ~uint64_t(0) : ((uint64_t(1) << bits) - 1);
   const uint64_t quads = n / 4;
-  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (uint64_t)gridDim.x * blockDim.x) {
-    const uint4 a = ld_stream_u4(reinterpret_cast<const uint4 *>(h) + 2 * q);
-    const uint4 b = ld_stream_u4(reinterpret_cast<const uint4 *>(h) + 2 * q + 1);
-    const uint64_t v[5] = {q ? h[4 * q - 1] : 0, (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
-                           (uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32)};
+  const unsigned lane = lane_id();
+  // whole warps iterate together: groups that need a closer look are handled by the warp, one after the other
+  for (uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); q0 < quads; q0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t q = q0 + lane;
+    unsigned need = 0;                                     // bit j: the boundary before record 4q + j needs a closer look
+    if (q < quads) {
+      // records 4q-2 .. 4q+4: the thread's four, two before and one after, all requested at once (the neighbours' lines are
+      // in L1 or L2: other threads stream them), so that the test below never waits for a dependent load
+      const uint4 *h4 = reinterpret_cast<const uint4 *>(h);
+      const uint4 a = __ldg(h4 + 2 * q), b = __ldg(h4 + 2 * q + 1);
+      const uint4 pv = q ? __ldg(h4 + 2 * q - 1) : make_uint4(0, 0, 0, 0);
+      const uint64_t nx = 4 * q + 4 < n ? __ldg(h + 4 * q + 4) : 0;
+      const uint64_t v[7] = {(uint64_t)pv.x | ((uint64_t)pv.y << 32), (uint64_t)pv.z | ((uint64_t)pv.w << 32),
+                             (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
+                             (uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32), nx};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                        // the boundary between records 4q+j-1 (v[j+1]) and 4q+j (v[j+2])
+        if (q == 0 && j == 0) continue;
+        if (((v[j + 1] ^ v[j + 2]) & lowmask) == 0 && v[j + 1] != v[j + 2]) {
+          // two k-mers share the low bits.  By far the commonest such group is just these two records (a collision of two
+          // k-mers with one position each): nothing to fix
+          const uint64_t idx = 4 * q + j, low = v[j + 1] & lowmask;
+          const bool left_out = idx < 2 || (v[j] & lowmask) != low;
+          const bool right_out = idx + 1 >= n || (v[j + 3] & lowmask) != low;
+          if (!(left_out && right_out)) need |= 1u << j;
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (q == 0 && j == 0) continue;
-      if (((v[j] ^ v[j + 1]) & lowmask) == 0 && v[j] != v[j + 1]) {
-        // two k-mers share the low bits.  By far the commonest such group is just these two records (a collision of two
-        // k-mers with one position each): nothing to fix, and the neighbours needed to see it are mostly in registers
-        const uint64_t idx = 4 * q + j, low = v[j] & lowmask;
-        bool left_out = idx < 2, right_out = idx + 1 >= n;
-        if (!left_out) left_out = ((j >= 1 ? v[j - 1] : h[idx - 2]) & lowmask) != low;
-        if (!right_out) right_out = ((j + 2 <= 4 ? v[j + 2] : h[idx + 1]) & lowmask) != low;
-        if (!(left_out && right_out)) file_group(h, n, lowmask, idx, fl);
+      unsigned bal = __ballot_sync(FULL, (need >> j) & 1u);
+      while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1;
+        file_group_warp(h, n, lowmask, 4 * (q0 + (uint64_t)src) + (uint64_t)j, fl);
       }
     }
   }
