@@ -217,10 +217,17 @@ __device__ __forceinline__ void file_group_warp(const uint64_t *__restrict__ h, 
   }
 }
 
-// four records per thread; boundaries are rare, the stream is the cost
+// Four records per thread; boundaries are rare, the stream is the cost -- and the instruction count: the test runs on
+// every record, so it is kept branch-free on 32-bit halves.  LOW32: the sorted bits are exactly the low word (the plan of
+// every build up to 400 M records); otherwise the two words are masked first (40 bits beyond 400 M records, fewer in tests).
+//   E[i]: records i and i+1 (of the seven the thread sees: 4q-2 .. 4q+4) share the sorted bits; D[i]: they differ as k-mers.
+//   boundary before record 4q+j  <=>  E[j+1] && D[j+1];  nothing to do if the group is just those two records, i.e. neither
+//   E[j] nor E[j+2] -- by far the commonest collision (two k-mers with one position each).
+template <bool LOW32>
 __global__ void group_detect_kernel(const uint64_t *__restrict__ h, const IndexStats *st, int bits, FixLists fl) {
   const uint64_t n = st->n;
   const uint64_t lowmask = bits >= 64 ? ~uint64_t(0) : ((uint64_t(1) << bits) - 1);
+  const uint32_t mlo = (uint32_t)lowmask, mhi = (uint32_t)(lowmask >> 32);
   const uint64_t quads = n / 4;
   const unsigned lane = lane_id();
   // whole warps iterate together: groups that need a closer look are handled by the warp, one after the other
@@ -228,28 +235,33 @@ __global__ void group_detect_kernel(const uint64_t *__restrict__ h, const IndexS
     const uint64_t q = q0 + lane;
     unsigned need = 0;                                     // bit j: the boundary before record 4q + j needs a closer look
     if (q < quads) {
-      // records 4q-2 .. 4q+4: the thread's four, two before and one after, all requested at once (the neighbours' lines are
-      // in L1 or L2: other threads stream them), so that the test below never waits for a dependent load
+      // all seven records requested at once (the neighbours' lines are in L1 or L2: other threads stream them)
       const uint4 *h4 = reinterpret_cast<const uint4 *>(h);
       const uint4 a = __ldg(h4 + 2 * q), b = __ldg(h4 + 2 * q + 1);
       const uint4 pv = q ? __ldg(h4 + 2 * q - 1) : make_uint4(0, 0, 0, 0);
       const uint64_t nx = 4 * q + 4 < n ? __ldg(h + 4 * q + 4) : 0;
-      const uint64_t v[7] = {(uint64_t)pv.x | ((uint64_t)pv.y << 32), (uint64_t)pv.z | ((uint64_t)pv.w << 32),
-                             (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
-                             (uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32), nx};
+      const uint32_t lo[7] = {pv.x, pv.z, a.x, a.z, b.x, b.z, (uint32_t)nx};
+      const uint32_t hi[7] = {pv.y, pv.w, a.y, a.w, b.y, b.w, (uint32_t)(nx >> 32)};
+      unsigned E = 0, D = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {                        // the boundary between records 4q+j-1 (v[j+1]) and 4q+j (v[j+2])
-        if (q == 0 && j == 0) continue;
-        if (((v[j + 1] ^ v[j + 2]) & lowmask) == 0 && v[j + 1] != v[j + 2]) {
-          // two k-mers share the low bits.  By far the commonest such group is just these two records (a collision of two
-          // k-mers with one position each): nothing to fix
-          const uint64_t idx = 4 * q + j, low = v[j + 1] & lowmask;
-          const bool left_out = idx < 2 || (v[j] & lowmask) != low;
-          const bool right_out = idx + 1 >= n || (v[j + 3] & lowmask) != low;
-          if (!(left_out && right_out)) need |= 1u << j;
+      for (int i = 0; i < 6; ++i) {
+        bool e, d;
+        if constexpr (LOW32) { e = lo[i] == lo[i + 1]; d = hi[i] != hi[i + 1]; }
+        else {
+          const uint32_t xl = lo[i] ^ lo[i + 1], xh = hi[i] ^ hi[i + 1];
+          e = ((xl & mlo) | (xh & mhi)) == 0;
+          d = (xl | xh) != 0;
         }
+        E |= (unsigned)e << i;
+        D |= (unsigned)d << i;
       }
+      // records that do not exist: 4q-2, 4q-1 for q = 0 (bits 0, 1 of E; the boundary before record 0), 4q+4 at the end (bit 5)
+      if (q == 0) { E &= ~3u; D &= ~2u; }
+      if (4 * q + 4 >= n) E &= ~(1u << 5);
+      const unsigned bnd = (E & D) >> 1;                   // bit j: a boundary before record 4q + j (E[j+1] && D[j+1])
+      need = bnd & ((E | (E >> 2)) & 0xFu);                // ... whose group is more than the two records
     }
+    if (!__any_sync(FULL, need != 0)) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       unsigned bal = __ballot_sync(FULL, (need >> j) & 1u);

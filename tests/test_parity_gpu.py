@@ -540,7 +540,7 @@ def test_every_sort_pass_variant_is_exact(kh, oracle, rank, shape, rb):
         assert L.kmg_tune_get(b"unstable_rebuilds", 0) == 0
     finally:
         _lib.check(L.kmg_tune(b"sort_cfg", -1))
-        _lib.check(L.kmg_tune(b"sort_shape", 0))
+        _lib.check(L.kmg_tune(b"sort_shape", -1))
         _lib.check(L.kmg_tune(b"hash_rb", 0))
 
 
