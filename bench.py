@@ -373,9 +373,11 @@ def bench_single(args, kh, torch, w, k, L, steps, warm, hbm_peak, peak_src, dev)
             kh.kmer_pos(h, 2 | 8, out={"pos": pos_pg, "count": cnt_pg})
             h.free()
         step_pg()
-        ms_pg = timed(torch, step_pg, max(3, steps // 4))
+        pg = sorted(timed(torch, step_pg, 1) for _ in range(max(5, steps // 4)))    # host memcpy threads share the box: per-step times, median
+        ms_pg = pg[len(pg) // 2]
         e2e_pageable = {"value": N / (ms_pg * 1e-3), "unit": "k-mers/s", "ms_per_step": ms_pg, "vs_pinned": ms_pg / ms_e2e,
-                        "what": "same calls, pageable numpy arrays in and out (the R glue's INTEGER(allocMatrix) / CHAR memory)"}
+                        "ms_min": pg[0], "ms_max": pg[-1], "steps": len(pg),
+                        "what": "same calls, pageable numpy arrays in and out (the R glue's INTEGER(allocMatrix) / CHAR memory); median step"}
         del seq_pg, pos_pg, cnt_pg
 
     probe = None if args.no_probe else probe_leg(kh, torch, _lib, w, seq_pin, seq_dev, k, steps, hbm_peak)

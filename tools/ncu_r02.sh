@@ -17,13 +17,13 @@ python bench.py --steps 3 --warmup 1 --no-cpu --no-pageable --no-secondary > $O/
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/r02_launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-pageable --no-secondary > $O/r02_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-python tools/sortbench.py 250000000 32 "3:0:8:32,3:0:8:40,3:1:8:32" c3 > $O/r02_sortbench_final_c3.log 2>&1 || { echo "plain sortbench failed"; exit 1; }
+python tools/sortbench.py 250000000 32 "3:-1:8:32,3:0:8:32,3:-1:8:40" c3 > $O/r02_sortbench_final_c3.log 2>&1 || { echo "plain sortbench failed"; exit 1; }
 cat $O/r02_sortbench_final_c3.log
 # record passes of the third build (2 warm builds = 8 pass launches at 32 sorted bits, then the from-sequence pass of the third)
-cap sort_pass scatter_pass_kernel 9 2 python tools/sortbench.py 250000000 32 "3:0:8:32" c3
-cap sort_pass_seq scatter_pass_kernel 8 1 python tools/sortbench.py 250000000 32 "3:0:8:32" c3
-cap rle rle_kernel 2 1 python tools/sortbench.py 250000000 32 "3:0:8:32" c3
-cap group_detect group_detect_kernel 2 1 python tools/sortbench.py 250000000 32 "3:0:8:32" c3
+cap sort_pass scatter_pass_kernel 9 3 python tools/sortbench.py 250000000 32 "3:-1:8:32" c3
+cap sort_pass_seq scatter_pass_kernel 8 1 python tools/sortbench.py 250000000 32 "3:-1:8:32" c3
+cap rle rle_kernel 2 1 python tools/sortbench.py 250000000 32 "3:-1:8:32" c3
+cap group_detect group_detect_kernel 2 1 python tools/sortbench.py 250000000 32 "3:-1:8:32" c3
 python tools/probebench.py > $O/r02_probebench3.log 2>&1 || { echo "plain probebench failed"; exit 1; }
 cap probe_lookup probe_lookup_kernel 1 1 python tools/probebench.py
 cap probe_emit probe_emit_kernel 0 1 python tools/probebench.py
