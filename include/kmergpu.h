@@ -70,10 +70,10 @@ int kmg_build(const char *seq, int64_t len, int k, kmg_index **out);   /* = kmg_
 
 /* The order of the k-mers in an index (and so the meaning of the k-mer number i) is not semantic: the
  * reference's is its hash table's bucket order.  KMG_ORDER_SORTED: ascending 2-bit key (A<C<T<G, first base
- * most significant), ceil(2k/8) radix passes.  KMG_ORDER_GROUPED: the records are sorted on 40 bits of a
- * bijective mix of the key, which tells almost all k-mers of a genome apart in 5 passes; the few groups in
- * which two k-mers share those bits are partitioned afterwards.  k-mers then come in the order of the mixed
- * key; used when it saves at least two passes (k >= 25), otherwise the build is sorted.  Everything else
+ * most significant), ceil(2k/8) radix passes.  KMG_ORDER_GROUPED: the records are sorted on 32 bits (40 beyond
+ * 400 M records) of a bijective mix of the key, which tells almost all k-mers of a genome apart in 4 passes; the
+ * few groups in which k-mers that share those bits interleave are partitioned afterwards.  k-mers then come in the
+ * order of those bits; used when it saves passes (k >= 21), otherwise the build is sorted.  Everything else
  * (positions ascending per k-mer, counts, pairs, probes) is identical; kmg_index_order tells which. */
 #define KMG_ORDER_GROUPED 0
 #define KMG_ORDER_SORTED 1
@@ -177,7 +177,7 @@ int kmg_query_records(const kmg_index *idx, const uint64_t *d_keys, const int32_
  *                     receives, d_info[1] = 1 if an owner would overflow (its surplus is dropped and
  *                     kmg_build_received / kmg_query_received then fail with KMG_ERR_RANGE).
  * `order` (kmg_shard_pack, kmg_shard_open_packed, kmg_build_received; the same value on every rank):
- * with KMG_ORDER_GROUPED and k >= 25 the sample, the owner ranges and the exchanged records are those of
+ * with KMG_ORDER_GROUPED and k >= 21 the sample, the owner ranges and the exchanged records are those of
  * the mixed key (see kmg_build_ordered) and every owner builds a grouped index; query records scattered
  * from a shard opened that way carry the mix too (kmg_query_received: mixed = 1).
  */

@@ -176,7 +176,7 @@ def make_kmer_hash(seq, k, do_sort=False) -> KmerHash:
     Position lists are always ascending, so the reference's `do.sort` has nothing to sort; here it selects
     the order of the K-MERS, which is not semantic (the reference's is hash-bucket order): do_sort=True gives
     ascending 2-bit key (KMG_ORDER_SORTED), the default the faster grouped build (KMG_ORDER_GROUPED: order of
-    a mix of the key, used for k >= 25).  `kmer_pos(..., canonical=True)` re-orders any index by key.
+    a mix of the key, used for k >= 21).  `kmer_pos(..., canonical=True)` re-orders any index by key.
     """
     if isinstance(seq, (list, tuple)):
         if len(seq) < 1:
