@@ -629,6 +629,9 @@ extern "C" int kmg_selftest_lane_order(uint32_t *failures) {
   if (!failures) return fail(KMG_ERR_ARG, "failures is NULL");
   return lane_order_failures(failures);
 }
+// Two tiles of the default record pass must fit the 196 KB shared-memory carve-out (1 KB per block is reserved): one step
+// further (228 KB) leaves 28 KB of L1 for the loads in flight and costs every pass 8 % (measured: profiles/r02_notes.md).
+static_assert(2 * (sizeof(PassSmem<PassCfg<256, 28, 2, 3, 4, 8>, false>) + 1024) <= 196 * 1024, "the record pass's tile outgrew the 196 KB carve-out");
 constexpr int REGION_SAMPLE_STRIDE = 251;   // prime: tandem arrays are sampled in all their phases
 constexpr int SORT_TILE_MIN = 4096;   // status sizing: smallest tile of any shape
 
@@ -807,7 +810,7 @@ static int fix_groups(SortScratch &sc, int bits, uint64_t *keys, uint32_t *pos, 
   if (bits == 32) LAUNCH("group_detect", s, group_detect_kernel<true><<<dgrid, 256, 0, s>>>(keys, sc.stats(), bits, fl));
   else LAUNCH("group_detect", s, group_detect_kernel<false><<<dgrid, 256, 0, s>>>(keys, sc.stats(), bits, fl));
   LAUNCH("small_fix", s, small_fix_kernel<<<g_ctx.sms * 4, 128, 0, s>>>(keys, pos, fl));
-  LAUNCH("big_fix", s, big_fix_kernel<256><<<g_ctx.sms, 256, 0, s>>>(keys, pos, sk, sp, fl));
+  LAUNCH("big_fix", s, big_fix_kernel<1024><<<g_ctx.sms, 1024, 0, s>>>(keys, pos, sk, sp, fl));   // 1024 threads: config 2's long groups 87 -> 50 us
   CU(cudaMemcpyAsync(h_cnt, fl.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   return KMG_OK;
 }
