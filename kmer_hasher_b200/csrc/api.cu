@@ -1378,7 +1378,9 @@ static int ensure_hash(kmg_index *ix) {
       CU(cudaMemcpyAsync(&h_last, d_last, 8, cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
       if (h_last + 1 < nb) CU(cudaMemsetAsync(slots + (h_last + 1) * BUCKET_SLOTS, 0, (nb - h_last - 1) * BUCKET_SLOTS * sizeof(uint4), s));
-      LAUNCH("hash_insert", s, hash_insert_kernel<<<grid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, kt, true));
+      constexpr int OV_ITEMS = 8;
+      const unsigned ogrid = (unsigned)ceil_div<uint64_t>(ix->U, 256 * OV_ITEMS);
+      LAUNCH("hash_insert", s, hash_overflow_kernel<OV_ITEMS><<<ogrid, 256, 0, s>>>(ix->ukeys, ix->ustart, ix->U, kt));
       CU(cudaStreamSynchronize(s));
       return KMG_OK;
     };

@@ -94,6 +94,60 @@ __global__ void hash_insert_kernel(const uint64_t *__restrict__ ukeys, const uin
   }
 }
 
+// The overflow phase of a streamed table (hash_stream_kernel below): a bucket's third and later k-mers, ~7 % of all, each
+// placed by 128-bit CAS in the first bucket after its home that has room.  A CAS is a ~1.5 us round trip and a k-mer needs
+// about two, so the cost is latency x (k-mers per thread in flight): a thread owns ITEMS consecutive k-mers and issues the
+// CAS of ALL its pending ones back to back before looking at any result (one k-mer per thread, 93 % of the lanes idle in
+// every round: 5.8 ms for 230 M k-mers; this way: see profiles/r02_notes.md).
+template <int ITEMS>
+__global__ void __launch_bounds__(256)
+hash_overflow_kernel(const uint64_t *__restrict__ ukeys, const uint32_t *__restrict__ ustart, uint64_t U, KeyHash kh) {
+  const uint64_t u0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * ITEMS;
+  if (u0 >= U) return;
+  uint64_t key[ITEMS], cur[ITEMS];                         // cur: the bucket tried next
+  uint32_t st[ITEMS], cn[ITEMS], slot = 0;                  // slot: bit i = which of the bucket's two slots item i tries next
+  uint32_t pend = 0;
+  uint64_t bm2 = u0 >= 2 ? kh.bucket(ukeys[u0 - 2]) : ~uint64_t(0), bm1 = u0 >= 1 ? kh.bucket(ukeys[u0 - 1]) : ~uint64_t(0);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint64_t u = u0 + i;
+    key[i] = u < U ? ukeys[u] : 0;
+    const uint64_t b = kh.bucket(key[i]);
+    if (u < U && u >= 2 && bm1 == b && bm2 == b) {         // the two k-mers before it share its home bucket: it did not fit
+      pend |= 1u << i;
+      cur[i] = kh.next(b);
+      st[i] = ustart[u];
+      cn[i] = ustart[u + 1] - st[i];
+    }
+    bm2 = bm1; bm1 = b;
+  }
+  while (pend) {
+    uint64_t olo[ITEMS], ohi[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      if ((pend >> i) & 1u) {
+        uint4 *sl = kh.slots + cur[i] * BUCKET_SLOTS + ((slot >> i) & 1u);
+        const uint64_t dlo = key[i], dhi = (uint64_t)st[i] | ((uint64_t)cn[i] << 32);
+        asm volatile(
+            "{\n\t.reg .b128 cmp, val, old;\n\t"
+            "mov.b128 cmp, {%3, %3};\n\t"
+            "mov.b128 val, {%4, %5};\n\t"
+            "atom.relaxed.gpu.global.cas.b128 old, [%2], cmp, val;\n\t"
+            "mov.b128 {%0, %1}, old;\n\t}"
+            : "=l"(olo[i]), "=l"(ohi[i]) : "l"(sl), "l"((uint64_t)0), "l"(dlo), "l"(dhi) : "memory");
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      if ((pend >> i) & 1u) {
+        if (olo[i] == 0 && ohi[i] == 0) pend &= ~(1u << i);          // the slot was empty: it is ours now
+        else if ((slot >> i) & 1u) { slot &= ~(1u << i); cur[i] = kh.next(cur[i]); }
+        else slot |= 1u << i;
+      }
+    }
+  }
+}
+
 // Table of a grouped index, written front to back (no memset, no atomics): the k-mers come in ascending home-bucket order,
 // so the first k-mer of a bucket (its leader) writes the whole 32-byte bucket -- itself, the next k-mer if it shares the
 // bucket, else an empty slot -- and zero-fills the empty buckets before it.  A bucket's third and later k-mers (~10 % at
