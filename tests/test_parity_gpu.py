@@ -177,6 +177,34 @@ def test_handles_coexist_and_free(kh, oracle):
         kh.kmer_pos(hs[2], 2, canonical=True)
 
 
+def test_pair_count_is_taken_on_demand(kh, oracle):
+    """P (rows of pair.pos), the number of k-mers with pairs and the longest list are not part of the build: kmg_sizes with
+    P = NULL never sweeps the index, the first request for P does (once), and the answer is the reference's."""
+    import ctypes as C
+    from kmer_hasher_b200 import _lib
+    L = _lib.load()
+    s = random_dna(60000, 77, p_n=0.002)
+    s[1000:1400] = ord("T")                                # a k-mer with a few hundred positions
+    for k, do_sort in ((12, False), (32, False), (21, True)):
+        ix = kh.make_kmer_hash(s, k, do_sort=do_sort)
+        o = oracle.build(s, k)
+        kh.profile(enable=True, reset=True)
+        assert ix.sizes_un == (o.U, o.N)
+        got = kh.kmer_pos(ix, 2 | 8, canonical=True)       # neither asks for P
+        assert "stats" not in kh.profile(reset=True)
+        assert np.array_equal(got["count"], o.extract(8)["count"])
+        assert ix.sizes == (o.U, o.N, o.P)                  # the sweep runs now ...
+        assert kh.profile(reset=True)["stats"][1] == 1
+        assert ix.sizes == (o.U, o.N, o.P)                  # ... and only once
+        assert "stats" not in kh.profile(enable=False)
+        kh.profile(reset=True)
+        U, N, P = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.check(L.kmg_sizes(ix._handle(), None, None, C.byref(P)))
+        assert P.value == o.P
+        assert np.array_equal(kh.kmer_pos(ix, 4, canonical=True)["pair.pos"].ravel(), o.extract(4)["pair_pos"])
+        ix.free()
+
+
 def test_pinned_and_device_buffers(kh, oracle):
     import torch
     s = random_dna(100000, 9, p_n=0.001)
