@@ -164,6 +164,7 @@ struct PassSmem {
   uint32_t tile;
   uint32_t seg_tp[MAX_SEGS + 1];                         // segmented record source only: TileSegs::tile_prefix
   uint32_t skip_write;                                   // region output: a bin outgrew its region, drop this tile's records
+  alignas(8) uint64_t bar[WARPS];                        // record source: one mbarrier per warp for the bulk copy of its keys
   uint32_t bstart[MAX_PEERS], bcnt[MAX_PEERS];           // PEER mode only: first tile slot and size of every owner's run
   PeerTable peer;                                        // PEER mode only
   TileCodes<FROM_SEQ ? TILE : 16> tc;
@@ -254,6 +255,30 @@ __device__ __forceinline__ void st_status(uint64_t *p, const uint64_t (&w)[BPT])
   }
 }
 
+// ---- bulk copy (TMA, 1-D) of a warp's keys into shared memory ---------------------------------------------------
+// A warp's ITEMS x 32 keys are one contiguous, 16-byte aligned piece of the record array: lane 0 arms the warp's mbarrier
+// with the byte count and issues ONE cp.async.bulk; the copy engine moves the data without occupying registers, load/store
+// slots or L1 lines while it is in flight.  The lanes then read their keys out of shared memory.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load_arm(uint64_t *bar, void *dst, const void *src, uint32_t bytes) {
+  const uint32_t b = smem_addr(bar), d = smem_addr(dst);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the initialised barrier is visible to the copy engine
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_load_wait(uint64_t *bar) {
+  const uint32_t b = smem_addr(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "KMG_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@p bra KMG_DONE;\n\t"
+      "bra KMG_WAIT;\n\t"
+      "KMG_DONE:\n\t}" ::"r"(b) : "memory");
+}
+
 // One tile.  FULL: every slot of the tile holds a valid record (no predicates on the hot path).
 template <class Cfg, bool FROM_SEQ, bool FULL, class BinFn, class NextFn, bool HAS_NEXT, bool PEER>
 __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, PassSmem<Cfg, FROM_SEQ> &sm,
@@ -283,6 +308,19 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     }
   } else {
     const uint64_t *ksrc = P.keys_in + q0 + t0;             // q0, n_in: physical indices (inside one segment of a segmented source)
+    bool bulk = false;
+    // (a segmented source's tiles start at segment base + k x TILE: the base, and so the address, may be only 8-byte aligned)
+    if constexpr (FULL && !PEER) bulk = !(P.dbg & 8u) && (((uintptr_t)(P.keys_in + q0) & 15u) == 0);   // dbg 8 (tuning runs): register loads
+    if (bulk) {
+      if constexpr (FULL && !PEER) {
+        uint64_t *stage = sm.keys + warp * (32 * ITEMS);
+        if (lane == 0) bulk_load_arm(&sm.bar[warp], stage, P.keys_in + q0 + warp * (32 * ITEMS), 32 * ITEMS * 8);
+        __syncwarp();
+        bulk_load_wait(&sm.bar[warp]);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) key[i] = stage[i * 32 + lane];
+      }
+    } else
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if constexpr (FULL) key[i] = ld_stream_u64(ksrc + i * 32);

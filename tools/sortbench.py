@@ -15,6 +15,8 @@ k = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 specs = sys.argv[3].split(",") if len(sys.argv) > 3 else ["3:0:8:32", "3:0:8:40", "3:0:9:36", "3:0:10:40", "3:1:8:32", "3:1:9:36", "3:2:8:32", "0:0:8:32", "0:0:9:36"]
 wl = sys.argv[4] if len(sys.argv) > 4 else "c2"
 lib = _lib.load()
+if os.environ.get("KMG_SORT_DBG"):                          # 4: generic scatter write-out, 8: register loads instead of the bulk copy
+    _lib.check(lib.kmg_tune(b"sort_dbg", int(os.environ["KMG_SORT_DBG"])))
 seq = torch.from_numpy(synth.config_c2(L) if wl == "c2" else synth.config_c3(L)).cuda()
 for spec in specs:
     parts = [int(x) for x in spec.split(":")]
