@@ -168,7 +168,14 @@ class CudaEngine:
         return rows
 
 
-_MARKS = None     # tuning runs: set to a list to collect (phase, cuda event, host time) marks of sharded_build_p2p
+_MARKS = None     # tuning runs: set to a list to collect (phase, cuda event, host time) marks of the sharded builds
+
+
+def _mark(name):
+    if _MARKS is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        _MARKS.append((name, e, time.perf_counter()))
 
 
 class PeerUnavailable(RuntimeError):
@@ -538,17 +545,21 @@ def sharded_build_ranges(own_bytes, L: int, k: int, engine, xchg, group=None) ->
     one-word all-reduce as the barrier, the owner build straight from the regions (kmg_build_regions), and one status
     all-reduce so that every rank takes the same path if any owner's region overflowed."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    _mark("start")
     own = own_bytes if isinstance(own_bytes, torch.Tensor) else engine.upload(np.asarray(own_bytes, np.uint8))
     pack = engine.shard_pack(own, k, 2, 0)                     # halo bytes (the two sample keys are not used)
     allpack = torch.empty(world * pack.numel(), dtype=torch.uint8, device=engine.device)
     dist.all_gather_into_tensor(allpack, pack, group=group)
+    _mark("halo")
     sh, _ = engine.shard_open_packed(own, L, world, rank, k, 2, allpack, 0, splitters=False)
     from ._lib import KmgError
     status, local = 0, None
     try:
         slot = xchg.next_slot()
         engine.shard_scatter_ranges(sh, world, rank, slot, xchg.region_cap, 0)
+        _mark("scatter")
         xchg.barrier()
+        _mark("barrier")
         try:
             local = engine.build_regions(slot, xchg.region_cap, world, k)
         except KmgError as e:
@@ -557,7 +568,9 @@ def sharded_build_ranges(own_bytes, L: int, k: int, engine, xchg, group=None) ->
             status = -e.code
     finally:
         engine.shard_close(sh)
+    _mark("built")
     worst, U_all, N_all = xchg.agree(status, local.sizes_un if local is not None else (0, 0))
+    _mark("agreed")
     if worst:
         if local is not None:
             local.free()
@@ -758,7 +771,9 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     def step_device():
         ix = build(own_dev)
         ix.kmer_pos(2 | 8, out={"pos": pos_dev, "count": cnt_dev})      # this owner's slice, global k-mer numbers
+        _mark("kmer.pos")
         ix.free()
+        _mark("freed")
 
     def step_e2e():
         ix = build(own_host.to(dev, non_blocking=True))
@@ -787,6 +802,23 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
     launches = kh.launch_count() - l0
     prof = kh.profile(enable=False)
     kh.profile(reset=True)
+    # where a step's time goes on rank 0 (device time between marks, host time to enqueue): three more steps, untimed
+    global _MARKS
+    phases = None
+    if use_ranges:
+        _MARKS = []
+        acc = {}
+        for _ in range(3):
+            del _MARKS[:]
+            barrier()
+            step_device()
+            torch.cuda.synchronize()
+            for (n0, e0, h0), (n1, e1, h1) in zip(_MARKS[:-1], _MARKS[1:]):
+                a = acc.setdefault(n1, [0.0, 0.0])
+                a[0] += e0.elapsed_time(e1) / 3
+                a[1] += 1e3 * (h1 - h0) / 3
+        _MARKS = None
+        phases = {n: {"gpu_ms": round(v[0], 4), "host_ms": round(v[1], 4)} for n, v in acc.items()}
     for _ in range(warm):
         step_e2e()
     ms_e2e = timed(step_e2e, steps)
@@ -845,7 +877,7 @@ def bench_sharded(args, w, k, L, steps, warm, hbm_peak, peak_src, barrier):
                                     f"{world} shards of {L} bases each of one {Ltot}-base sequence") + "; (key,pos) records " + path,
                        "bases_total": Ltot, "kmers": int(ntot), "per_rank_kmers": all_sizes[:, 0].tolist(),
                        "per_rank_distinct": all_sizes[:, 1].tolist(), "l2": "inputs_exceed_l2"},
-            "parity_checked": parity, "host_placement": numa,
+            "parity_checked": parity, "host_placement": numa, "phases_rank0": phases,
             "e2e": {"value": ntot / (ms_e2e * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": int(Ltot),
                     "d2h_bytes_per_step": int((8 * all_sizes[:, 0] + 4 * all_sizes[:, 1]).sum()), "ms_per_step": ms_e2e,
                     "what": "per rank: pinned host shard -> device, sharded build, kmer_pos(2|8) of the owner's slice into pinned host arrays"},
