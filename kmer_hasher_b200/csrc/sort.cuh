@@ -6,7 +6,8 @@
 // the reference, README "positions are sorted").
 //
 // One kernel does a whole pass:
-//   - records come either from HBM arrays or straight from the ASCII sequence (the 2-bit encoder
+//   - records come either from HBM arrays (a warp's keys by one 1-D bulk copy -- cp.async.bulk + mbarrier -- into the
+//     shared-memory array that later holds the regrouped tile) or straight from the ASCII sequence (the 2-bit encoder
 //     of windows.cuh is fused into the first pass: keys are never written unsorted, and windows
 //     that contain an N are dropped by simply not being ranked);
 //   - the rank of a record inside the tile comes from one shared-memory atomic per record on its warp's
@@ -19,7 +20,8 @@
 // build (digits of mix64(key)) and for builds from records (sharded build) the histogram of the NEXT
 // pass's digit is taken while the regrouped keys stream out (HAS_NEXT).
 // The same kernel with OwnerBin (key-range owner instead of digit) is the multi-GPU partitioner; with PEER
-// it writes every record straight into its owner's arrays over NVLink.
+// it writes every record straight into its owner's arrays over NVLink, owner by owner in 32-record-aligned blocks
+// (whole 128-byte lines per remote store instruction).
 #pragma once
 #include "common.cuh"
 #include "lookback.cuh"
