@@ -269,7 +269,7 @@ int kmg_selftest_lane_order(uint32_t *failures); /* precondition of the one-atom
 int kmg_tune(const char *key, int value); /* tests and tuning runs: "sort_cfg" (rank variant: -1 auto, 0 bitmap, 3 one
                                             atomic, 4 unstable on purpose), "sort_shape" (-1 auto, 0..2), "hash_bits" (0 = from the
                                             record count), "hash_rb", "fix_cap", "reset_rank", "sort_dbg" (bit 2: generic write-out of
-                                            the NVLink scatter, bit 3: register loads instead of the bulk copy), "sort_trace" */
+                                            the NVLink scatter, bit 3 / bit 4: keys / positions by register loads instead of the bulk copy), "sort_trace" */
 int64_t kmg_tune_get(const char *key, int64_t arg); /* "rank_variant" in use on this device, "unstable_rebuilds" so far,
                                             "hash_bits" / "hash_rb" the grouped build picks for `arg` records */
 int kmg_trim(void);                      /* return the library's cached (free) device blocks of this device to the driver */

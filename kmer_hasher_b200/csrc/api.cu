@@ -629,8 +629,10 @@ extern "C" int kmg_selftest_lane_order(uint32_t *failures) {
   if (!failures) return fail(KMG_ERR_ARG, "failures is NULL");
   return lane_order_failures(failures);
 }
-// Two tiles of the default record pass must fit the 196 KB shared-memory carve-out (1 KB per block is reserved): one step
-// further (228 KB) leaves 28 KB of L1 for the loads in flight and costs every pass 8 % (measured: profiles/r02_notes.md).
+// Two tiles of the default record pass fit the 196 KB shared-memory carve-out (1 KB per block is reserved).  With register
+// loads, one step further (228 KB) left 28 KB of L1 for the loads in flight and cost every pass 8 % (profiles/r02_notes.md);
+// since keys and positions arrive by bulk copy (no L1 lines) a 30-record tile at 228 KB runs as fast as this one -- and no
+// faster (profiles/r02_sortbench_30.log), so the tile stays where register loads (partial tiles, dbg runs) are safe too.
 static_assert(2 * (sizeof(PassSmem<PassCfg<256, 28, 2, 3, 4, 8>, false>) + 1024) <= 196 * 1024, "the record pass's tile outgrew the 196 KB carve-out");
 constexpr int REGION_SAMPLE_STRIDE = 251;   // prime: tandem arrays are sampled in all their phases
 constexpr int SORT_TILE_MIN = 4096;   // status sizing: smallest tile of any shape

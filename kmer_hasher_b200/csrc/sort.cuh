@@ -167,6 +167,7 @@ struct PassSmem {
   uint32_t seg_tp[MAX_SEGS + 1];                         // segmented record source only: TileSegs::tile_prefix
   uint32_t skip_write;                                   // region output: a bin outgrew its region, drop this tile's records
   alignas(8) uint64_t bar[WARPS];                        // record source: one mbarrier per warp for the bulk copy of its keys
+  alignas(8) uint64_t bar2[WARPS];                       //   and one for its positions
   uint32_t bstart[MAX_PEERS], bcnt[MAX_PEERS];           // PEER mode only: first tile slot and size of every owner's run
   PeerTable peer;                                        // PEER mode only
   TileCodes<FROM_SEQ ? TILE : 16> tc;
@@ -299,6 +300,7 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
   //      warp's chunk), which is memory order => the ranks below are stable
   uint64_t key[ITEMS];
   uint32_t valid = FULL ? 0xFFFFFFFFu : 0u;
+  bool bulk_pos = false;                                 // record source: the positions come by bulk copy too
   if constexpr (FROM_SEQ) {
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -313,10 +315,15 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
     bool bulk = false;
     // (a segmented source's tiles start at segment base + k x TILE: the base, and so the address, may be only 8-byte aligned)
     if constexpr (FULL && !PEER) bulk = !(P.dbg & 8u) && (((uintptr_t)(P.keys_in + q0) & 15u) == 0);   // dbg 8 (tuning runs): register loads
+    if constexpr (FULL && !PEER) bulk_pos = bulk && !(P.dbg & 16u) && (((uintptr_t)(P.pos_in + q0) & 15u) == 0);   // dbg 16: positions by register loads
     if (bulk) {
       if constexpr (FULL && !PEER) {
         uint64_t *stage = sm.keys + warp * (32 * ITEMS);
-        if (lane == 0) bulk_load_arm(&sm.bar[warp], stage, P.keys_in + q0 + warp * (32 * ITEMS), 32 * ITEMS * 8);
+        if (lane == 0) {
+          bulk_load_arm(&sm.bar[warp], stage, P.keys_in + q0 + warp * (32 * ITEMS), 32 * ITEMS * 8);
+          if constexpr (!FROM_SEQ)                         // the positions travel meanwhile; they are needed after the ranking
+            if (bulk_pos) bulk_load_arm(&sm.bar2[warp], sm.pos + warp * (32 * ITEMS), P.pos_in + q0 + warp * (32 * ITEMS), 32 * ITEMS * 4);
+        }
         __syncwarp();
         bulk_load_wait(&sm.bar[warp]);
 #pragma unroll
@@ -447,6 +454,12 @@ __device__ __forceinline__ void pass_tile(const PassParams<BinFn, NextFn> &P, Pa
       if (FULL || ((valid >> i) & 1u)) sm.pos[rk[i]] = (uint16_t)(t0 + i * 32);
   } else {
     uint32_t val[ITEMS];
+    if (bulk_pos) {                                        // (block-uniform) staged linearly in sm.pos, the array they are regrouped in:
+      bulk_load_wait(&sm.bar2[warp]);                      //   every thread reads its own first, then a barrier, then the scatter
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) val[i] = sm.pos[t0 + i * 32];
+      __syncthreads();
+    } else
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       val[i] = (FULL || ((valid >> i) & 1u)) ? ld_stream_u32(P.pos_in + q0 + t0 + i * 32) : 0;
