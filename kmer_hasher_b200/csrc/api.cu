@@ -324,6 +324,7 @@ static void dfree(T *&p, cudaStream_t s) {
 // memory is staged by the driver in small pieces at a fraction of the link rate, so large transfers go through three
 // pinned slots instead: the DMA fills (drains) one slot while a few host threads memcpy another to (from) the caller's
 // buffer.  Worker threads touch caller memory only between entry and return of the library call that started them.
+extern "C" void kmg_host_copy(void *dst, const void *src, size_t n);   // hostcopy.c: non-temporal stores for large pieces
 class CopyPool {
   struct Task { char *dst; const char *src; size_t n; int group; };
   std::mutex mu;
@@ -342,7 +343,7 @@ class CopyPool {
         t = q.front();
         q.pop_front();
       }
-      memcpy(t.dst, t.src, t.n);
+      kmg_host_copy(t.dst, t.src, t.n);
       {
         std::lock_guard<std::mutex> l(mu);
         if (--pending[t.group & 7] == 0) cv_done.notify_all();
