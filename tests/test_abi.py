@@ -70,3 +70,21 @@ def test_canonical_renumbering_is_a_stable_regrouping():
     pairs = np.array([[1, 7, 9], [3, 1, 4], [3, 1, 8], [3, 4, 8]], np.int32)
     assert kh._renumber(pairs, rank).tolist() == [[2, 1, 4], [2, 1, 8], [2, 4, 8], [3, 7, 9]]
     assert kh._renumber(np.empty((0, 2), np.int32), rank).shape == (0, 2)
+
+
+def test_host_copy_of_the_staging_path():
+    """kmg_host_copy (csrc/hostcopy.c): non-temporal stores above 1 MB, memcpy below; any alignment of either side."""
+    import ctypes as C
+    import numpy as np
+    from kmer_hasher_b200 import _lib
+    raw = C.CDLL(_lib.LIB_PATH)
+    raw.kmg_host_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    raw.kmg_host_copy.restype = None
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, 5_000_000, dtype=np.uint8)
+    for n, so, do in [(0, 0, 0), (1, 3, 5), (4096, 1, 0), ((1 << 20) - 1, 7, 9), (1 << 20, 0, 0), ((1 << 20) + 1, 1, 31), (3_000_017, 13, 1),
+                      (4_194_304, 0, 33)]:
+        dst = np.full(n + 128, 0xEE, np.uint8)
+        raw.kmg_host_copy(dst.ctypes.data + do, src.ctypes.data + so, n)
+        assert np.array_equal(dst[do:do + n], src[so:so + n])
+        assert (dst[:do] == 0xEE).all() and (dst[do + n:] == 0xEE).all()      # nothing written outside
